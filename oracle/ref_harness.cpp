@@ -17,6 +17,8 @@
 //   * DielectricMaterial::scatter leaves Ray::m_time uninitialised (DielectricMaterial.cpp:82,
 //     Ray.cpp:6-7).  Dielectrics are wrapped in TimeFixMaterial, which calls the reference scatter and
 //     then re-attaches the incoming ray's time (what the reference's CUDA path does, Material.cuh:139).
+//   * Sphere::pdf_value has the same uninitialised-time read (Sphere.cpp:149); sphere light proxies use
+//     FixedTimeSphereLight below (same formula, probe time 0).
 //   * The reference's flattened BVH is undefined behaviour above 1000 nodes (BVHNode.cpp:327,339-360),
 //     so for more than 400 objects the tree is assembled from reference BVHNode(left,right) nodes by
 //     median split (BVHNode.hpp:92-100); traversal, AABB::hit and primitive tests stay reference code.
@@ -120,6 +122,26 @@ public:
 
 private:
   MaterialPtr m_inner;
+};
+
+// Sphere::pdf_value builds its probe ray with the 2-argument Ray constructor, which leaves m_time
+// uninitialised (Sphere.cpp:149, Ray.cpp:6-7); the value it then reads is whatever the stack held, so
+// the reference's own renders differ between code paths (list vs BVH world) whenever that garbage is
+// a NaN.  Sphere light proxies therefore use this subclass: the reference formula (Sphere.cpp:145-157)
+// with the probe ray's time pinned to 0 (light proxies are static, so any finite time is equivalent).
+class FixedTimeSphereLight : public Sphere {
+public:
+  using Sphere::Sphere;
+  double pdf_value(const Point3 &origin, const Vec3 &direction) const override {
+    HitRecord record;
+    if (!this->hit(Ray(origin, direction, 0.0), Interval(0.001, INF), record))
+      return 0;
+    double radius = get_radius();
+    double dist_squared = (get_center().at(0) - origin).length_squared();
+    double cos_theta_max = std::sqrt(1 - radius * radius / dist_squared);
+    double solid_angle = 2 * PI * (1 - cos_theta_max);
+    return 1 / solid_angle;
+  }
 };
 
 void set3(double *dst, const Vec3 &v) {
@@ -384,7 +406,7 @@ struct RefScene {
     set3(l.a, c);
     l.radius = r;
     light_recs.push_back(l);
-    lights.add(std::make_shared<Sphere>(c, r, MaterialPtr()));
+    lights.add(std::make_shared<FixedTimeSphereLight>(c, r, MaterialPtr()));
   }
 
   void finalize() {

@@ -74,6 +74,11 @@ typedef struct ora_counters {
 double ora_render(ora_scene *s, const rt_camera_config *cfg, int rng_kind, int sampler, uint64_t seed,
                   int use_bvh, int row0, int row1, int single_stratum, double *out, ora_counters *counters);
 
+/* Log every segment the integrator traces during ora_render / ora_trace into buf (up to cap rays);
+ * pass NULL to stop.  Gives tests realistic secondary-ray sets. */
+void ora_ray_log(rt_ray *buf, int64_t cap);
+int64_t ora_ray_log_count(void);
+
 /* to_byte (ColorUtility.hpp:18-23). */
 int ora_to_byte(double v);
 

@@ -1,0 +1,580 @@
+// rt_api.cu — the C ABI of librt_b200.so (include/rt_b200.h): contexts, scenes, films and the host
+// side of the wavefront render loop.  There is no CPU fallback anywhere in this library: without a
+// CUDA device every entry point that needs one returns RT_ERR_NO_DEVICE.
+#include "rt_internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+
+static thread_local std::string g_last_error;
+
+void rt_set_error(const std::string &msg) { g_last_error = msg; }
+
+int rt_cuda_fail(cudaError_t e, const char *what) {
+  g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+  return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? RT_ERR_NO_DEVICE : RT_ERR_CUDA;
+}
+
+namespace {
+
+int invalid(const char *msg) {
+  rt_set_error(msg);
+  return RT_ERR_INVALID;
+}
+
+// Grow the per-context wavefront storage.
+int ensure_wave(rt_context *ctx, size_t n_paths, size_t n_counts) {
+  WaveBuffers &w = ctx->wave;
+  if (n_paths > w.capacity_paths) {
+    RT_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < 2; k++) {
+      cudaFree(w.ray_a[k]);
+      cudaFree(w.ray_b[k]);
+      cudaFree(w.hit[k]);
+      w.ray_a[k] = w.ray_b[k] = nullptr;
+      w.hit[k] = nullptr;
+    }
+    cudaFree(w.throughput);
+    cudaFree(w.radiance);
+    w.throughput = w.radiance = nullptr;
+    w.capacity_paths = 0;
+    for (int k = 0; k < 2; k++) {
+      RT_CUDA(cudaMalloc((void **)&w.ray_a[k], n_paths * sizeof(float4)));
+      RT_CUDA(cudaMalloc((void **)&w.ray_b[k], n_paths * sizeof(float4)));
+      RT_CUDA(cudaMalloc((void **)&w.hit[k], n_paths * sizeof(float2)));
+    }
+    RT_CUDA(cudaMalloc((void **)&w.throughput, n_paths * sizeof(float4)));
+    RT_CUDA(cudaMalloc((void **)&w.radiance, n_paths * sizeof(float4)));
+    w.capacity_paths = n_paths;
+  }
+  if (n_counts > w.capacity_counts) {
+    RT_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(w.counts);
+    w.counts = nullptr;
+    RT_CUDA(cudaMalloc((void **)&w.counts, n_counts * sizeof(unsigned int)));
+    w.capacity_counts = n_counts;
+  }
+  if (!w.stats) {
+    RT_CUDA(cudaMalloc((void **)&w.stats, 4 * sizeof(unsigned long long)));
+    RT_CUDA(cudaMemsetAsync(w.stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+  }
+  return RT_OK;
+}
+
+DCamera to_device_camera(const rt_camera *c) {
+  DCamera d{};
+  for (int a = 0; a < 3; a++) {
+    d.center[a] = (float)c->center[a];
+    d.p00c[a] = (float)(c->pixel00_loc[a] - c->center[a]);
+    d.du[a] = (float)c->pixel_delta_u[a];
+    d.dv[a] = (float)c->pixel_delta_v[a];
+    d.disk_u[a] = (float)c->defocus_disk_u[a];
+    d.disk_v[a] = (float)c->defocus_disk_v[a];
+  }
+  d.defocus = c->defocus_angle > 0;
+  d.width = c->image_width;
+  d.height = c->image_height;
+  return d;
+}
+
+// One wavefront pass over `n_samples` strata starting at linear stratum `first_sample`.
+int render_pass(rt_scene *scene, const rt_camera *camera, rt_film *film, int first_sample, int n_samples,
+                int sqrt_spp, int max_depth, uint64_t seed) {
+  rt_context *ctx = scene->ctx;
+  PassParams pp{};
+  pp.cam = to_device_camera(camera);
+  pp.map = film->map;
+  pp.n_owned = (int)film->n_owned;
+  pp.n_paths = (int)(film->n_owned * n_samples);
+  pp.first_sample = first_sample;
+  pp.n_samples = n_samples;
+  pp.sqrt_spp = sqrt_spp;
+  pp.recip_sqrt_spp = (float)(1.0 / sqrt_spp);
+  pp.max_depth = max_depth;
+  pp.seed = seed;
+  if (pp.n_paths == 0)
+    return RT_OK;
+  int st = ensure_wave(ctx, (size_t)pp.n_paths, (size_t)max_depth + 2);
+  if (st != RT_OK)
+    return st;
+  DScene sc = scene->d;
+  for (int a = 0; a < 3; a++)
+    sc.bg[a] = (float)camera->background[a];
+  WaveBuffers &w = ctx->wave;
+  RT_CUDA(cudaMemsetAsync(w.counts, 0, ((size_t)max_depth + 2) * sizeof(unsigned int), ctx->stream));
+  launch_generate(ctx, pp, w);
+  for (int bounce = 0; bounce < max_depth; bounce++) {
+    launch_extend(ctx, sc, pp, w, bounce);
+    launch_shade(ctx, sc, pp, w, bounce);
+  }
+  launch_accumulate(ctx, pp, w, film->accum);
+  ctx->counters.kernel_launches += 2 + 2 * (uint64_t)max_depth;
+  ctx->counters.paths += (uint64_t)pp.n_paths;
+  RT_CUDA(cudaGetLastError());
+  return RT_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int rt_abi_version(void) { return RT_B200_ABI_VERSION; }
+
+const char *rt_last_error(void) { return g_last_error.c_str(); }
+
+int rt_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+// Camera::initialize (core/camera/Camera.cpp:31-73), same FP64 operation order.
+int rt_camera_init(const rt_camera_config *cfg, rt_camera *out) {
+  if (!cfg || !out)
+    return invalid("rt_camera_init: null argument");
+  if (cfg->image_width < 1 || !(cfg->aspect_ratio > 0) || cfg->samples_per_pixel < 1)
+    return invalid("rt_camera_init: image_width, aspect_ratio and samples_per_pixel must be positive");
+  const double pi = 3.1415926535897932385;
+  struct V {
+    double x, y, z;
+  };
+  auto sub = [](V a, V b) { return V{a.x - b.x, a.y - b.y, a.z - b.z}; };
+  auto add = [](V a, V b) { return V{a.x + b.x, a.y + b.y, a.z + b.z}; };
+  auto scale = [](double t, V a) { return V{t * a.x, t * a.y, t * a.z}; };
+  auto divide = [&](V a, double t) { return scale(1 / t, a); };
+  auto cross = [](V a, V b) { return V{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; };
+  auto unit = [&](V a) {
+    double len = std::sqrt(a.x * a.x + a.y * a.y + a.z * a.z);
+    if (len > 1e-8) {
+      double s = 1.0 / len;
+      return V{a.x * s, a.y * s, a.z * s};
+    }
+    return V{1.0, 0.0, 0.0};
+  };
+  auto load = [](const double *p) { return V{p[0], p[1], p[2]}; };
+  auto store = [](double *p, V a) {
+    p[0] = a.x;
+    p[1] = a.y;
+    p[2] = a.z;
+  };
+  int W = cfg->image_width;
+  int H = int(W / cfg->aspect_ratio);
+  H = (H < 1) ? 1 : H;
+  V center = load(cfg->lookfrom);
+  double theta = cfg->vfov * pi / 180.0;
+  double h = std::tan(theta / 2);
+  double viewport_height = 2 * h * cfg->focus_dist;
+  double viewport_width = viewport_height * (double(W) / H);
+  V w = unit(sub(load(cfg->lookfrom), load(cfg->lookat)));
+  V u = unit(cross(load(cfg->vup), w));
+  V v = cross(w, u);
+  V viewport_u = scale(viewport_width, u);
+  V viewport_v = scale(viewport_height, V{-v.x, -v.y, -v.z});
+  V du = divide(viewport_u, W);
+  V dv = divide(viewport_v, H);
+  V upper_left = sub(sub(sub(center, scale(cfg->focus_dist, w)), divide(viewport_u, 2)), divide(viewport_v, 2));
+  V p00 = add(upper_left, scale(0.5, add(du, dv)));
+  double defocus_radius = cfg->focus_dist * std::tan((cfg->defocus_angle / 2) * pi / 180.0);
+  std::memset(out, 0, sizeof *out);
+  out->image_width = W;
+  out->image_height = H;
+  store(out->center, center);
+  store(out->pixel00_loc, p00);
+  store(out->pixel_delta_u, du);
+  store(out->pixel_delta_v, dv);
+  store(out->defocus_disk_u, scale(defocus_radius, u));
+  store(out->defocus_disk_v, scale(defocus_radius, v));
+  out->defocus_angle = cfg->defocus_angle;
+  std::memcpy(out->background, cfg->background, sizeof out->background);
+  return RT_OK;
+}
+
+int rt_context_create(int device, rt_context **out) {
+  if (!out)
+    return invalid("rt_context_create: null output");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    rt_set_error("no CUDA device available; this backend has no CPU fallback");
+    return RT_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= n)
+    return invalid("rt_context_create: device index out of range");
+  RT_CUDA(cudaSetDevice(device));
+  rt_context *ctx = new (std::nothrow) rt_context();
+  if (!ctx)
+    return invalid("out of host memory");
+  ctx->device = device;
+  cudaDeviceProp prop;
+  RT_CUDA(cudaGetDeviceProperties(&prop, device));
+  ctx->sm_count = prop.multiProcessorCount;
+  RT_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  *out = ctx;
+  return RT_OK;
+}
+
+void rt_context_destroy(rt_context *ctx) {
+  if (!ctx)
+    return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  WaveBuffers &w = ctx->wave;
+  for (int k = 0; k < 2; k++) {
+    cudaFree(w.ray_a[k]);
+    cudaFree(w.ray_b[k]);
+    cudaFree(w.hit[k]);
+  }
+  cudaFree(w.throughput);
+  cudaFree(w.radiance);
+  cudaFree(w.counts);
+  cudaFree(w.stats);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int rt_context_synchronize(rt_context *ctx) {
+  if (!ctx)
+    return invalid("null context");
+  RT_CUDA(cudaSetDevice(ctx->device));
+  RT_CUDA(cudaStreamSynchronize(ctx->stream));
+  return RT_OK;
+}
+
+uint64_t rt_context_stream(rt_context *ctx) { return ctx ? (uint64_t)(uintptr_t)ctx->stream : 0; }
+
+int rt_scene_create(rt_context *ctx, const rt_scene_desc *desc, rt_scene **out) {
+  if (!ctx || !desc || !out)
+    return invalid("rt_scene_create: null argument");
+  *out = nullptr;
+  RT_CUDA(cudaSetDevice(ctx->device));
+  rt_scene *sc = new (std::nothrow) rt_scene();
+  if (!sc)
+    return invalid("out of host memory");
+  int st = rt_scene_build(ctx, desc, sc);
+  if (st != RT_OK) {
+    rt_scene_release(sc);
+    delete sc;
+    return st;
+  }
+  *out = sc;
+  return RT_OK;
+}
+
+void rt_scene_destroy(rt_scene *scene) {
+  if (!scene)
+    return;
+  cudaSetDevice(scene->ctx->device);
+  cudaStreamSynchronize(scene->ctx->stream);
+  rt_scene_release(scene);
+  delete scene;
+}
+
+int rt_scene_get_info(rt_scene *scene, rt_scene_info *out) {
+  if (!scene || !out)
+    return invalid("rt_scene_get_info: null argument");
+  *out = scene->info;
+  return RT_OK;
+}
+
+int rt_trace_rays(rt_scene *scene, const rt_ray *rays, int64_t n, int mode, uint64_t seed, rt_hit *hits) {
+  if (!scene || (n > 0 && (!rays || !hits)) || n < 0)
+    return invalid("rt_trace_rays: bad argument");
+  if (mode != RT_TRACE_EXACT_F64 && mode != RT_TRACE_FAST_F32)
+    return invalid("rt_trace_rays: unknown mode");
+  if (n == 0)
+    return RT_OK;
+  rt_context *ctx = scene->ctx;
+  RT_CUDA(cudaSetDevice(ctx->device));
+  rt_ray *d_rays = nullptr;
+  rt_hit *d_hits = nullptr;
+  RT_CUDA(cudaMalloc((void **)&d_rays, (size_t)n * sizeof(rt_ray)));
+  cudaError_t e = cudaMalloc((void **)&d_hits, (size_t)n * sizeof(rt_hit));
+  if (e != cudaSuccess) {
+    cudaFree(d_rays);
+    return rt_cuda_fail(e, "cudaMalloc (hits)");
+  }
+  int st = RT_OK;
+  e = cudaMemcpyAsync(d_rays, rays, (size_t)n * sizeof(rt_ray), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) {
+    if (mode == RT_TRACE_EXACT_F64)
+      launch_trace_exact(ctx->stream, scene->ex, d_rays, n, seed, d_hits);
+    else
+      launch_trace_fast(ctx, scene->d, d_rays, n, seed, scene->leaf_object, scene->leaf_id, d_hits);
+    ctx->counters.kernel_launches += 1;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(hits, d_hits, (size_t)n * sizeof(rt_hit), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess)
+    e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess)
+    st = rt_cuda_fail(e, "rt_trace_rays");
+  cudaFree(d_rays);
+  cudaFree(d_hits);
+  return st;
+}
+
+int64_t rt_film_owned_pixels_for(int width, int height, int rank, int n_ranks, int tile_rows) {
+  if (width < 1 || height < 1 || n_ranks < 1 || rank < 0 || rank >= n_ranks || tile_rows < 1)
+    return -1;
+  return (int64_t)owned_rows(height, rank, n_ranks, tile_rows) * width;
+}
+
+int rt_film_create(rt_context *ctx, int width, int height, int rank, int n_ranks, int tile_rows, void *external_accum,
+                   rt_film **out) {
+  if (!ctx || !out)
+    return invalid("rt_film_create: null argument");
+  *out = nullptr;
+  int64_t owned = rt_film_owned_pixels_for(width, height, rank, n_ranks, tile_rows);
+  if (owned < 0)
+    return invalid("rt_film_create: bad geometry");
+  if ((int64_t)width * height > (int64_t)1 << 30)
+    return invalid("rt_film_create: image too large");
+  RT_CUDA(cudaSetDevice(ctx->device));
+  rt_film *f = new (std::nothrow) rt_film();
+  if (!f)
+    return invalid("out of host memory");
+  f->ctx = ctx;
+  f->map.width = width;
+  f->map.height = height;
+  f->map.rank = rank;
+  f->map.n_ranks = n_ranks;
+  f->map.tile_rows = tile_rows;
+  f->n_owned = owned;
+  if (external_accum) {
+    f->accum = (float4 *)external_accum;
+    f->owns_accum = false;
+  } else {
+    cudaError_t e = cudaMalloc((void **)&f->accum, std::max<int64_t>(owned, 1) * sizeof(float4));
+    if (e != cudaSuccess) {
+      delete f;
+      return rt_cuda_fail(e, "cudaMalloc (film)");
+    }
+    f->owns_accum = true;
+  }
+  *out = f;
+  return rt_film_clear(f);
+}
+
+void rt_film_destroy(rt_film *film) {
+  if (!film)
+    return;
+  cudaSetDevice(film->ctx->device);
+  cudaStreamSynchronize(film->ctx->stream);
+  if (film->owns_accum)
+    cudaFree(film->accum);
+  delete film;
+}
+
+int rt_film_clear(rt_film *film) {
+  if (!film)
+    return invalid("null film");
+  RT_CUDA(cudaSetDevice(film->ctx->device));
+  if (film->n_owned > 0)
+    RT_CUDA(cudaMemsetAsync(film->accum, 0, (size_t)film->n_owned * sizeof(float4), film->ctx->stream));
+  film->samples = 0;
+  return RT_OK;
+}
+
+int64_t rt_film_owned_pixels(const rt_film *film) { return film ? film->n_owned : -1; }
+uint64_t rt_film_device_ptr(rt_film *film) { return film ? (uint64_t)(uintptr_t)film->accum : 0; }
+int64_t rt_film_samples(const rt_film *film) { return film ? film->samples : -1; }
+
+static int check_render_args(rt_scene *scene, const rt_camera *camera, rt_film *film, int sqrt_spp, int max_depth) {
+  if (!scene || !camera || !film)
+    return invalid("render: null argument");
+  if (scene->ctx != film->ctx)
+    return invalid("render: scene and film belong to different contexts");
+  if (camera->image_width != film->map.width || camera->image_height != film->map.height)
+    return invalid("render: camera and film sizes differ");
+  if (sqrt_spp < 1 || max_depth < 1 || max_depth > 4096)
+    return invalid("render: sqrt_spp and max_depth must be positive");
+  return RT_OK;
+}
+
+int rt_render_accumulate(rt_scene *scene, const rt_camera *camera, rt_film *film, int s_i, int s_j, int sqrt_spp,
+                         int max_depth, uint64_t seed) {
+  int st = check_render_args(scene, camera, film, sqrt_spp, max_depth);
+  if (st != RT_OK)
+    return st;
+  if (s_i < 0 || s_i >= sqrt_spp || s_j < 0 || s_j >= sqrt_spp)
+    return invalid("rt_render_accumulate: stratum out of range");
+  RT_CUDA(cudaSetDevice(scene->ctx->device));
+  st = render_pass(scene, camera, film, s_j * sqrt_spp + s_i, 1, sqrt_spp, max_depth, seed);
+  if (st == RT_OK)
+    film->samples += 1;
+  return st;
+}
+
+int rt_render_static(rt_scene *scene, const rt_camera *camera, rt_film *film, int sqrt_spp, int max_depth,
+                     uint64_t seed) {
+  int st = check_render_args(scene, camera, film, sqrt_spp, max_depth);
+  if (st != RT_OK)
+    return st;
+  RT_CUDA(cudaSetDevice(scene->ctx->device));
+  if ((st = rt_film_clear(film)) != RT_OK)
+    return st;
+  const int total = sqrt_spp * sqrt_spp;
+  // enough paths per pass to fill the GPU several times over, bounded so the queues stay modest
+  const int64_t target_paths = (int64_t)4 << 20;
+  int per_pass = (int)std::max<int64_t>(1, std::min<int64_t>(total, target_paths / std::max<int64_t>(film->n_owned, 1)));
+  for (int first = 0; first < total; first += per_pass) {
+    int n = std::min(per_pass, total - first);
+    if ((st = render_pass(scene, camera, film, first, n, sqrt_spp, max_depth, seed)) != RT_OK)
+      return st;
+    film->samples += n;
+  }
+  return RT_OK;
+}
+
+int rt_film_read_rgb(rt_film *film, double scale, float *host_rgb) {
+  if (!film || !host_rgb)
+    return invalid("rt_film_read_rgb: null argument");
+  if (film->n_owned == 0)
+    return RT_OK;
+  rt_context *ctx = film->ctx;
+  RT_CUDA(cudaSetDevice(ctx->device));
+  float *d = nullptr;
+  RT_CUDA(cudaMalloc((void **)&d, (size_t)film->n_owned * 3 * sizeof(float)));
+  launch_resolve_rgb(ctx->stream, film->accum, film->n_owned, scale, d);
+  ctx->counters.kernel_launches += 1;
+  cudaError_t e = cudaMemcpyAsync(host_rgb, d, (size_t)film->n_owned * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess)
+    e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d);
+  if (e != cudaSuccess)
+    return rt_cuda_fail(e, "rt_film_read_rgb");
+  return RT_OK;
+}
+
+int rt_film_resolve_rgb8_device(rt_film *film, double scale, void *device_rgb8) {
+  if (!film || !device_rgb8)
+    return invalid("rt_film_resolve_rgb8_device: null argument");
+  RT_CUDA(cudaSetDevice(film->ctx->device));
+  launch_resolve_rgb8(film->ctx->stream, film->accum, film->n_owned, scale, (uint8_t *)device_rgb8);
+  film->ctx->counters.kernel_launches += 1;
+  RT_CUDA(cudaGetLastError());
+  return RT_OK;
+}
+
+int rt_film_resolve_rgb8(rt_film *film, double scale, uint8_t *host_rgb8) {
+  if (!film || !host_rgb8)
+    return invalid("rt_film_resolve_rgb8: null argument");
+  if (film->n_owned == 0)
+    return RT_OK;
+  rt_context *ctx = film->ctx;
+  RT_CUDA(cudaSetDevice(ctx->device));
+  uint8_t *d = nullptr;
+  RT_CUDA(cudaMalloc((void **)&d, (size_t)film->n_owned * 3));
+  int st = rt_film_resolve_rgb8_device(film, scale, d);
+  cudaError_t e = cudaSuccess;
+  if (st == RT_OK) {
+    e = cudaMemcpyAsync(host_rgb8, d, (size_t)film->n_owned * 3, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess)
+      e = cudaStreamSynchronize(ctx->stream);
+  }
+  cudaFree(d);
+  if (st != RT_OK)
+    return st;
+  if (e != cudaSuccess)
+    return rt_cuda_fail(e, "rt_film_resolve_rgb8");
+  return RT_OK;
+}
+
+int rt_film_scatter_gathered(rt_context *ctx, int width, int height, int n_ranks, int tile_rows,
+                             const void *device_gathered, void *device_full_image) {
+  if (!ctx || !device_gathered || !device_full_image || width < 1 || height < 1 || n_ranks < 1 || tile_rows < 1)
+    return invalid("rt_film_scatter_gathered: bad argument");
+  RT_CUDA(cudaSetDevice(ctx->device));
+  launch_scatter_gathered(ctx->stream, width, height, n_ranks, tile_rows, (const float4 *)device_gathered,
+                          (float4 *)device_full_image);
+  ctx->counters.kernel_launches += 1;
+  RT_CUDA(cudaGetLastError());
+  return RT_OK;
+}
+
+// Single-process multi-GPU gather: every rank's compact film is copied over NVLink (peer copy) into
+// one rank-major buffer on rank 0's device and scattered into the full image there.
+int rt_film_gather_p2p(rt_film **films, int n_ranks, double scale, float *host_rgb) {
+  if (!films || n_ranks < 1 || !host_rgb)
+    return invalid("rt_film_gather_p2p: bad argument");
+  for (int r = 0; r < n_ranks; r++) {
+    if (!films[r] || films[r]->map.rank != r || films[r]->map.n_ranks != n_ranks ||
+        films[r]->map.width != films[0]->map.width || films[r]->map.height != films[0]->map.height ||
+        films[r]->map.tile_rows != films[0]->map.tile_rows)
+      return invalid("rt_film_gather_p2p: films[r] must be rank r of n_ranks with one geometry");
+  }
+  rt_context *ctx0 = films[0]->ctx;
+  const int W = films[0]->map.width, H = films[0]->map.height;
+  const int64_t total = (int64_t)W * H;
+  for (int r = 0; r < n_ranks; r++) {
+    RT_CUDA(cudaSetDevice(films[r]->ctx->device));
+    RT_CUDA(cudaStreamSynchronize(films[r]->ctx->stream));
+  }
+  RT_CUDA(cudaSetDevice(ctx0->device));
+  float4 *gathered = nullptr, *full = nullptr;
+  RT_CUDA(cudaMalloc((void **)&gathered, (size_t)total * sizeof(float4)));
+  cudaError_t e = cudaMalloc((void **)&full, (size_t)total * sizeof(float4));
+  if (e != cudaSuccess) {
+    cudaFree(gathered);
+    return rt_cuda_fail(e, "cudaMalloc (gather)");
+  }
+  int64_t offset = 0;
+  for (int r = 0; r < n_ranks && e == cudaSuccess; r++) {
+    size_t bytes = (size_t)films[r]->n_owned * sizeof(float4);
+    if (bytes)
+      e = cudaMemcpyPeerAsync(gathered + offset, ctx0->device, films[r]->accum, films[r]->ctx->device, bytes,
+                              ctx0->stream);
+    offset += films[r]->n_owned;
+  }
+  int st = RT_OK;
+  if (e == cudaSuccess) {
+    launch_scatter_gathered(ctx0->stream, W, H, n_ranks, films[0]->map.tile_rows, gathered, full);
+    rt_film tmp;
+    tmp.ctx = ctx0;
+    tmp.accum = full;
+    tmp.n_owned = total;
+    st = rt_film_read_rgb(&tmp, scale, host_rgb);
+  } else {
+    st = rt_cuda_fail(e, "cudaMemcpyPeerAsync");
+  }
+  cudaStreamSynchronize(ctx0->stream);
+  cudaFree(gathered);
+  cudaFree(full);
+  return st;
+}
+
+int rt_get_counters(rt_context *ctx, rt_counters *out) {
+  if (!ctx || !out)
+    return invalid("rt_get_counters: null argument");
+  RT_CUDA(cudaSetDevice(ctx->device));
+  unsigned long long stats[4] = {0, 0, 0, 0};
+  if (ctx->wave.stats) {
+    RT_CUDA(cudaStreamSynchronize(ctx->stream));
+    RT_CUDA(cudaMemcpy(stats, ctx->wave.stats, sizeof stats, cudaMemcpyDeviceToHost));
+  }
+  *out = ctx->counters;
+  out->segments = stats[0];
+  out->nodes_visited = stats[1];
+  out->prim_tests = stats[2];
+  return RT_OK;
+}
+
+int rt_reset_counters(rt_context *ctx) {
+  if (!ctx)
+    return invalid("null context");
+  RT_CUDA(cudaSetDevice(ctx->device));
+  ctx->counters = rt_counters{};
+  if (ctx->wave.stats)
+    RT_CUDA(cudaMemsetAsync(ctx->wave.stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+  return RT_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,786 @@
+// rt_device.h — device-side data layout and per-thread functions of the B200 path tracer.
+//
+// Everything here is a plain inline function of one thread's data (RT_HD = __host__ __device__), so
+// the kernels in rt_kernels.cu stay thin and the same bodies can be compiled by a host compiler for
+// the unit tests in tests/emu (a TEST build; librt_b200.so contains device code only and has no CPU
+// path).  FP32 throughout, except the *_exact functions, which evaluate the reference's FP64
+// primitive tests in the reference's operation order without fused multiply-adds.
+//
+// Reference semantics mirrored (paths relative to the reference's src/):
+//   camera ray          core/camera/Camera.cpp:186-230, CameraKernels.cu:61-95
+//   sphere / quad hit   scene/objects/Sphere.cpp:101-143, Plane.cpp:78-112
+//   constant medium     scene/mediums/ConstantMedium.cpp:25-94
+//   slab test           optimization/AABB.cpp:141-164
+//   scatter / emit      scene/materials/*.cpp, utils/math/PDF.hpp, ONB.hpp, Vec3Utility.cuh:57-70
+//   textures            scene/textures/*.cpp, utils/math/PerlinNoise.hpp:43-79,186-201
+//   integrator step     core/camera/Camera.cpp:232-309, CameraKernels.cu:106-202
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#define RT_HD __host__ __device__ __forceinline__
+#else
+#define RT_HD inline
+struct float4 {
+  float x, y, z, w;
+};
+struct float2 {
+  float x, y;
+};
+struct int4 {
+  int x, y, z, w;
+};
+struct uint2 {
+  uint32_t x, y;
+};
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+#endif
+
+#define RT_PI_F 3.14159265358979323846f
+#define RT_INF_F (__builtin_huge_valf())
+#define RT_T_MIN 0.001f /* Camera.cpp:242 */
+
+// ---------------------------------------------------------------------------------------------------
+// bit casts
+// ---------------------------------------------------------------------------------------------------
+RT_HD int f2i(float f) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_int(f);
+#else
+  int i;
+  __builtin_memcpy(&i, &f, 4);
+  return i;
+#endif
+}
+RT_HD float i2f(int i) {
+#if defined(__CUDA_ARCH__)
+  return __int_as_float(i);
+#else
+  float f;
+  __builtin_memcpy(&f, &i, 4);
+  return f;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------------
+// float3 math
+// ---------------------------------------------------------------------------------------------------
+struct f3 {
+  float x, y, z;
+};
+RT_HD f3 F3(float x, float y, float z) {
+  f3 r;
+  r.x = x;
+  r.y = y;
+  r.z = z;
+  return r;
+}
+RT_HD f3 F3(float4 v) { return F3(v.x, v.y, v.z); }
+RT_HD f3 operator+(f3 a, f3 b) { return F3(a.x + b.x, a.y + b.y, a.z + b.z); }
+RT_HD f3 operator-(f3 a, f3 b) { return F3(a.x - b.x, a.y - b.y, a.z - b.z); }
+RT_HD f3 operator-(f3 a) { return F3(-a.x, -a.y, -a.z); }
+RT_HD f3 operator*(f3 a, f3 b) { return F3(a.x * b.x, a.y * b.y, a.z * b.z); }
+RT_HD f3 operator*(float t, f3 a) { return F3(t * a.x, t * a.y, t * a.z); }
+RT_HD f3 operator*(f3 a, float t) { return F3(t * a.x, t * a.y, t * a.z); }
+RT_HD float dot(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+RT_HD f3 cross(f3 a, f3 b) { return F3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+RT_HD float length(f3 a) { return sqrtf(dot(a, a)); }
+RT_HD f3 normalize(f3 a) { // Vec3::normalize (Vec3.hpp:141-149)
+  float len = length(a);
+  if (len > 1e-8f)
+    return (1.0f / len) * a;
+  return F3(1.f, 0.f, 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Philox4x32-10, keyed by the render seed, counter = (pixel, sample, bounce, stream << 16 | block).
+// Replaces the reference's per-pixel curand XORWOW state (CameraKernels.cu:15-25): no state in
+// memory, and a sample's random numbers do not depend on launch shape, queue order or GPU count.
+// ---------------------------------------------------------------------------------------------------
+enum { RT_STREAM_CAMERA = 0, RT_STREAM_SHADE = 1, RT_STREAM_MEDIUM0 = 2 };
+
+RT_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+struct Uniform4 {
+  float x, y, z, w;
+};
+
+RT_HD Uniform4 philox_uniform4(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t stream,
+                               uint32_t block) {
+  uint32_t c0 = pixel, c1 = sample, c2 = bounce, c3 = (stream << 16) | block;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t hi0 = mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0;
+    c1 = lo1;
+    c2 = n2;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  const float s = 1.0f / 16777216.0f; // 24-bit uniforms in [0,1), exact in FP32
+  Uniform4 u;
+  u.x = (float)(c0 >> 8) * s;
+  u.y = (float)(c1 >> 8) * s;
+  u.z = (float)(c2 >> 8) * s;
+  u.w = (float)(c3 >> 8) * s;
+  return u;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Device scene layout
+// ---------------------------------------------------------------------------------------------------
+// BVH4 node: 8 x float4 = 128 B (one L1/L2 line), SoA over the four children.
+//   [0] lo.x  [1] hi.x  [2] lo.y  [3] hi.y  [4] lo.z  [5] hi.z  [6] child refs (int bits)  [7] spare
+// child ref >= 0: node index;  < 0 and != RT_EMPTY: leaf, primitive index = ~ref;  RT_EMPTY: unused slot.
+#define RT_NODE_F4 8
+#define RT_EMPTY ((int)0x80000000)
+
+// Primitive record: 4 x float4 = 64 B, in BVH leaf (Morton) order, world space (instances baked).
+//   sphere: [0] c0.xyz, radius       [1] center_dir.xyz, -          [2] -                [3] -, typemat, id, object
+//   quad:   [0] normal.xyz, D        [1] A.xyz, Q.x                 [2] B.xyz, Q.y       [3] Q.z, typemat, id, object
+//           alpha = A . (p - Q), beta = B . (p - Q)   with A = v x w, B = w x u  (Plane.cpp:93-94 rearranged)
+//   medium: [0] -1/density, first boundary record, n boundary records, medium index      [3] -, typemat, id, object
+// typemat = type << 28 | material index.  id = unified primitive id of include/rt_b200.h.
+#define RT_PRIM_F4 4
+enum { RT_PT_SPHERE = 0, RT_PT_QUAD = 1, RT_PT_MEDIUM = 2 };
+
+// Material record: 3 x float4.
+//   [0] type, texture type (int bits), p0, p1   [1] color A   [2] color B
+//   lambertian / isotropic / diffuse_light: solid -> A; checker -> p0 = scale, A = even, B = odd;
+//                                           noise -> p0 = scale, p1 = perlin table index (int bits)
+//   metal: A = albedo, p0 = fuzz.   dielectric: p0 = refraction index.
+#define RT_MAT_F4 3
+
+// Light record: 4 x float4.  quad: [0] corner, shape  [1] u, area  [2] v, D  [3] normal, -  ([4],[5] below)
+// sphere: [0] center, shape  [1] radius
+#define RT_LIGHT_F4 6
+
+struct DScene {
+  const float4 *nodes;
+  const float4 *prims;
+  const float4 *bprims; // boundary records of constant media (same layout as prims)
+  const float4 *mats;
+  const float4 *lights;
+  const float4 *perlin_grad;        // 256 float4 per table
+  const unsigned char *perlin_perm; // 3 x 256 bytes per table (x, y, z)
+  int n_prims;
+  int n_lights;
+  int n_media;
+  float bg[3];
+};
+
+struct DCamera {
+  float center[3];
+  float p00c[3]; // pixel00_loc - center (so the direction needs no large cancelling subtraction)
+  float du[3], dv[3];
+  float disk_u[3], disk_v[3];
+  int defocus; // defocus_angle > 0
+  int width, height;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Ray / hit
+// ---------------------------------------------------------------------------------------------------
+struct Ray {
+  f3 o, d;
+  float time;
+};
+
+struct Hit {
+  float t;
+  int prim; // leaf-order primitive index, -1 = miss
+};
+
+// Camera::get_ray (Camera.cpp:186-205) with the reference CUDA path's polar disk sampler
+// (Vec3Utility.cuh:57-61).  u0 = (jitter x, jitter y, disk r^2, disk angle), u1.x = time.
+RT_HD Ray camera_ray(const DCamera &cam, int i, int j, int s_i, int s_j, float recip_sqrt_spp, Uniform4 u0,
+                     Uniform4 u1) {
+  float px = ((float)s_i + u0.x) * recip_sqrt_spp - 0.5f;
+  float py = ((float)s_j + u0.y) * recip_sqrt_spp - 0.5f;
+  float fx = (float)i + px, fy = (float)j + py;
+  f3 du = F3(cam.du[0], cam.du[1], cam.du[2]), dv = F3(cam.dv[0], cam.dv[1], cam.dv[2]);
+  f3 rel = F3(cam.p00c[0], cam.p00c[1], cam.p00c[2]) + fx * du + fy * dv; // pixel sample - center
+  f3 lens = F3(0.f, 0.f, 0.f);
+  if (cam.defocus) {
+    float r = sqrtf(u0.z);
+    float th = 2.0f * RT_PI_F * u0.w;
+    float sn, cs;
+#if defined(__CUDA_ARCH__)
+    sincosf(th, &sn, &cs);
+#else
+    sn = sinf(th);
+    cs = cosf(th);
+#endif
+    lens = (r * cs) * F3(cam.disk_u[0], cam.disk_u[1], cam.disk_u[2]) +
+           (r * sn) * F3(cam.disk_v[0], cam.disk_v[1], cam.disk_v[2]);
+  }
+  Ray ray;
+  ray.o = F3(cam.center[0], cam.center[1], cam.center[2]) + lens;
+  ray.d = rel - lens;
+  ray.time = u1.x;
+  return ray;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Primitive tests (FP32 render path)
+// ---------------------------------------------------------------------------------------------------
+RT_HD float4 ldg4(const float4 *p) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+
+// Sphere::hit (Sphere.cpp:101-143): roots (h -+ sqrt(disc)) / a on the open interval (tmin, tmax).
+// The discriminant is evaluated as a * (r^2 - |oc - (h/a) d|^2), which is the same quantity as
+// h^2 - a c without the catastrophic cancellation of c = |oc|^2 - r^2 in FP32 (radius-1000 ground).
+RT_HD bool sphere_hit(float4 r0, float4 r1, const Ray &ray, float tmin, float tmax, float &t_out) {
+  f3 center = F3(r0.x, r0.y, r0.z) + ray.time * F3(r1.x, r1.y, r1.z);
+  float radius = r0.w;
+  f3 oc = center - ray.o;
+  float a = dot(ray.d, ray.d);
+  float h = dot(ray.d, oc);
+  float inv_a = 1.0f / a;
+  f3 perp = oc - (h * inv_a) * ray.d;
+  float disc = a * (radius * radius - dot(perp, perp));
+  if (disc < 0.f)
+    return false;
+  float sq = sqrtf(disc);
+  float root = (h - sq) * inv_a;
+  if (!(tmin < root && root < tmax)) {
+    root = (h + sq) * inv_a;
+    if (!(tmin < root && root < tmax))
+      return false;
+  }
+  t_out = root;
+  return true;
+}
+
+// Plane::hit (Plane.cpp:78-112): closed interval on t and on the planar coordinates.
+RT_HD bool quad_hit(float4 r0, float4 r1, float4 r2, float qz, const Ray &ray, float tmin, float tmax,
+                    float &t_out) {
+  f3 n = F3(r0.x, r0.y, r0.z);
+  f3 q = F3(r1.w, r2.w, qz);
+  float denom = dot(n, ray.d);
+  if (fabsf(denom) < 1e-8f)
+    return false;
+  float t = dot(n, q - ray.o) / denom; // (D - n.o) / denom with the subtraction done on the point
+  if (!(tmin <= t && t <= tmax))
+    return false;
+  f3 hp = (ray.o - q) + t * ray.d;
+  float alpha = dot(F3(r1.x, r1.y, r1.z), hp);
+  float beta = dot(F3(r2.x, r2.y, r2.z), hp);
+  if (!(0.f <= alpha && alpha <= 1.f) || !(0.f <= beta && beta <= 1.f))
+    return false;
+  t_out = t;
+  return true;
+}
+
+// Closest boundary crossing of a constant medium's convex boundary on the open/closed interval the
+// member type uses.
+RT_HD bool boundary_hit(const DScene &sc, int first, int count, const Ray &ray, float tmin, float tmax,
+                        float &t_out) {
+  bool any = false;
+  float closest = tmax;
+  for (int k = 0; k < count; k++) {
+    const float4 *rec = sc.bprims + (size_t)(first + k) * RT_PRIM_F4;
+    float4 r0 = ldg4(rec), r1 = ldg4(rec + 1), r3 = ldg4(rec + 3);
+    int type = (uint32_t)f2i(r3.y) >> 28;
+    float t;
+    bool ok;
+    if (type == RT_PT_SPHERE)
+      ok = sphere_hit(r0, r1, ray, tmin, closest, t);
+    else
+      ok = quad_hit(r0, r1, ldg4(rec + 2), r3.x, ray, tmin, closest, t);
+    if (ok) {
+      any = true;
+      closest = t;
+    }
+  }
+  t_out = closest;
+  return any;
+}
+
+// ConstantMedium::hit (ConstantMedium.cpp:25-94).  xi is the segment's uniform for this medium.
+RT_HD bool medium_hit(const DScene &sc, float4 r0, const Ray &ray, float tmin, float tmax, float xi,
+                      float &t_out) {
+  int first = f2i(r0.y), count = f2i(r0.z);
+  float t1, t2;
+  if (!boundary_hit(sc, first, count, ray, -RT_INF_F, RT_INF_F, t1))
+    return false;
+  if (!boundary_hit(sc, first, count, ray, t1 + 0.0001f, RT_INF_F, t2))
+    return false;
+  if (t1 < tmin)
+    t1 = tmin;
+  if (t2 > tmax)
+    t2 = tmax;
+  if (t1 >= t2)
+    return false;
+  if (t1 < 0.f)
+    t1 = 0.f;
+  float ray_length = length(ray.d);
+  float distance_inside = (t2 - t1) * ray_length;
+  float hit_distance = r0.x * logf(xi); // -1/density * log(xi)
+  if (hit_distance > distance_inside)
+    return false;
+  t_out = t1 + hit_distance / ray_length;
+  return true;
+}
+
+// One leaf primitive against the current interval; updates `hit` when closer.
+struct RayKey {
+  uint64_t seed;
+  uint32_t pixel, sample, bounce;
+};
+
+RT_HD void leaf_test(const DScene &sc, int prim, const Ray &ray, float tmin, Hit &hit, int skip_prim,
+                     const RayKey &key) {
+  if (prim == skip_prim)
+    return;
+  const float4 *rec = sc.prims + (size_t)prim * RT_PRIM_F4;
+  float4 r0 = ldg4(rec), r3 = ldg4(rec + 3);
+  int type = (uint32_t)f2i(r3.y) >> 28;
+  float t;
+  bool ok;
+  if (type == RT_PT_SPHERE) {
+    ok = sphere_hit(r0, ldg4(rec + 1), ray, tmin, hit.t, t);
+  } else if (type == RT_PT_QUAD) {
+    ok = quad_hit(r0, ldg4(rec + 1), ldg4(rec + 2), r3.x, ray, tmin, hit.t, t);
+  } else {
+    Uniform4 u = philox_uniform4(key.seed, key.pixel, key.sample, key.bounce,
+                                 (uint32_t)(RT_STREAM_MEDIUM0 + f2i(r0.w)), 0);
+    ok = medium_hit(sc, r0, ray, tmin, hit.t, u.x, t);
+  }
+  if (ok) {
+    hit.t = t;
+    hit.prim = prim;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// BVH4 traversal (FP32).  Slab test as AABB::hit (AABB.cpp:141-164) but with the reciprocal
+// direction hoisted, NaN-safe min/max, and the far plane widened by 2 ulp so that no box the FP64
+// reference would enter is culled (Ize, "Robust BVH ray traversal").
+// The stack holds (child ref, entry distance); `stack` is caller-provided storage of RT_STACK entries
+// (shared-memory short stack in the kernels, spilling to local memory beyond RT_STACK_SMEM).
+// ---------------------------------------------------------------------------------------------------
+#define RT_STACK 48
+
+struct StackEntry {
+  int ref;
+  float t;
+};
+
+template <class Stack>
+RT_HD void traverse(const DScene &sc, const Ray &ray, float tmin, Hit &hit, int skip_prim, const RayKey &key,
+                    Stack &stack) {
+  f3 inv = F3(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);
+  f3 o = ray.o;
+  int sp = 0;
+  int ref = 0; // root node
+  float ref_t = tmin;
+  for (;;) {
+    if (ref >= 0) {
+      const float4 *n = sc.nodes + (size_t)ref * RT_NODE_F4;
+      float4 lox = ldg4(n), hix = ldg4(n + 1), loy = ldg4(n + 2), hiy = ldg4(n + 3), loz = ldg4(n + 4),
+             hiz = ldg4(n + 5), cr = ldg4(n + 6);
+      float tn[4];
+      int cref[4] = {f2i(cr.x), f2i(cr.y), f2i(cr.z), f2i(cr.w)};
+      const float lx[4] = {lox.x, lox.y, lox.z, lox.w}, hx[4] = {hix.x, hix.y, hix.z, hix.w};
+      const float ly[4] = {loy.x, loy.y, loy.z, loy.w}, hy[4] = {hiy.x, hiy.y, hiy.z, hiy.w};
+      const float lz[4] = {loz.x, loz.y, loz.z, loz.w}, hz[4] = {hiz.x, hiz.y, hiz.z, hiz.w};
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        // (bound - origin) * inv: the subtraction first, so a ray that starts close to a slab plane
+        // keeps full relative accuracy (an o * inv term would cancel catastrophically)
+        float t0x = (lx[c] - o.x) * inv.x, t1x = (hx[c] - o.x) * inv.x;
+        float t0y = (ly[c] - o.y) * inv.y, t1y = (hy[c] - o.y) * inv.y;
+        float t0z = (lz[c] - o.z) * inv.z, t1z = (hz[c] - o.z) * inv.z;
+        float tnear = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), tmin));
+        float tfar = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), hit.t));
+        bool ok = (tnear <= tfar * 1.0000004f) && (cref[c] != RT_EMPTY);
+        tn[c] = ok ? tnear : RT_INF_F;
+      }
+      // sort the four children by entry distance (ascending), 5-comparator network
+#define RT_CSWAP(a, b)                                                                                       \
+  if (tn[b] < tn[a]) {                                                                                       \
+    float tt = tn[a];                                                                                        \
+    tn[a] = tn[b];                                                                                           \
+    tn[b] = tt;                                                                                              \
+    int ti = cref[a];                                                                                        \
+    cref[a] = cref[b];                                                                                       \
+    cref[b] = ti;                                                                                            \
+  }
+      RT_CSWAP(0, 1)
+      RT_CSWAP(2, 3)
+      RT_CSWAP(0, 2)
+      RT_CSWAP(1, 3)
+      RT_CSWAP(1, 2)
+#undef RT_CSWAP
+      // push far-to-near, continue with the nearest
+#pragma unroll
+      for (int c = 3; c >= 1; c--)
+        if (tn[c] < RT_INF_F) {
+          if (sp < RT_STACK) {
+            stack.set(sp, cref[c], tn[c]);
+            sp++;
+          }
+        }
+      if (tn[0] < RT_INF_F) {
+        ref = cref[0];
+        ref_t = tn[0];
+        continue;
+      }
+    } else {
+      leaf_test(sc, ~ref, ray, tmin, hit, skip_prim, key);
+    }
+    // pop
+    for (;;) {
+      if (sp == 0)
+        return;
+      sp--;
+      stack.get(sp, ref, ref_t);
+      if (ref_t <= hit.t)
+        break;
+    }
+  }
+}
+
+// The inexact FP32 slab test above may only ever ENTER more boxes than the exact one, so a simple
+// array stack is enough for host-side use.
+struct LocalStack {
+  StackEntry e[RT_STACK];
+  RT_HD void set(int i, int ref, float t) {
+    e[i].ref = ref;
+    e[i].t = t;
+  }
+  RT_HD void get(int i, int &ref, float &t) const {
+    ref = e[i].ref;
+    t = e[i].t;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Textures and materials
+// ---------------------------------------------------------------------------------------------------
+// PerlinNoise::noise / turb (PerlinNoise.hpp:43-79,186-201).
+RT_HD float perlin_noise(const DScene &sc, int table, f3 p) {
+  const float4 *grad = sc.perlin_grad + (size_t)table * 256;
+  const unsigned char *perm = sc.perlin_perm + (size_t)table * 768;
+  float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
+  float u = p.x - fx, v = p.y - fy, w = p.z - fz;
+  int xi = (int)fx, yi = (int)fy, zi = (int)fz;
+  float uu = u * u * (3.f - 2.f * u), vv = v * v * (3.f - 2.f * v), ww = w * w * (3.f - 2.f * w);
+  float accum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        int idx = perm[(xi + i) & 255] ^ perm[256 + ((yi + j) & 255)] ^ perm[512 + ((zi + k) & 255)];
+        float4 g = ldg4(grad + idx);
+        float wx = u - (float)i, wy = v - (float)j, wz = w - (float)k;
+        accum += (i ? uu : 1.f - uu) * (j ? vv : 1.f - vv) * (k ? ww : 1.f - ww) * (g.x * wx + g.y * wy + g.z * wz);
+      }
+  return accum;
+}
+
+RT_HD float perlin_turb(const DScene &sc, int table, f3 p, int depth) {
+  float accum = 0.f, weight = 1.f;
+  for (int i = 0; i < depth; i++) {
+    accum += weight * perlin_noise(sc, table, p);
+    weight *= 0.5f;
+    p = 2.f * p;
+  }
+  return fabsf(accum);
+}
+
+enum { RT_DTEX_SOLID = 0, RT_DTEX_CHECKER = 1, RT_DTEX_NOISE = 2 };
+
+// Texture::value for the material's texture (SolidColorTexture.cpp:8-10, CheckerTexture.cpp:43-54,
+// NoiseTexture.cpp:29-30).  None of the reference's textures reads (u, v).
+RT_HD f3 material_texture(const DScene &sc, const float4 *m, float4 m0, f3 p) {
+  int tex = f2i(m0.y);
+  if (tex == RT_DTEX_SOLID)
+    return F3(ldg4(m + 1));
+  if (tex == RT_DTEX_CHECKER) {
+    float inv_scale = 1.0f / m0.z;
+    int xi = (int)floorf(inv_scale * p.x), yi = (int)floorf(inv_scale * p.y), zi = (int)floorf(inv_scale * p.z);
+    bool even = ((xi + yi + zi) % 2) == 0;
+    return F3(ldg4(m + (even ? 1 : 2)));
+  }
+  float f = 1.f + sinf(m0.z * p.z + 10.f * perlin_turb(sc, f2i(m0.w), p, 7));
+  return F3(0.5f * f, 0.5f * f, 0.5f * f);
+}
+
+// ONB (ONB.hpp:33-36,64)
+struct Onb {
+  f3 u, v, w;
+};
+RT_HD Onb onb_make(f3 n) {
+  Onb b;
+  b.w = normalize(n);
+  f3 a = fabsf(b.w.x) > 0.9f ? F3(0.f, 1.f, 0.f) : F3(1.f, 0.f, 0.f);
+  b.v = normalize(cross(b.w, a));
+  b.u = cross(b.w, b.v);
+  return b;
+}
+RT_HD f3 onb_transform(const Onb &b, f3 a) { return a.x * b.u + a.y * b.v + a.z * b.w; }
+
+RT_HD void sincos_2pi(float u, float &sn, float &cs) {
+#if defined(__CUDA_ARCH__)
+  sincospif(2.0f * u, &sn, &cs);
+#else
+  sn = sinf(2.0f * RT_PI_F * u);
+  cs = cosf(2.0f * RT_PI_F * u);
+#endif
+}
+
+// cuda_vec3_random_unit_vector (Vec3Utility.cuh:65-70)
+RT_HD f3 unit_vector_polar(float u1, float u2) {
+  float z = -1.0f + 2.0f * u1;
+  float r = sqrtf(fmaxf(0.f, 1.0f - z * z));
+  float sn, cs;
+  sincos_2pi(u2, sn, cs);
+  return F3(r * cs, r * sn, z);
+}
+// random_cosine_direction (Vec3Utility.hpp:94-104)
+RT_HD f3 cosine_direction(float r1, float r2) {
+  float sn, cs;
+  sincos_2pi(r1, sn, cs);
+  float s = sqrtf(r2);
+  return F3(cs * s, sn * s, sqrtf(1.f - r2));
+}
+
+// Lights: HittablePDF over the light list (PDF.hpp:82-113, HittableList.cpp:44-63).
+//   quad   [0] corner, shape   [1] u, area   [2] v, -   [3] normal, D   [4] A, -   [5] B, -
+//   sphere [0] center, shape   [1] radius
+RT_HD f3 light_random(const float4 *l, f3 origin, float r1, float r2) {
+  float4 l0 = ldg4(l), l1 = ldg4(l + 1);
+  if (f2i(l0.w) == 1) { // quad: Plane::random (Plane.cpp:128-133)
+    float4 l2 = ldg4(l + 2);
+    f3 p = F3(l0) + r1 * F3(l1) + r2 * F3(l2);
+    return p - origin;
+  }
+  // Sphere::random (Sphere.cpp:161-179)
+  f3 direction = F3(l0) - origin;
+  float distance_squared = dot(direction, direction);
+  Onb uvw = onb_make(direction);
+  float radius = l1.x;
+  float z = 1.f + r2 * (sqrtf(fmaxf(0.f, 1.f - radius * radius / distance_squared)) - 1.f);
+  float sn, cs;
+  sincos_2pi(r1, sn, cs);
+  float s = sqrtf(fmaxf(0.f, 1.f - z * z));
+  return onb_transform(uvw, F3(cs * s, sn * s, z));
+}
+
+RT_HD float light_pdf_value(const float4 *l, f3 origin, f3 dir) {
+  float4 l0 = ldg4(l), l1 = ldg4(l + 1);
+  Ray r;
+  r.o = origin;
+  r.d = dir;
+  r.time = 0.f;
+  float t;
+  if (f2i(l0.w) == 1) { // Plane::pdf_value (Plane.cpp:115-126)
+    float4 l2 = ldg4(l + 2), l3 = ldg4(l + 3), l4 = ldg4(l + 4), l5 = ldg4(l + 5);
+    float4 q0 = make_float4(l3.x, l3.y, l3.z, l3.w);
+    float4 q1 = make_float4(l4.x, l4.y, l4.z, l0.x);
+    float4 q2 = make_float4(l5.x, l5.y, l5.z, l0.y);
+    (void)l2;
+    if (!quad_hit(q0, q1, q2, l0.z, r, RT_T_MIN, RT_INF_F, t))
+      return 0.f;
+    float dd = dot(dir, dir);
+    float distance_squared = t * t * dd;
+    float cosine = fabsf(dot(dir, F3(l3)) / sqrtf(dd));
+    return distance_squared / (cosine * l1.w);
+  }
+  // Sphere::pdf_value (Sphere.cpp:145-159)
+  float4 s0 = make_float4(l0.x, l0.y, l0.z, l1.x);
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!sphere_hit(s0, s1, r, RT_T_MIN, RT_INF_F, t))
+    return 0.f;
+  f3 oc = F3(l0) - origin;
+  float cos_theta_max = sqrtf(fmaxf(0.f, 1.f - l1.x * l1.x / dot(oc, oc)));
+  float solid_angle = 2.f * RT_PI_F * (1.f - cos_theta_max);
+  return 1.f / solid_angle;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// One integrator step (Camera::ray_color unrolled into a loop, Camera.cpp:232-309; pdf guard of
+// CameraKernels.cu:192).  Returns true when the path continues with `next` (throughput already
+// multiplied in); otherwise `radiance_out` is the path's contribution (throughput * emitted or
+// throughput * background) and the path ends.
+// ---------------------------------------------------------------------------------------------------
+struct ShadeResult {
+  Ray next;
+  f3 throughput;
+  f3 radiance;
+  int next_skip_prim;
+};
+
+RT_HD bool shade_segment(const DScene &sc, const Ray &ray, Hit hit, f3 throughput, const RayKey &key,
+                         bool last_bounce, ShadeResult &out) {
+  out.radiance = F3(0.f, 0.f, 0.f);
+  out.next_skip_prim = -1;
+  if (hit.prim < 0) {
+    out.radiance = throughput * F3(sc.bg[0], sc.bg[1], sc.bg[2]);
+    return false;
+  }
+  const float4 *rec = sc.prims + (size_t)hit.prim * RT_PRIM_F4;
+  float4 r0 = ldg4(rec), r3 = ldg4(rec + 3);
+  uint32_t typemat = (uint32_t)f2i(r3.y);
+  int type = typemat >> 28;
+  const float4 *m = sc.mats + (size_t)(typemat & 0x0fffffffu) * RT_MAT_F4;
+  float4 m0 = ldg4(m);
+  int mtype = f2i(m0.x);
+
+  // hit point, normal, front face (HitRecord::set_face_normal, HitRecord.hpp:36-39)
+  f3 p = ray.o + hit.t * ray.d;
+  f3 normal;
+  bool front;
+  if (type == RT_PT_SPHERE) {
+    float4 r1 = ldg4(rec + 1);
+    f3 center = F3(r0) + ray.time * F3(r1);
+    f3 outward = (1.0f / r0.w) * (p - center);
+    outward = normalize(outward);
+    p = center + r0.w * outward; // keep the point on the surface (FP32 drift on large spheres)
+    front = dot(ray.d, outward) < 0.f;
+    normal = front ? outward : -outward;
+  } else if (type == RT_PT_QUAD) {
+    f3 outward = F3(r0);
+    front = dot(ray.d, outward) < 0.f;
+    normal = front ? outward : -outward;
+    out.next_skip_prim = hit.prim; // a ray leaving a flat primitive cannot hit it again
+  } else {
+    normal = F3(1.f, 0.f, 0.f); // ConstantMedium.cpp:86-88
+    front = true;
+  }
+
+  if (mtype == 3) { // diffuse light: emits on the front face, never scatters (DiffuseLightMaterial.cpp:12-19)
+    if (front)
+      out.radiance = throughput * material_texture(sc, m, m0, p);
+    return false;
+  }
+  if (last_bounce) // the scattered ray would be traced with depth 0 and contribute nothing
+    return false;
+
+  Uniform4 u = philox_uniform4(key.seed, key.pixel, key.sample, key.bounce, RT_STREAM_SHADE, 0);
+  out.next.o = p;
+  out.next.time = ray.time;
+
+  if (mtype == 1) { // metal (MetalMaterial.cpp:46-61)
+    f3 reflected = ray.d - (2.f * dot(ray.d, normal)) * normal;
+    out.next.d = normalize(reflected) + m0.z * unit_vector_polar(u.y, u.z);
+    out.throughput = throughput * F3(ldg4(m + 1));
+    return true;
+  }
+  if (mtype == 2) { // dielectric (DielectricMaterial.cpp:62-84, Vec3Utility.hpp:76-89)
+    float ri = front ? (1.0f / m0.z) : m0.z;
+    f3 unit_direction = normalize(ray.d);
+    float cos_theta = fminf(dot(-unit_direction, normal), 1.0f);
+    float sin_theta = sqrtf(fmaxf(0.f, 1.0f - cos_theta * cos_theta));
+    bool cannot_refract = ri * sin_theta > 1.0f;
+    float r0s = (1.f - ri) / (1.f + ri);
+    r0s = r0s * r0s;
+    float c1 = 1.f - cos_theta;
+    float reflectance = r0s + (1.f - r0s) * (c1 * c1 * c1 * c1 * c1);
+    if (cannot_refract || reflectance > u.x) {
+      out.next.d = unit_direction - (2.f * dot(unit_direction, normal)) * normal;
+    } else {
+      f3 perp = ri * (unit_direction + cos_theta * normal);
+      f3 parallel = (-sqrtf(fabsf(1.0f - dot(perp, perp)))) * normal;
+      out.next.d = perp + parallel;
+    }
+    out.throughput = throughput;
+    out.next_skip_prim = -1;
+    return true;
+  }
+
+  // lambertian (LambertianMaterial.cpp:15-59) / isotropic (IsotropicMaterial.cpp:12-31)
+  bool lambert = mtype == 0;
+  f3 attenuation = material_texture(sc, m, m0, p);
+  Onb uvw;
+  if (lambert)
+    uvw = onb_make(normal);
+  f3 dir;
+  if (u.x < 0.5f && sc.n_lights > 0) { // MixturePDF::generate (PDF.hpp:135-139)
+    int pick = (int)(u.w * (float)sc.n_lights);
+    pick = pick > sc.n_lights - 1 ? sc.n_lights - 1 : pick;
+    dir = light_random(sc.lights + (size_t)pick * RT_LIGHT_F4, p, u.y, u.z);
+  } else if (lambert) {
+    dir = onb_transform(uvw, cosine_direction(u.y, u.z));
+  } else {
+    dir = unit_vector_polar(u.y, u.z);
+  }
+  f3 unit_dir = normalize(dir);
+  float mat_pdf = lambert ? fmaxf(0.f, dot(unit_dir, uvw.w) * (1.0f / RT_PI_F)) : 1.0f / (4.0f * RT_PI_F);
+  float first_pdf = mat_pdf;
+  if (sc.n_lights > 0) { // HittableList::pdf_value (HittableList.cpp:44-55)
+    float weight = 1.0f / (float)sc.n_lights;
+    first_pdf = 0.f;
+    for (int i = 0; i < sc.n_lights; i++)
+      first_pdf += weight * light_pdf_value(sc.lights + (size_t)i * RT_LIGHT_F4, p, dir);
+  }
+  float pdf_value = 0.5f * first_pdf + 0.5f * mat_pdf;
+  float scattering_pdf;
+  if (lambert) {
+    float cos_theta = dot(normal, unit_dir);
+    scattering_pdf = cos_theta < 0.f ? 0.f : cos_theta * (1.0f / RT_PI_F);
+  } else {
+    scattering_pdf = 1.0f / (4.0f * RT_PI_F);
+  }
+  if (!(pdf_value > 1e-8f) || !(scattering_pdf > 0.f)) // zero weight: nothing further can contribute
+    return false;
+  out.next.d = dir;
+  out.throughput = throughput * ((scattering_pdf / pdf_value) * attenuation);
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Film
+// ---------------------------------------------------------------------------------------------------
+// Scanline-tile ownership: tile k (tile_rows consecutive scanlines) belongs to rank k % n_ranks; a
+// rank stores its tiles compactly in tile order.
+struct DFilmMap {
+  int width, height, rank, n_ranks, tile_rows;
+};
+RT_HD int owned_row_to_global(const DFilmMap &m, int local_row) {
+  int tile_local = local_row / m.tile_rows;
+  return (tile_local * m.n_ranks + m.rank) * m.tile_rows + local_row % m.tile_rows;
+}
+RT_HD int owned_rows(int height, int rank, int n_ranks, int tile_rows) {
+  int rows = 0;
+  int n_tiles = (height + tile_rows - 1) / tile_rows;
+  for (int t = rank; t < n_tiles; t += n_ranks) {
+    int r0 = t * tile_rows;
+    int r1 = r0 + tile_rows < height ? r0 + tile_rows : height;
+    rows += r1 - r0;
+  }
+  return rows;
+}
+
+// to_byte (utils/ColorUtility.hpp:11-26) in the reference's FP64.
+RT_HD unsigned char to_byte_f64(double v) {
+  double x = v > 0 ? sqrt(v) : 0;
+  if (x < 0.000)
+    x = 0.000;
+  if (x > 0.999)
+    x = 0.999;
+  return (unsigned char)(256 * x);
+}

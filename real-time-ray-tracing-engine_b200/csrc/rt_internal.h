@@ -1,0 +1,120 @@
+// rt_internal.h — host-side structures shared by the translation units of librt_b200.so and the
+// launch wrappers of the kernels (rt_kernels.cu, rt_exact.cu).
+#pragma once
+
+#include "../../include/rt_b200.h"
+#include "rt_bvh.h"
+#include "rt_device.h"
+#include "rt_exact.h"
+
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+
+// One wavefront pass: `n_paths` = owned pixels x samples of this pass.  Path p covers owned pixel
+// p % n_owned and sample first_sample + p / n_owned of a sqrt_spp x sqrt_spp stratification.
+struct PassParams {
+  DCamera cam;
+  DFilmMap map;
+  int n_owned;      // owned pixels
+  int n_paths;      // paths of this pass
+  int first_sample; // linear stratum index of the pass's first sample
+  int n_samples;    // samples in this pass
+  int sqrt_spp;
+  float recip_sqrt_spp;
+  int max_depth;
+  uint64_t seed;
+};
+
+// Per-context wavefront storage (sized for the largest pass so far).
+struct WaveBuffers {
+  float4 *ray_a[2] = {nullptr, nullptr}; // origin.xyz, time
+  float4 *ray_b[2] = {nullptr, nullptr}; // direction.xyz, path id (int bits)
+  float2 *hit[2] = {nullptr, nullptr};   // in: (-, skip primitive)  out: (t, primitive) for the same queue slot
+  float4 *throughput = nullptr;          // per path
+  float4 *radiance = nullptr;            // per path: final contribution
+  unsigned int *counts = nullptr;        // queue length per bounce (max_depth + 2 entries)
+  unsigned long long *stats = nullptr;   // [0] segments traced  [1] nodes visited  [2] primitive tests
+  size_t capacity_paths = 0;
+  size_t capacity_counts = 0;
+};
+
+struct rt_context {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  WaveBuffers wave;
+  rt_counters counters{};
+};
+
+struct rt_scene {
+  rt_context *ctx = nullptr;
+  DScene d{};
+  ExactScene ex{};
+  // device allocations (owned)
+  float4 *nodes = nullptr, *prims = nullptr, *bprims = nullptr, *mats = nullptr, *lights = nullptr,
+         *perlin_grad = nullptr;
+  unsigned char *perlin_perm = nullptr;
+  PrimExact *ex_prims = nullptr, *ex_bprims = nullptr;
+  XformOpExact *ex_ops = nullptr;
+  int *ex_chain_first = nullptr, *ex_chain_count = nullptr;
+  int *leaf_object = nullptr, *leaf_id = nullptr; // per leaf-order primitive: object / unified id
+  rt_scene_info info{};
+  int n_leaf = 0;
+};
+
+struct rt_film {
+  rt_context *ctx = nullptr;
+  DFilmMap map{};
+  int64_t n_owned = 0;
+  float4 *accum = nullptr;
+  bool owns_accum = false;
+  int64_t samples = 0;
+};
+
+// ---- error reporting (rt_api.cu) ----
+void rt_set_error(const std::string &msg);
+int rt_cuda_fail(cudaError_t e, const char *what);
+#define RT_CUDA(call)                                                                                        \
+  do {                                                                                                       \
+    cudaError_t e_ = (call);                                                                                 \
+    if (e_ != cudaSuccess)                                                                                   \
+      return rt_cuda_fail(e_, #call);                                                                        \
+  } while (0)
+
+// ---- scene construction (rt_scene.cu) ----
+int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *scene);
+void rt_scene_release(rt_scene *scene);
+
+// ---- kernel launch wrappers (rt_kernels.cu); all asynchronous on `stream` ----
+struct LaunchShape {
+  int blocks, threads;
+};
+LaunchShape rt_persistent_shape(const rt_context *ctx, int threads, int blocks_per_sm);
+
+// LBVH build
+void launch_morton(cudaStream_t s, const BuildBox *boxes, int n, const float *scene_lo, const float *scene_inv,
+                   uint64_t *codes, uint32_t *index);
+int sort_pairs(cudaStream_t s, uint64_t *keys_in, uint64_t *keys_out, uint32_t *vals_in, uint32_t *vals_out, int n);
+void launch_gather_boxes(cudaStream_t s, const BuildBox *in, const uint32_t *index, BuildBox *out, int n);
+void launch_hierarchy(cudaStream_t s, const uint64_t *codes, BinTree t);
+void launch_refit(cudaStream_t s, BinTree t, const BuildBox *leaf_boxes);
+void launch_collapse(cudaStream_t s, BinTree t, const BuildBox *leaf_boxes, float4 *nodes, const CollapseItem *items,
+                     int n_items, CollapseItem *next, int *next_count, int *wide_count);
+void launch_gather_records(cudaStream_t s, const void *in, const uint32_t *index, void *out, int n, int bytes_per);
+
+// wavefront render
+void launch_generate(const rt_context *ctx, const PassParams &pp, WaveBuffers &w);
+void launch_extend(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int bounce);
+void launch_shade(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int bounce);
+void launch_accumulate(const rt_context *ctx, const PassParams &pp, WaveBuffers &w, float4 *film);
+void launch_resolve_rgb8(cudaStream_t s, const float4 *film, int64_t n, double scale, uint8_t *out);
+void launch_resolve_rgb(cudaStream_t s, const float4 *film, int64_t n, double scale, float *out);
+void launch_scatter_gathered(cudaStream_t s, int width, int height, int n_ranks, int tile_rows, const float4 *gathered,
+                             float4 *full);
+
+// parity hook
+void launch_trace_fast(const rt_context *ctx, const DScene &sc, const rt_ray *d_rays, int64_t n, uint64_t seed,
+                       const int *leaf_object, const int *leaf_id, rt_hit *d_hits);
+void launch_trace_exact(cudaStream_t s, const ExactScene &sc, const rt_ray *d_rays, int64_t n, uint64_t seed,
+                        rt_hit *d_hits); // rt_exact.cu

@@ -1,0 +1,507 @@
+// rt_kernels.cu — the CUDA kernels of the wavefront path tracer and of the LBVH build, for sm_100a.
+//
+// Pipeline per pass (replaces the reference's one-thread-per-pixel recursive megakernels,
+// core/camera/CameraKernels.cu:206-278):
+//   k_generate    camera rays for all paths of the pass             -> ray queue 0
+//   k_extend      BVH4 traversal + sphere / quad / medium tests     -> hit per queue slot
+//   k_shade       emit / scatter / light sampling, Philox draws     -> compacted ray queue of the next bounce
+//   k_accumulate  per-pixel sum of the pass's samples, in order     -> film
+// Queue lengths stay on the device (counts[bounce]); every kernel is a persistent grid sized in
+// multiples of the SM count that strides over the queue, so the host never synchronises between
+// bounces.  Compaction uses one ballot + one atomic per warp.
+#include "rt_internal.h"
+
+#include <cub/device/device_radix_sort.cuh>
+
+#define RT_BLOCK 128
+#define RT_STACK_SMEM 8
+
+LaunchShape rt_persistent_shape(const rt_context *ctx, int threads, int blocks_per_sm) {
+  LaunchShape s;
+  s.threads = threads;
+  s.blocks = ctx->sm_count * blocks_per_sm;
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Short traversal stack: the first RT_STACK_SMEM entries of every thread live in shared memory
+// (column-interleaved: no bank conflicts), deeper entries spill to local memory.
+// ---------------------------------------------------------------------------------------------------
+struct SmemStack {
+  int *s_ref;
+  float *s_t;
+  StackEntry spill[RT_STACK - RT_STACK_SMEM];
+  __device__ __forceinline__ void set(int i, int ref, float t) {
+    if (i < RT_STACK_SMEM) {
+      s_ref[i * RT_BLOCK] = ref;
+      s_t[i * RT_BLOCK] = t;
+    } else {
+      spill[i - RT_STACK_SMEM].ref = ref;
+      spill[i - RT_STACK_SMEM].t = t;
+    }
+  }
+  __device__ __forceinline__ void get(int i, int &ref, float &t) const {
+    if (i < RT_STACK_SMEM) {
+      ref = s_ref[i * RT_BLOCK];
+      t = s_t[i * RT_BLOCK];
+    } else {
+      ref = spill[i - RT_STACK_SMEM].ref;
+      t = spill[i - RT_STACK_SMEM].t;
+    }
+  }
+};
+
+__device__ __forceinline__ void path_to_key(const PassParams &pp, int path, int bounce, RayKey &key, int &owned_pixel) {
+  int k = path % pp.n_owned;
+  int s_local = path / pp.n_owned;
+  int local_row = k / pp.map.width;
+  int col = k - local_row * pp.map.width;
+  int row = owned_row_to_global(pp.map, local_row);
+  key.seed = pp.seed;
+  key.pixel = (uint32_t)row * (uint32_t)pp.map.width + (uint32_t)col;
+  key.sample = (uint32_t)(pp.first_sample + s_local);
+  key.bounce = (uint32_t)bounce;
+  owned_pixel = k;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// generate
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RT_BLOCK)
+    k_generate(const __grid_constant__ PassParams pp, float4 *__restrict__ ray_a, float4 *__restrict__ ray_b,
+               float2 *__restrict__ hit, float4 *__restrict__ throughput, float4 *__restrict__ radiance,
+               unsigned int *__restrict__ counts) {
+  int stride = gridDim.x * blockDim.x;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < pp.n_paths; p += stride) {
+    RayKey key;
+    int k;
+    path_to_key(pp, p, 0, key, k);
+    int row = (int)(key.pixel / (uint32_t)pp.map.width), col = (int)(key.pixel % (uint32_t)pp.map.width);
+    int s = (int)key.sample;
+    int s_i = s % pp.sqrt_spp, s_j = s / pp.sqrt_spp;
+    Uniform4 u0 = philox_uniform4(pp.seed, key.pixel, key.sample, 0, RT_STREAM_CAMERA, 0);
+    Uniform4 u1 = philox_uniform4(pp.seed, key.pixel, key.sample, 0, RT_STREAM_CAMERA, 1);
+    Ray r = camera_ray(pp.cam, col, row, s_i, s_j, pp.recip_sqrt_spp, u0, u1);
+    ray_a[p] = make_float4(r.o.x, r.o.y, r.o.z, r.time);
+    ray_b[p] = make_float4(r.d.x, r.d.y, r.d.z, __int_as_float(p));
+    hit[p] = make_float2(0.f, __int_as_float(-1));
+    throughput[p] = make_float4(1.f, 1.f, 1.f, 0.f);
+    radiance[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    counts[0] = (unsigned int)pp.n_paths;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// extend
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RT_BLOCK)
+    k_extend(const __grid_constant__ DScene sc, const __grid_constant__ PassParams pp,
+             const float4 *__restrict__ ray_a, const float4 *__restrict__ ray_b, float2 *__restrict__ hit,
+             const unsigned int *__restrict__ counts, int bounce, int has_media, unsigned long long *stats) {
+  __shared__ int s_ref[RT_STACK_SMEM * RT_BLOCK];
+  __shared__ float s_t[RT_STACK_SMEM * RT_BLOCK];
+  SmemStack stack;
+  stack.s_ref = s_ref + threadIdx.x;
+  stack.s_t = s_t + threadIdx.x;
+  const int n = (int)counts[bounce];
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    atomicAdd(&stats[0], (unsigned long long)n);
+  int stride = gridDim.x * blockDim.x;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride) {
+    float4 a = ray_a[q], b = ray_b[q];
+    float2 h = hit[q];
+    Ray r;
+    r.o = F3(a.x, a.y, a.z);
+    r.d = F3(b.x, b.y, b.z);
+    r.time = a.w;
+    RayKey key;
+    key.seed = pp.seed;
+    key.pixel = key.sample = 0;
+    key.bounce = (uint32_t)bounce;
+    if (has_media) {
+      int k;
+      path_to_key(pp, __float_as_int(b.w), bounce, key, k);
+    }
+    Hit best;
+    best.t = RT_INF_F;
+    best.prim = -1;
+    traverse(sc, r, RT_T_MIN, best, __float_as_int(h.y), key, stack);
+    hit[q] = make_float2(best.t, __int_as_float(best.prim));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// shade + queue compaction
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RT_BLOCK)
+    k_shade(const __grid_constant__ DScene sc, const __grid_constant__ PassParams pp, const float4 *__restrict__ ray_a,
+            const float4 *__restrict__ ray_b, const float2 *__restrict__ hit, float4 *__restrict__ next_a,
+            float4 *__restrict__ next_b, float2 *__restrict__ next_hit, float4 *__restrict__ throughput,
+            float4 *__restrict__ radiance, unsigned int *__restrict__ counts, int bounce) {
+  const int n = (int)counts[bounce];
+  const int lane = threadIdx.x & 31;
+  const bool last_bounce = bounce + 1 >= pp.max_depth;
+  int stride = gridDim.x * blockDim.x;
+  for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < n; base += stride) {
+    int q = base + lane;
+    bool active = q < n;
+    bool cont = false;
+    ShadeResult res;
+    int path = 0;
+    if (active) {
+      float4 a = ray_a[q], b = ray_b[q];
+      float2 h = hit[q];
+      path = __float_as_int(b.w);
+      Ray r;
+      r.o = F3(a.x, a.y, a.z);
+      r.d = F3(b.x, b.y, b.z);
+      r.time = a.w;
+      Hit ht;
+      ht.t = h.x;
+      ht.prim = __float_as_int(h.y);
+      RayKey key;
+      int k;
+      path_to_key(pp, path, bounce, key, k);
+      float4 tp = throughput[path];
+      cont = shade_segment(sc, r, ht, F3(tp.x, tp.y, tp.z), key, last_bounce, res);
+      if (!cont)
+        radiance[path] = make_float4(res.radiance.x, res.radiance.y, res.radiance.z, 0.f);
+    }
+    unsigned int mask = __ballot_sync(0xffffffffu, cont);
+    if (mask) {
+      unsigned int pos = 0;
+      if (lane == __ffs(mask) - 1)
+        pos = atomicAdd(&counts[bounce + 1], (unsigned int)__popc(mask));
+      pos = __shfl_sync(0xffffffffu, pos, __ffs(mask) - 1);
+      if (cont) {
+        unsigned int slot = pos + (unsigned int)__popc(mask & ((1u << lane) - 1u));
+        next_a[slot] = make_float4(res.next.o.x, res.next.o.y, res.next.o.z, res.next.time);
+        next_b[slot] = make_float4(res.next.d.x, res.next.d.y, res.next.d.z, __int_as_float(path));
+        next_hit[slot] = make_float2(0.f, __int_as_float(res.next_skip_prim));
+        throughput[path] = make_float4(res.throughput.x, res.throughput.y, res.throughput.z, 0.f);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// accumulate / resolve
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_accumulate(const float4 *__restrict__ radiance, int n_owned, int n_samples, float4 *__restrict__ film) {
+  int stride = gridDim.x * blockDim.x;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_owned; k += stride) {
+    float4 acc = film[k];
+    for (int s = 0; s < n_samples; s++) {
+      float4 r = radiance[(size_t)s * n_owned + k];
+      acc.x += r.x;
+      acc.y += r.y;
+      acc.z += r.z;
+    }
+    film[k] = acc;
+  }
+}
+
+// to_byte(scale * sum) per channel in the reference's FP64 (ColorUtility.hpp:11-26,
+// DynamicCamera.cpp:280-306).
+__global__ void k_resolve_rgb8(const float4 *__restrict__ film, long long n, double scale, uint8_t *__restrict__ out) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+    float4 v = film[k];
+    out[k * 3 + 0] = to_byte_f64(scale * (double)v.x);
+    out[k * 3 + 1] = to_byte_f64(scale * (double)v.y);
+    out[k * 3 + 2] = to_byte_f64(scale * (double)v.z);
+  }
+}
+
+__global__ void k_resolve_rgb(const float4 *__restrict__ film, long long n, double scale, float *__restrict__ out) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+    float4 v = film[k];
+    out[k * 3 + 0] = (float)(scale * (double)v.x);
+    out[k * 3 + 1] = (float)(scale * (double)v.y);
+    out[k * 3 + 2] = (float)(scale * (double)v.z);
+  }
+}
+
+// Rank-major gathered compact films -> one row-major image.
+__global__ void k_scatter_gathered(int width, int height, int n_ranks, int tile_rows,
+                                   const float4 *__restrict__ gathered, float4 *__restrict__ full) {
+  long long total = (long long)width * height;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride) {
+    int row = (int)(g / width), col = (int)(g - (long long)row * width);
+    int tile = row / tile_rows;
+    int rank = tile % n_ranks;
+    int tile_local = tile / n_ranks;
+    // rows this rank owns before `row`: full tiles before tile_local (only the image's last tile can be short)
+    int local_row = tile_local * tile_rows + (row - tile * tile_rows);
+    long long base = 0;
+    for (int r = 0; r < rank; r++)
+      base += (long long)owned_rows(height, r, n_ranks, tile_rows) * width;
+    full[g] = gathered[base + (long long)local_row * width + col];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// parity hook: FP32 closest hit for explicit rays, through the same traverse() as k_extend
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RT_BLOCK)
+    k_trace_fast(const __grid_constant__ DScene sc, const rt_ray *__restrict__ rays, long long n, uint64_t seed,
+                 const int *__restrict__ leaf_object, const int *__restrict__ leaf_id, rt_hit *__restrict__ hits) {
+  __shared__ int s_ref[RT_STACK_SMEM * RT_BLOCK];
+  __shared__ float s_t[RT_STACK_SMEM * RT_BLOCK];
+  SmemStack stack;
+  stack.s_ref = s_ref + threadIdx.x;
+  stack.s_t = s_t + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride) {
+    const rt_ray &in = rays[q];
+    Ray r;
+    r.o = F3((float)in.origin[0], (float)in.origin[1], (float)in.origin[2]);
+    r.d = F3((float)in.direction[0], (float)in.direction[1], (float)in.direction[2]);
+    r.time = (float)in.time;
+    RayKey key;
+    key.seed = seed;
+    key.pixel = in.rng_pixel;
+    key.sample = in.rng_sample;
+    key.bounce = in.rng_bounce;
+    Hit best;
+    best.t = (float)in.t_max;
+    best.prim = -1;
+    traverse(sc, r, (float)in.t_min, best, -1, key, stack);
+    rt_hit out;
+    out.t = best.prim >= 0 ? (double)best.t : (double)RT_INF_F;
+    out.prim = best.prim >= 0 ? leaf_id[best.prim] : -1;
+    out.object = best.prim >= 0 ? leaf_object[best.prim] : -1;
+    out.front_face = 0;
+    out.pad_ = 0;
+    if (best.prim >= 0) { // front face as the shader derives it
+      const float4 *rec = sc.prims + (size_t)best.prim * RT_PRIM_F4;
+      float4 r0 = rec[0], r3 = rec[3];
+      int type = (uint32_t)__float_as_int(r3.y) >> 28;
+      if (type == RT_PT_SPHERE) {
+        float4 r1 = rec[1];
+        f3 center = F3(r0) + r.time * F3(r1);
+        f3 p = r.o + best.t * r.d;
+        out.front_face = dot(r.d, p - center) < 0.f;
+      } else if (type == RT_PT_QUAD) {
+        out.front_face = dot(r.d, F3(r0)) < 0.f;
+      } else {
+        out.front_face = 1;
+      }
+    }
+    hits[q] = out;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// LBVH build kernels
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_morton(const BuildBox *__restrict__ boxes, int n, const float *__restrict__ scene_lo,
+                         const float *__restrict__ scene_inv, uint64_t *__restrict__ codes, uint32_t *__restrict__ index) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  codes[i] = morton_body(boxes[i], scene_lo, scene_inv);
+  index[i] = (uint32_t)i;
+}
+
+__global__ void k_gather_boxes(const BuildBox *__restrict__ in, const uint32_t *__restrict__ index, BuildBox *__restrict__ out,
+                               int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    out[i] = in[index[i]];
+}
+
+__global__ void k_gather_records(const uint4 *__restrict__ in, const uint32_t *__restrict__ index, uint4 *__restrict__ out, int n,
+                                 int vec_per) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)n * vec_per;
+  if (t >= total)
+    return;
+  int i = (int)(t / vec_per), v = (int)(t - (long long)i * vec_per);
+  out[(size_t)i * vec_per + v] = in[(size_t)index[i] * vec_per + v];
+}
+
+__global__ void k_hierarchy(const uint64_t *__restrict__ codes, BinTree t) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < t.n - 1)
+    hierarchy_body(codes, t, i);
+}
+
+__global__ void k_refit(BinTree t, const BuildBox *__restrict__ leaf_boxes) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= t.n)
+    return;
+  int n_internal = t.n - 1;
+  int node = t.parent[n_internal + j];
+  while (node >= 0) {
+    __threadfence();
+    unsigned int old = atomicAdd(&t.visits[node], 1u);
+    if (old == 0)
+      return; // the sibling subtree is not finished yet; its thread will continue upwards
+    __threadfence();
+    const volatile BuildBox *vb = t.box;
+    int l = t.left[node], r = t.right[node];
+    BuildBox a, b;
+    if (l >= 0) {
+      for (int k = 0; k < 3; k++) {
+        a.lo[k] = vb[l].lo[k];
+        a.hi[k] = vb[l].hi[k];
+      }
+    } else {
+      a = leaf_boxes[~l];
+    }
+    if (r >= 0) {
+      for (int k = 0; k < 3; k++) {
+        b.lo[k] = vb[r].lo[k];
+        b.hi[k] = vb[r].hi[k];
+      }
+    } else {
+      b = leaf_boxes[~r];
+    }
+    t.box[node] = box_union(a, b);
+    node = t.parent[node];
+  }
+}
+
+__global__ void k_collapse(BinTree t, const BuildBox *__restrict__ leaf_boxes, float4 *__restrict__ nodes,
+                           const CollapseItem *__restrict__ items, int n_items, CollapseItem *__restrict__ next,
+                           int *next_count, int *wide_count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_items)
+    return;
+  CollapseItem it = items[i];
+  int child[4];
+  int n_child = collapse_gather(t, leaf_boxes, it.bin, child);
+  int n_inner = 0;
+  for (int k = 0; k < n_child; k++)
+    n_inner += child[k] >= 0;
+  int wide_ref[4] = {0, 0, 0, 0};
+  if (n_inner) {
+    int first_wide = atomicAdd(wide_count, n_inner);
+    int first_slot = atomicAdd(next_count, n_inner);
+    int m = 0;
+    for (int k = 0; k < n_child; k++)
+      if (child[k] >= 0) {
+        wide_ref[k] = first_wide + m;
+        next[first_slot + m].bin = child[k];
+        next[first_slot + m].wide = first_wide + m;
+        m++;
+      }
+  }
+  collapse_write(t, leaf_boxes, nodes, it.wide, child, n_child, wide_ref);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// launch wrappers
+// ---------------------------------------------------------------------------------------------------
+static inline int ceil_div(long long a, int b) { return (int)((a + b - 1) / b); }
+
+void launch_morton(cudaStream_t s, const BuildBox *boxes, int n, const float *scene_lo, const float *scene_inv,
+                   uint64_t *codes, uint32_t *index) {
+  k_morton<<<ceil_div(n, 256), 256, 0, s>>>(boxes, n, scene_lo, scene_inv, codes, index);
+}
+
+int sort_pairs(cudaStream_t s, uint64_t *keys_in, uint64_t *keys_out, uint32_t *vals_in, uint32_t *vals_out, int n) {
+  size_t bytes = 0;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys_in, keys_out, vals_in, vals_out, n, 0, 63, s);
+  if (e != cudaSuccess)
+    return rt_cuda_fail(e, "cub::DeviceRadixSort::SortPairs (size query)");
+  void *tmp = nullptr;
+  e = cudaMalloc(&tmp, bytes ? bytes : 16);
+  if (e != cudaSuccess)
+    return rt_cuda_fail(e, "cudaMalloc (sort scratch)");
+  e = cub::DeviceRadixSort::SortPairs(tmp, bytes, keys_in, keys_out, vals_in, vals_out, n, 0, 63, s);
+  cudaError_t e2 = cudaStreamSynchronize(s);
+  cudaFree(tmp);
+  if (e != cudaSuccess)
+    return rt_cuda_fail(e, "cub::DeviceRadixSort::SortPairs");
+  if (e2 != cudaSuccess)
+    return rt_cuda_fail(e2, "cudaStreamSynchronize (sort)");
+  return RT_OK;
+}
+
+void launch_gather_boxes(cudaStream_t s, const BuildBox *in, const uint32_t *index, BuildBox *out, int n) {
+  k_gather_boxes<<<ceil_div(n, 256), 256, 0, s>>>(in, index, out, n);
+}
+
+void launch_gather_records(cudaStream_t s, const void *in, const uint32_t *index, void *out, int n, int bytes_per) {
+  int vec_per = bytes_per / 16;
+  long long total = (long long)n * vec_per;
+  k_gather_records<<<ceil_div(total, 256), 256, 0, s>>>((const uint4 *)in, index, (uint4 *)out, n, vec_per);
+}
+
+void launch_hierarchy(cudaStream_t s, const uint64_t *codes, BinTree t) {
+  if (t.n >= 2)
+    k_hierarchy<<<ceil_div(t.n - 1, 256), 256, 0, s>>>(codes, t);
+}
+
+void launch_refit(cudaStream_t s, BinTree t, const BuildBox *leaf_boxes) {
+  if (t.n >= 2)
+    k_refit<<<ceil_div(t.n, 256), 256, 0, s>>>(t, leaf_boxes);
+}
+
+void launch_collapse(cudaStream_t s, BinTree t, const BuildBox *leaf_boxes, float4 *nodes, const CollapseItem *items,
+                     int n_items, CollapseItem *next, int *next_count, int *wide_count) {
+  k_collapse<<<ceil_div(n_items, 128), 128, 0, s>>>(t, leaf_boxes, nodes, items, n_items, next, next_count, wide_count);
+}
+
+void launch_generate(const rt_context *ctx, const PassParams &pp, WaveBuffers &w) {
+  LaunchShape sh = rt_persistent_shape(ctx, RT_BLOCK, 16);
+  int need = ceil_div(pp.n_paths, RT_BLOCK);
+  k_generate<<<need < sh.blocks ? need : sh.blocks, RT_BLOCK, 0, ctx->stream>>>(pp, w.ray_a[0], w.ray_b[0], w.hit[0],
+                                                                                 w.throughput, w.radiance, w.counts);
+}
+
+void launch_extend(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int bounce) {
+  LaunchShape sh = rt_persistent_shape(ctx, RT_BLOCK, 8);
+  int need = ceil_div(pp.n_paths, RT_BLOCK);
+  int b = bounce & 1;
+  k_extend<<<need < sh.blocks ? need : sh.blocks, RT_BLOCK, 0, ctx->stream>>>(sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b],
+                                                                              w.counts, bounce, sc.n_media > 0, w.stats);
+}
+
+void launch_shade(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int bounce) {
+  LaunchShape sh = rt_persistent_shape(ctx, RT_BLOCK, 8);
+  int need = ceil_div(pp.n_paths, RT_BLOCK);
+  int b = bounce & 1, nb = b ^ 1;
+  k_shade<<<need < sh.blocks ? need : sh.blocks, RT_BLOCK, 0, ctx->stream>>>(sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b],
+                                                                             w.ray_a[nb], w.ray_b[nb], w.hit[nb],
+                                                                             w.throughput, w.radiance, w.counts, bounce);
+}
+
+void launch_accumulate(const rt_context *ctx, const PassParams &pp, WaveBuffers &w, float4 *film) {
+  LaunchShape sh = rt_persistent_shape(ctx, 256, 8);
+  int need = ceil_div(pp.n_owned, 256);
+  k_accumulate<<<need < sh.blocks ? need : sh.blocks, 256, 0, ctx->stream>>>(w.radiance, pp.n_owned, pp.n_samples, film);
+}
+
+void launch_resolve_rgb8(cudaStream_t s, const float4 *film, int64_t n, double scale, uint8_t *out) {
+  if (n > 0)
+    k_resolve_rgb8<<<ceil_div(n, 256) < 4096 ? ceil_div(n, 256) : 4096, 256, 0, s>>>(film, n, scale, out);
+}
+
+void launch_resolve_rgb(cudaStream_t s, const float4 *film, int64_t n, double scale, float *out) {
+  if (n > 0)
+    k_resolve_rgb<<<ceil_div(n, 256) < 4096 ? ceil_div(n, 256) : 4096, 256, 0, s>>>(film, n, scale, out);
+}
+
+void launch_scatter_gathered(cudaStream_t s, int width, int height, int n_ranks, int tile_rows, const float4 *gathered,
+                             float4 *full) {
+  long long total = (long long)width * height;
+  if (total > 0)
+    k_scatter_gathered<<<ceil_div(total, 256) < 4096 ? ceil_div(total, 256) : 4096, 256, 0, s>>>(
+        width, height, n_ranks, tile_rows, gathered, full);
+}
+
+void launch_trace_fast(const rt_context *ctx, const DScene &sc, const rt_ray *d_rays, int64_t n, uint64_t seed,
+                       const int *leaf_object, const int *leaf_id, rt_hit *d_hits) {
+  if (n <= 0)
+    return;
+  LaunchShape sh = rt_persistent_shape(ctx, RT_BLOCK, 8);
+  int need = ceil_div(n, RT_BLOCK);
+  k_trace_fast<<<need < sh.blocks ? need : sh.blocks, RT_BLOCK, 0, ctx->stream>>>(sc, d_rays, n, seed, leaf_object,
+                                                                                  leaf_id, d_hits);
+}

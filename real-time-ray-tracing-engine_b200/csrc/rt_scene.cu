@@ -1,0 +1,235 @@
+// rt_scene.cu — scene upload: flat description -> device SoA records + GPU-built BVH4.
+//
+// Replaces initialize_cuda_scene and the per-object converters (scene/CudaSceneInitialization.cuh:249-299,
+// core/HittableConverter.cuh:50-111): instead of mirroring the object graph node by node with one
+// cudaMemcpy each, instance chains are baked into world-space primitives on the host in FP64, every
+// array is uploaded once, and the hierarchy is built on the device (Morton sort + Karras + refit +
+// 4-wide collapse, rt_bvh.h).
+#include "rt_internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+#include "rt_flatten.h"
+
+using namespace rtflat;
+
+namespace {
+
+template <class T> int upload(T **dst, const std::vector<T> &src, size_t min_count = 1) {
+  size_t n = std::max(src.size(), min_count);
+  RT_CUDA(cudaMalloc((void **)dst, n * sizeof(T)));
+  RT_CUDA(cudaMemset(*dst, 0, n * sizeof(T)));
+  if (!src.empty())
+    RT_CUDA(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return RT_OK;
+}
+
+struct Scratch { // frees build scratch on every exit path
+  std::vector<void *> ptrs;
+  ~Scratch() {
+    for (void *p : ptrs)
+      cudaFree(p);
+  }
+  template <class T> cudaError_t alloc(T **p, size_t count) {
+    cudaError_t e = cudaMalloc((void **)p, std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess)
+      ptrs.push_back(*p);
+    return e;
+  }
+};
+
+} // namespace
+
+int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
+  Flat f;
+  int st = flatten(desc, f);
+  if (st != RT_OK)
+    return st;
+  const int n = (int)f.boxes.size();
+  sc->ctx = ctx;
+  sc->n_leaf = n;
+  cudaStream_t s = ctx->stream;
+
+  // everything that does not depend on leaf order
+  if ((st = upload(&sc->bprims, f.bprims)) || (st = upload(&sc->mats, f.mats)) || (st = upload(&sc->lights, f.lights)) ||
+      (st = upload(&sc->perlin_grad, f.perlin_grad)) || (st = upload(&sc->perlin_perm, f.perlin_perm)) ||
+      (st = upload(&sc->ex_bprims, f.ex_bprims)) || (st = upload(&sc->ex_ops, f.ops)) ||
+      (st = upload(&sc->ex_chain_first, f.chain_first)) || (st = upload(&sc->ex_chain_count, f.chain_count)))
+    return st;
+
+  std::vector<BuildBox> boxes(n);
+  BoxD all, centroids;
+  for (int i = 0; i < n; i++) {
+    boxes[i] = to_build_box(f.boxes[i]);
+    all.grow(f.boxes[i]);
+    centroids.grow(D3{0.5 * (boxes[i].lo[0] + boxes[i].hi[0]), 0.5 * (boxes[i].lo[1] + boxes[i].hi[1]),
+                      0.5 * (boxes[i].lo[2] + boxes[i].hi[2])});
+  }
+
+  const int n_wide_cap = std::max(n, 1);
+  RT_CUDA(cudaMalloc((void **)&sc->nodes, (size_t)n_wide_cap * RT_NODE_F4 * sizeof(float4)));
+  RT_CUDA(cudaMalloc((void **)&sc->prims, (size_t)std::max(n, 1) * RT_PRIM_F4 * sizeof(float4)));
+  RT_CUDA(cudaMalloc((void **)&sc->ex_prims, (size_t)std::max(n, 1) * sizeof(PrimExact)));
+  RT_CUDA(cudaMalloc((void **)&sc->leaf_object, (size_t)std::max(n, 1) * sizeof(int)));
+  RT_CUDA(cudaMalloc((void **)&sc->leaf_id, (size_t)std::max(n, 1) * sizeof(int)));
+
+  cudaEvent_t ev0, ev1;
+  RT_CUDA(cudaEventCreate(&ev0));
+  RT_CUDA(cudaEventCreate(&ev1));
+  int n_wide = 1;
+  std::vector<uint32_t> order(n);
+
+  if (n <= 1) {
+    // degenerate trees: one wide node with zero or one leaf child
+    std::vector<float4> node(RT_NODE_F4);
+    const float inf = std::numeric_limits<float>::infinity();
+    for (int a = 0; a < 3; a++) {
+      node[2 * a] = make_float4(n ? boxes[0].lo[a] : inf, inf, inf, inf);
+      node[2 * a + 1] = make_float4(n ? boxes[0].hi[a] : -inf, -inf, -inf, -inf);
+    }
+    node[6] = make_float4(ibits(n ? ~0 : RT_EMPTY), ibits(RT_EMPTY), ibits(RT_EMPTY), ibits(RT_EMPTY));
+    node[7] = make_float4(0.f, 0.f, 0.f, 0.f);
+    RT_CUDA(cudaMemcpy(sc->nodes, node.data(), sizeof(float4) * RT_NODE_F4, cudaMemcpyHostToDevice));
+    if (n) {
+      RT_CUDA(cudaMemcpy(sc->prims, f.prims.data(), sizeof(float4) * RT_PRIM_F4, cudaMemcpyHostToDevice));
+      RT_CUDA(cudaMemcpy(sc->ex_prims, f.ex_prims.data(), sizeof(PrimExact), cudaMemcpyHostToDevice));
+      order[0] = 0;
+    }
+    sc->info.build_ms = 0.0;
+  } else {
+    Scratch scratch;
+    BuildBox *d_boxes = nullptr, *d_sorted_boxes = nullptr;
+    float4 *d_prims_in = nullptr;
+    PrimExact *d_ex_in = nullptr;
+    uint64_t *d_codes = nullptr, *d_codes_sorted = nullptr;
+    uint32_t *d_index = nullptr, *d_index_sorted = nullptr;
+    float *d_bounds = nullptr;
+    BinTree t{};
+    CollapseItem *d_items[2] = {nullptr, nullptr};
+    int *d_counters = nullptr; // [0] next queue length  [1] wide node count
+    RT_CUDA(scratch.alloc(&d_boxes, n));
+    RT_CUDA(scratch.alloc(&d_sorted_boxes, n));
+    RT_CUDA(scratch.alloc(&d_prims_in, (size_t)n * RT_PRIM_F4));
+    RT_CUDA(scratch.alloc(&d_ex_in, n));
+    RT_CUDA(scratch.alloc(&d_codes, n));
+    RT_CUDA(scratch.alloc(&d_codes_sorted, n));
+    RT_CUDA(scratch.alloc(&d_index, n));
+    RT_CUDA(scratch.alloc(&d_index_sorted, n));
+    RT_CUDA(scratch.alloc(&d_bounds, 6));
+    RT_CUDA(scratch.alloc(&t.left, n - 1));
+    RT_CUDA(scratch.alloc(&t.right, n - 1));
+    RT_CUDA(scratch.alloc(&t.parent, 2 * n - 1));
+    RT_CUDA(scratch.alloc(&t.box, n - 1));
+    RT_CUDA(scratch.alloc(&t.visits, n - 1));
+    RT_CUDA(scratch.alloc(&d_items[0], n));
+    RT_CUDA(scratch.alloc(&d_items[1], n));
+    RT_CUDA(scratch.alloc(&d_counters, 2));
+    t.n = n;
+
+    float bounds[6];
+    for (int a = 0; a < 3; a++) {
+      bounds[a] = (float)centroids.lo[a];
+      double ext = centroids.hi[a] - centroids.lo[a];
+      bounds[3 + a] = ext > 0 ? (float)(1.0 / ext) : 0.f;
+    }
+    RT_CUDA(cudaMemcpyAsync(d_boxes, boxes.data(), sizeof(BuildBox) * n, cudaMemcpyHostToDevice, s));
+    RT_CUDA(cudaMemcpyAsync(d_prims_in, f.prims.data(), sizeof(float4) * RT_PRIM_F4 * n, cudaMemcpyHostToDevice, s));
+    RT_CUDA(cudaMemcpyAsync(d_ex_in, f.ex_prims.data(), sizeof(PrimExact) * n, cudaMemcpyHostToDevice, s));
+    RT_CUDA(cudaMemcpyAsync(d_bounds, bounds, sizeof bounds, cudaMemcpyHostToDevice, s));
+    RT_CUDA(cudaMemsetAsync(t.visits, 0, sizeof(unsigned int) * (n - 1), s));
+
+    RT_CUDA(cudaEventRecord(ev0, s));
+    launch_morton(s, d_boxes, n, d_bounds, d_bounds + 3, d_codes, d_index);
+    if ((st = sort_pairs(s, d_codes, d_codes_sorted, d_index, d_index_sorted, n)))
+      return st;
+    launch_gather_boxes(s, d_boxes, d_index_sorted, d_sorted_boxes, n);
+    launch_gather_records(s, d_prims_in, d_index_sorted, sc->prims, n, RT_PRIM_F4 * (int)sizeof(float4));
+    static_assert(sizeof(PrimExact) % 16 == 0, "PrimExact must be a multiple of 16 bytes");
+    launch_gather_records(s, d_ex_in, d_index_sorted, sc->ex_prims, n, (int)sizeof(PrimExact));
+    launch_hierarchy(s, d_codes_sorted, t);
+    launch_refit(s, t, d_sorted_boxes);
+
+    // collapse, level by level; the root binary node 0 becomes wide node 0
+    CollapseItem root{0, 0};
+    int counters[2] = {0, 1};
+    RT_CUDA(cudaMemcpyAsync(d_items[0], &root, sizeof root, cudaMemcpyHostToDevice, s));
+    RT_CUDA(cudaMemcpyAsync(d_counters, counters, sizeof counters, cudaMemcpyHostToDevice, s));
+    int n_items = 1, cur = 0;
+    while (n_items > 0) {
+      RT_CUDA(cudaMemsetAsync(d_counters, 0, sizeof(int), s)); // next level's queue length
+      launch_collapse(s, t, d_sorted_boxes, sc->nodes, d_items[cur], n_items, d_items[cur ^ 1], d_counters,
+                      d_counters + 1);
+      RT_CUDA(cudaMemcpyAsync(counters, d_counters, sizeof counters, cudaMemcpyDeviceToHost, s));
+      RT_CUDA(cudaStreamSynchronize(s));
+      n_items = counters[0];
+      cur ^= 1;
+    }
+    n_wide = counters[1];
+    RT_CUDA(cudaEventRecord(ev1, s));
+    RT_CUDA(cudaEventSynchronize(ev1));
+    float ms = 0.f;
+    RT_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    sc->info.build_ms = ms;
+    RT_CUDA(cudaMemcpy(order.data(), d_index_sorted, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+    RT_CUDA(cudaGetLastError());
+  }
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+
+  // per-leaf object / id tables in leaf order
+  std::vector<int> leaf_object(std::max(n, 1), -1), leaf_id(std::max(n, 1), -1);
+  for (int j = 0; j < n; j++) {
+    leaf_object[j] = f.ex_prims[order[j]].object;
+    leaf_id[j] = f.ex_prims[order[j]].id;
+  }
+  RT_CUDA(cudaMemcpy(sc->leaf_object, leaf_object.data(), sizeof(int) * leaf_object.size(), cudaMemcpyHostToDevice));
+  RT_CUDA(cudaMemcpy(sc->leaf_id, leaf_id.data(), sizeof(int) * leaf_id.size(), cudaMemcpyHostToDevice));
+
+  sc->d.nodes = sc->nodes;
+  sc->d.prims = sc->prims;
+  sc->d.bprims = sc->bprims;
+  sc->d.mats = sc->mats;
+  sc->d.lights = sc->lights;
+  sc->d.perlin_grad = sc->perlin_grad;
+  sc->d.perlin_perm = sc->perlin_perm;
+  sc->d.n_prims = n;
+  sc->d.n_lights = desc->n_lights;
+  sc->d.n_media = desc->n_media;
+  sc->d.bg[0] = sc->d.bg[1] = sc->d.bg[2] = 0.f; // set per render from the camera
+  sc->ex.nodes = sc->nodes;
+  sc->ex.prims = sc->ex_prims;
+  sc->ex.bprims = sc->ex_bprims;
+  sc->ex.ops = sc->ex_ops;
+  sc->ex.chain_first = sc->ex_chain_first;
+  sc->ex.chain_count = sc->ex_chain_count;
+
+  sc->info.n_prims = n;
+  sc->info.n_nodes = n_wide;
+  sc->info.node_bytes = (int64_t)n_wide * RT_NODE_F4 * (int64_t)sizeof(float4);
+  sc->info.prim_bytes = (int64_t)n * RT_PRIM_F4 * (int64_t)sizeof(float4);
+  for (int a = 0; a < 3; a++) {
+    sc->info.bounds_min[a] = n ? all.lo[a] : 0.0;
+    sc->info.bounds_max[a] = n ? all.hi[a] : 0.0;
+  }
+  return RT_OK;
+}
+
+void rt_scene_release(rt_scene *sc) {
+  cudaFree(sc->nodes);
+  cudaFree(sc->prims);
+  cudaFree(sc->bprims);
+  cudaFree(sc->mats);
+  cudaFree(sc->lights);
+  cudaFree(sc->perlin_grad);
+  cudaFree(sc->perlin_perm);
+  cudaFree(sc->ex_prims);
+  cudaFree(sc->ex_bprims);
+  cudaFree(sc->ex_ops);
+  cudaFree(sc->ex_chain_first);
+  cudaFree(sc->ex_chain_count);
+  cudaFree(sc->leaf_object);
+  cudaFree(sc->leaf_id);
+}

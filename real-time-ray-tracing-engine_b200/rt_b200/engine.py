@@ -1,0 +1,144 @@
+"""Thin object wrappers over the C ABI of librt_b200.so (include/rt_b200.h).
+
+The class names follow the reference's render drivers: a `Context` is one GPU, a `Scene` the uploaded
+world + BVH (initialize_cuda_scene), a `Film` the accumulation buffer of a Static/Dynamic camera, and
+`render_static` / `render_accumulate` the two launch wrappers the reference's cameras call
+(core/camera/CameraKernelWrappers.cuh:15-32).  All compute happens in the CUDA library; importing this
+module without it raises (no CPU fallback).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+
+
+class Context:
+    def __init__(self, device=0):
+        self.lib = abi.load_library()
+        h = C.c_void_p()
+        abi.check(self.lib, self.lib.rt_context_create(device, C.byref(h)), "rt_context_create")
+        self._h = h
+        self.device = device
+
+    @property
+    def stream(self):
+        """cudaStream_t of the context as an integer."""
+        return self.lib.rt_context_stream(self._h)
+
+    def synchronize(self):
+        abi.check(self.lib, self.lib.rt_context_synchronize(self._h), "rt_context_synchronize")
+
+    def counters(self):
+        c = abi.rt_counters()
+        abi.check(self.lib, self.lib.rt_get_counters(self._h, C.byref(c)), "rt_get_counters")
+        return c
+
+    def reset_counters(self):
+        abi.check(self.lib, self.lib.rt_reset_counters(self._h), "rt_reset_counters")
+
+    def close(self):
+        if self._h:
+            self.lib.rt_context_destroy(self._h)
+            self._h = None
+
+
+class Scene:
+    def __init__(self, ctx, desc):
+        """desc: rt_scene_desc or a pointer to one (e.g. HostScene.desc)."""
+        self.ctx = ctx
+        self.lib = ctx.lib
+        h = C.c_void_p()
+        ptr = desc if isinstance(desc, C.POINTER(abi.rt_scene_desc)) else C.pointer(desc)
+        abi.check(self.lib, self.lib.rt_scene_create(ctx._h, ptr, C.byref(h)), "rt_scene_create")
+        self._h = h
+
+    def info(self):
+        i = abi.rt_scene_info()
+        abi.check(self.lib, self.lib.rt_scene_get_info(self._h, C.byref(i)), "rt_scene_get_info")
+        return i
+
+    def trace(self, rays, mode=abi.RT_TRACE_EXACT_F64, seed=0):
+        """rays: ctypes array of rt_ray.  Returns a ctypes array of rt_hit."""
+        n = len(rays)
+        hits = (abi.rt_hit * n)()
+        abi.check(self.lib, self.lib.rt_trace_rays(self._h, rays, n, mode, seed, hits), "rt_trace_rays")
+        return hits
+
+    def close(self):
+        if self._h:
+            self.lib.rt_scene_destroy(self._h)
+            self._h = None
+
+
+def camera_from_config(cfg):
+    lib = abi.load_library()
+    cam = abi.rt_camera()
+    abi.check(lib, lib.rt_camera_init(C.byref(cfg), C.byref(cam)), "rt_camera_init")
+    return cam
+
+
+class Film:
+    def __init__(self, ctx, width, height, rank=0, n_ranks=1, tile_rows=8, external_accum=None):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        self.width, self.height = width, height
+        self.rank, self.n_ranks, self.tile_rows = rank, n_ranks, tile_rows
+        h = C.c_void_p()
+        ext = C.c_void_p(external_accum) if external_accum else None
+        abi.check(self.lib, self.lib.rt_film_create(ctx._h, width, height, rank, n_ranks, tile_rows, ext, C.byref(h)),
+                  "rt_film_create")
+        self._h = h
+
+    @property
+    def owned_pixels(self):
+        return self.lib.rt_film_owned_pixels(self._h)
+
+    @property
+    def samples(self):
+        return self.lib.rt_film_samples(self._h)
+
+    @property
+    def device_ptr(self):
+        return self.lib.rt_film_device_ptr(self._h)
+
+    def clear(self):
+        abi.check(self.lib, self.lib.rt_film_clear(self._h), "rt_film_clear")
+
+    def read_rgb(self, scale):
+        out = np.empty((self.owned_pixels, 3), dtype=np.float32)
+        abi.check(self.lib, self.lib.rt_film_read_rgb(self._h, scale, out.ctypes.data_as(C.POINTER(C.c_float))),
+                  "rt_film_read_rgb")
+        return out
+
+    def resolve_rgb8(self, scale, out=None):
+        if out is None:
+            out = np.empty((self.owned_pixels, 3), dtype=np.uint8)
+        abi.check(self.lib, self.lib.rt_film_resolve_rgb8(self._h, scale, out.ctypes.data_as(C.POINTER(C.c_uint8))),
+                  "rt_film_resolve_rgb8")
+        return out
+
+    def owned_rows(self):
+        """Global scanline index of every owned row, in storage order."""
+        rows = []
+        n_tiles = (self.height + self.tile_rows - 1) // self.tile_rows
+        for t in range(self.rank, n_tiles, self.n_ranks):
+            rows.extend(range(t * self.tile_rows, min((t + 1) * self.tile_rows, self.height)))
+        return np.asarray(rows, dtype=np.int64)
+
+    def close(self):
+        if self._h:
+            self.lib.rt_film_destroy(self._h)
+            self._h = None
+
+
+def render_accumulate(scene, camera, film, s_i, s_j, sqrt_spp, max_depth, seed):
+    """One progressive frame (cuda_dynamic_render_tile_wrapper semantics, whole frame).  Asynchronous."""
+    abi.check(scene.lib, scene.lib.rt_render_accumulate(scene._h, C.byref(camera), film._h, s_i, s_j, sqrt_spp,
+                                                        max_depth, seed), "rt_render_accumulate")
+
+
+def render_static(scene, camera, film, sqrt_spp, max_depth, seed):
+    """All sqrt_spp^2 strata (cuda_static_render_wrapper semantics).  Asynchronous."""
+    abi.check(scene.lib, scene.lib.rt_render_static(scene._h, C.byref(camera), film._h, sqrt_spp, max_depth, seed),
+              "rt_render_static")

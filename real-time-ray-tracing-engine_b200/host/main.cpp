@@ -1,0 +1,152 @@
+// raytracer — the host program: the reference's CLI (src/main.cpp:133-173) in front of the B200
+// backend.  Static camera: renders the image and writes output/<file> as ASCII PPM
+// (StaticCamera::render, core/camera/StaticCamera.cpp:25-57,94-99).  Dynamic camera: the reference
+// opens an SDL3 window and adds one stratum per frame (DynamicCamera.cpp:103-194); SDL3 is not
+// available in this build, so the dynamic camera runs headless: it renders the progressive frames,
+// resolves each to RGB8 exactly as update_texture does (:280-306), reports per-frame times and writes the
+// last frame.  Images are partitioned over --gpus devices by interleaved scanline tiles and gathered over
+// NVLink peer copies.  There is no CPU rendering path: without a CUDA device the program fails.
+#include "../../include/rt_b200.h"
+#include "../../include/rt_host.h"
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <sys/stat.h>
+#include <vector>
+
+#define CHECK(call)                                                                                          \
+  do {                                                                                                       \
+    int st_ = (call);                                                                                        \
+    if (st_ != RT_OK) {                                                                                      \
+      std::fprintf(stderr, "[ERROR] %s failed (%d): %s\n", #call, st_, rt_last_error());                      \
+      return 1;                                                                                              \
+    }                                                                                                        \
+  } while (0)
+
+static double now_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+int main(int argc, char **argv) {
+  rth_cli_options opt;
+  if (rth_cli_parse(argc, argv, &opt) != 0) {
+    std::fprintf(stderr, "%s", rth_last_error());
+    std::fputs(rth_cli_help(), stdout);
+    return 1;
+  }
+  if (opt.help) {
+    std::fputs(rth_cli_help(), stdout);
+    return 0;
+  }
+  std::string scene_name = opt.scene;
+  bool is_file = scene_name.size() > 5 && scene_name.substr(scene_name.size() - 5) == ".json";
+  rth_scene *hs = is_file ? rth_scene_load_json(scene_name.c_str()) : rth_scene_builtin(scene_name.c_str(), opt.seed, 0, -1);
+  if (!hs) {
+    std::fprintf(stderr, "[ERROR] %s\n", rth_last_error());
+    return 1;
+  }
+  if (opt.debug) {
+    mkdir("logs", 0755);
+    rth_scene_save_json(hs, "logs/scene_debug.json");
+    std::fprintf(stderr, "[DEBUG] scene written to logs/scene_debug.json\n");
+  }
+  rt_camera_config cfg;
+  rth_scene_camera(hs, opt.width, opt.samples, opt.depth, &cfg);
+  rt_camera cam;
+  CHECK(rt_camera_init(&cfg, &cam));
+  const int W = cam.image_width, H = cam.image_height;
+  const int sqrt_spp = int(std::sqrt(double(opt.samples))); // Camera.cpp:209
+  const int n_gpus = opt.gpus;
+  if (rt_device_count() < n_gpus) {
+    std::fprintf(stderr, "[ERROR] %d CUDA device(s) requested, %d available; there is no CPU fallback\n", n_gpus,
+                 rt_device_count());
+    return 1;
+  }
+
+  std::vector<rt_context *> ctx(n_gpus);
+  std::vector<rt_scene *> scene(n_gpus);
+  std::vector<rt_film *> film(n_gpus);
+  const int tile_rows = 8;
+  for (int g = 0; g < n_gpus; g++) {
+    CHECK(rt_context_create(g, &ctx[g]));
+    CHECK(rt_scene_create(ctx[g], rth_scene_desc(hs), &scene[g])); // the scene is replicated on every GPU
+    CHECK(rt_film_create(ctx[g], W, H, g, n_gpus, tile_rows, nullptr, &film[g]));
+  }
+  rt_scene_info info;
+  CHECK(rt_scene_get_info(scene[0], &info));
+  std::fprintf(stderr, "[INFO] scene %s: %lld primitives, %lld BVH4 nodes, device build %.2f ms; image %dx%d, %d spp, depth %d, %d GPU(s)\n",
+               opt.scene, (long long)info.n_prims, (long long)info.n_nodes, info.build_ms, W, H, sqrt_spp * sqrt_spp,
+               opt.depth, n_gpus);
+
+  std::vector<float> rgb((size_t)W * H * 3);
+  std::vector<uint8_t> rgb8((size_t)W * H * 3);
+  auto to_bytes = [&](void) {
+    for (size_t k = 0; k < rgb.size(); k++) { // to_byte (utils/ColorUtility.hpp:18-26)
+      double v = rgb[k];
+      double x = v > 0 ? std::sqrt(v) : 0;
+      x = x < 0.0 ? 0.0 : (x > 0.999 ? 0.999 : x);
+      rgb8[k] = (uint8_t)(256 * x);
+    }
+  };
+
+  double t0 = now_ms();
+  if (!opt.camera_dynamic) {
+    for (int g = 0; g < n_gpus; g++)
+      CHECK(rt_render_static(scene[g], &cam, film[g], sqrt_spp, opt.depth, opt.seed));
+    if (n_gpus == 1) {
+      CHECK(rt_film_resolve_rgb8(film[0], 1.0 / opt.samples, rgb8.data())); // pixel_samples_scale = 1/spp
+    } else {
+      CHECK(rt_film_gather_p2p(film.data(), n_gpus, 1.0 / opt.samples, rgb.data()));
+      to_bytes();
+    }
+    double t1 = now_ms();
+    long long paths = (long long)W * H * sqrt_spp * sqrt_spp;
+    std::fprintf(stderr, "[INFO] rendered %lld path samples in %.1f ms (%.1f Mpath-samples/s)\n", paths, t1 - t0,
+                 paths / (t1 - t0) / 1e3);
+    mkdir("output", 0755);
+    std::string path = std::string("output/") + opt.output;
+    if (rth_write_ppm_p3(path.c_str(), W, H, rgb8.data()) != 0) {
+      std::fprintf(stderr, "[ERROR] %s\n", rth_last_error());
+      return 1;
+    }
+    std::fprintf(stderr, "[INFO] wrote %s\n", path.c_str());
+  } else {
+    int frames = opt.frames > 0 ? opt.frames : sqrt_spp * sqrt_spp;
+    int taken = 0;
+    for (int f = 0; f < frames; f++) {
+      double f0 = now_ms();
+      int s = taken % (sqrt_spp * sqrt_spp);
+      for (int g = 0; g < n_gpus; g++)
+        CHECK(rt_render_accumulate(scene[g], &cam, film[g], s % sqrt_spp, s / sqrt_spp, sqrt_spp, opt.depth,
+                                   opt.seed + (uint64_t)(taken / (sqrt_spp * sqrt_spp))));
+      taken++;
+      double scale = 1.0 / std::max(1, taken); // DynamicCamera.cpp:285
+      if (n_gpus == 1) {
+        CHECK(rt_film_resolve_rgb8(film[0], scale, rgb8.data()));
+      } else {
+        CHECK(rt_film_gather_p2p(film.data(), n_gpus, scale, rgb.data()));
+        to_bytes();
+      }
+      double f1 = now_ms();
+      if (f < 5 || f == frames - 1)
+        std::fprintf(stderr, "[INFO] frame %d: %.3f ms (%.1f FPS)\n", f, f1 - f0, 1000.0 / (f1 - f0));
+    }
+    mkdir("output", 0755);
+    std::string path = std::string("output/") + opt.output;
+    rth_write_ppm_p3(path.c_str(), W, H, rgb8.data());
+    std::fprintf(stderr, "[INFO] %d progressive frames in %.1f ms; last frame written to %s\n", frames, now_ms() - t0,
+                 path.c_str());
+  }
+  for (int g = 0; g < n_gpus; g++) {
+    rt_film_destroy(film[g]);
+    rt_scene_destroy(scene[g]);
+    rt_context_destroy(ctx[g]);
+  }
+  rth_scene_free(hs);
+  return 0;
+}

@@ -1,0 +1,108 @@
+"""The per-thread device functions of csrc/ (rt_device.h, rt_exact.h, rt_bvh.h, rt_flatten.h) compiled for
+the host (tests/emu, a TEST build) and checked against the oracle: scene flattening, the LBVH build logic,
+FP64 parity traversal, FP32 traversal and the shading arithmetic.  CPU only.  The GPU tests run the same
+checks against the real kernels through the C ABI."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from conftest import oracle_segments
+from rt_b200 import abi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "emu")])
+    em = C.CDLL(os.path.join(HERE, "emu", "libemu.so"))
+    em.emu_scene_create.restype = C.c_void_p
+    em.emu_scene_create.argtypes = [C.POINTER(abi.rt_scene_desc)]
+    em.emu_scene_destroy.argtypes = [C.c_void_p]
+    em.emu_trace.argtypes = [C.c_void_p, C.POINTER(abi.rt_ray), C.c_int64, C.c_int, C.c_uint64, C.POINTER(abi.rt_hit)]
+    for f in ("emu_scene_check_bvh", "emu_scene_nodes", "emu_scene_leaves"):
+        getattr(em, f).argtypes = [C.c_void_p]
+    em.emu_render.argtypes = [C.c_void_p, C.POINTER(abi.rt_camera), C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64,
+                              C.c_double, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
+    return em
+
+
+CASES = [("spheres", 11, -1, 96), ("spheres", 40, -1, 64), ("spheres_textured", 12, -1, 64), ("cornell", 0, -1, 48),
+         ("cornell_smoke", 0, -1, 48), ("final", 5, 60, 64)]
+
+
+@pytest.mark.parametrize("name,p0,p1,width", CASES)
+def test_flatten_build_trace_shade(oracle, emu, host_scenes, name, p0, p1, width):
+    hs = host_scenes(name, p0, p1)
+    desc = hs.desc
+    cfg = hs.camera_config(width, 4, 8)
+    es = emu.emu_scene_create(desc)
+    assert es
+    n_leaf = desc.contents.n_objects if name != "final" and "cornell" not in name else emu.emu_scene_leaves(es)
+    assert emu.emu_scene_leaves(es) == n_leaf
+    assert emu.emu_scene_check_bvh(es) == 0  # every leaf once, children inside parents
+    assert emu.emu_scene_nodes(es) <= max(1, emu.emu_scene_leaves(es) - 1)
+    osc = oracle.ora_scene_create(desc)
+    img, rays, cnt = oracle_segments(oracle, osc, cfg, ol.ORA_RNG_PHILOX, ol.ORA_SAMPLER_POLAR, 42, 1)
+    n = len(rays)
+    want = (abi.rt_hit * n)()
+    oracle.ora_trace(osc, rays, n, 1, ol.ORA_RNG_PHILOX, 42, want)
+    exact, fast = (abi.rt_hit * n)(), (abi.rt_hit * n)()
+    emu.emu_trace(es, rays, n, abi.RT_TRACE_EXACT_F64, 42, exact)
+    emu.emu_trace(es, rays, n, abi.RT_TRACE_FAST_F32, 42, fast)
+    a, b, c = ol.hits_to_numpy(want), ol.hits_to_numpy(exact), ol.hits_to_numpy(fast)
+    assert np.array_equal(a["prim"], b["prim"]) and np.array_equal(a["object"], b["object"])
+    assert np.array_equal(a["front_face"], b["front_face"])
+    assert np.array_equal(a["t"], b["t"])  # host libm == oracle libm, so even medium hits are bit-exact here
+    assert (a["prim"] != c["prim"]).mean() < 2e-3  # FP32: only silhouette / grazing rays may flip
+    # FP32 wavefront arithmetic follows the oracle's FP64 paths (same Philox stream)
+    cam = abi.rt_camera()
+    oracle.ora_camera_init(C.byref(cfg), C.byref(cam))
+    npix = cam.image_width * cam.image_height
+    out = (C.c_float * (npix * 3))()
+    segs = C.c_uint64()
+    emu.emu_render(es, C.byref(cam), 0, 4, 2, 8, 42, 0.25, out, C.byref(segs))
+    got = np.frombuffer(out, dtype=np.float32).reshape(-1, 3).astype(np.float64)
+    follows = np.abs(got - img).max(axis=1) < 2e-3
+    assert follows.mean() > 0.97
+    assert abs(got.mean() - img.mean()) < 0.01 * img.mean()
+    emu.emu_scene_destroy(es)
+    oracle.ora_scene_destroy(osc)
+
+
+def test_degenerate_scenes(emu):
+    # empty scene and single-primitive scene build valid one-node trees
+    empty = abi.rt_scene_desc()
+    es = emu.emu_scene_create(C.byref(empty))
+    assert es and emu.emu_scene_leaves(es) == 0 and emu.emu_scene_check_bvh(es) == 0
+    ray = (abi.rt_ray * 1)()
+    ray[0].direction[:] = (0, 0, -1)
+    ray[0].t_min, ray[0].t_max = 0.001, float("inf")
+    hit = (abi.rt_hit * 1)()
+    for mode in (0, 1):
+        emu.emu_trace(es, ray, 1, mode, 0, hit)
+        assert hit[0].prim == -1 and hit[0].t == float("inf")
+    emu.emu_scene_destroy(es)
+
+    sph = abi.rt_sphere(radius=0.5, material=0, xform=-1, object=0)
+    sph.center0[:] = (0, 0, -2)
+    mat = abi.rt_material(type=abi.RT_MAT_LAMBERTIAN, texture=0)
+    tex = abi.rt_texture(type=abi.RT_TEX_SOLID, even=-1, odd=-1, perlin=-1)
+    one = abi.rt_scene_desc(n_spheres=1, n_materials=1, n_textures=1, n_objects=1, spheres=C.pointer(sph),
+                            materials=C.pointer(mat), textures=C.pointer(tex))
+    es = emu.emu_scene_create(C.byref(one))
+    assert es and emu.emu_scene_leaves(es) == 1 and emu.emu_scene_check_bvh(es) == 0
+    for mode in (0, 1):
+        emu.emu_trace(es, ray, 1, mode, 0, hit)
+        assert hit[0].prim == 0 and abs(hit[0].t - 1.5) < 1e-6
+    emu.emu_scene_destroy(es)
+
+
+def test_invalid_scenes_are_rejected(emu):
+    sph = abi.rt_sphere(radius=0.5, material=3, xform=-1, object=0)  # material index out of range
+    bad = abi.rt_scene_desc(n_spheres=1, n_objects=1, spheres=C.pointer(sph))
+    assert not emu.emu_scene_create(C.byref(bad))

@@ -79,6 +79,35 @@ DCamera to_device_camera(const rt_camera *c) {
   return d;
 }
 
+cudaEvent_t timer_event(StageTimer &t) {
+  if (t.next == t.pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    t.pool.push_back(e);
+  }
+  return t.pool[t.next++];
+}
+
+// Brackets one launch with events when stage timing is on.
+struct StageSpan {
+  rt_context *ctx;
+  int stage;
+  cudaEvent_t begin = nullptr;
+  StageSpan(rt_context *c, int s) : ctx(c), stage(s) {
+    if (ctx->timer.enabled) {
+      begin = timer_event(ctx->timer);
+      cudaEventRecord(begin, ctx->stream);
+    }
+  }
+  ~StageSpan() {
+    if (begin) {
+      cudaEvent_t end = timer_event(ctx->timer);
+      cudaEventRecord(end, ctx->stream);
+      ctx->timer.spans.push_back({stage, {begin, end}});
+    }
+  }
+};
+
 // One wavefront pass over `n_samples` strata starting at linear stratum `first_sample`.
 int render_pass(rt_scene *scene, const rt_camera *camera, rt_film *film, int first_sample, int n_samples,
                 int sqrt_spp, int max_depth, uint64_t seed) {
@@ -104,12 +133,24 @@ int render_pass(rt_scene *scene, const rt_camera *camera, rt_film *film, int fir
     sc.bg[a] = (float)camera->background[a];
   WaveBuffers &w = ctx->wave;
   RT_CUDA(cudaMemsetAsync(w.counts, 0, ((size_t)max_depth + 2) * sizeof(unsigned int), ctx->stream));
-  launch_generate(ctx, pp, w);
-  for (int bounce = 0; bounce < max_depth; bounce++) {
-    launch_extend(ctx, sc, pp, w, bounce);
-    launch_shade(ctx, sc, pp, w, bounce);
+  {
+    StageSpan span(ctx, RT_STAGE_GENERATE);
+    launch_generate(ctx, pp, w);
   }
-  launch_accumulate(ctx, pp, w, film->accum);
+  for (int bounce = 0; bounce < max_depth; bounce++) {
+    {
+      StageSpan span(ctx, RT_STAGE_EXTEND);
+      launch_extend(ctx, sc, pp, w, bounce);
+    }
+    {
+      StageSpan span(ctx, RT_STAGE_SHADE);
+      launch_shade(ctx, sc, pp, w, bounce);
+    }
+  }
+  {
+    StageSpan span(ctx, RT_STAGE_ACCUMULATE);
+    launch_accumulate(ctx, pp, w, film->accum);
+  }
   ctx->counters.kernel_launches += 2 + 2 * (uint64_t)max_depth;
   ctx->counters.paths += (uint64_t)pp.n_paths;
   RT_CUDA(cudaGetLastError());
@@ -235,6 +276,8 @@ void rt_context_destroy(rt_context *ctx) {
   cudaFree(w.radiance);
   cudaFree(w.counts);
   cudaFree(w.stats);
+  for (cudaEvent_t e : ctx->timer.pool)
+    cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -564,6 +607,37 @@ int rt_get_counters(rt_context *ctx, rt_counters *out) {
   out->segments = stats[0];
   out->nodes_visited = stats[1];
   out->prim_tests = stats[2];
+  return RT_OK;
+}
+
+int rt_context_set_stage_timing(rt_context *ctx, int enable) {
+  if (!ctx)
+    return invalid("null context");
+  RT_CUDA(cudaSetDevice(ctx->device));
+  RT_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->timer.enabled = enable != 0;
+  ctx->timer.spans.clear();
+  ctx->timer.next = 0;
+  return RT_OK;
+}
+
+int rt_get_stage_times(rt_context *ctx, double ms[RT_STAGE_COUNT], uint64_t launches[RT_STAGE_COUNT]) {
+  if (!ctx || !ms || !launches)
+    return invalid("rt_get_stage_times: null argument");
+  RT_CUDA(cudaSetDevice(ctx->device));
+  RT_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < RT_STAGE_COUNT; k++) {
+    ms[k] = 0.0;
+    launches[k] = 0;
+  }
+  for (const auto &span : ctx->timer.spans) {
+    float t = 0.f;
+    RT_CUDA(cudaEventElapsedTime(&t, span.second.first, span.second.second));
+    ms[span.first] += t;
+    launches[span.first] += 1;
+  }
+  ctx->timer.spans.clear();
+  ctx->timer.next = 0;
   return RT_OK;
 }
 

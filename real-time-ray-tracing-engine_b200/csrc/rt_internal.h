@@ -39,12 +39,20 @@ struct WaveBuffers {
   size_t capacity_counts = 0;
 };
 
+struct StageTimer {
+  bool enabled = false;
+  std::vector<cudaEvent_t> pool;               // reusable events
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> spans; // (stage, (begin, end))
+  size_t next = 0;
+};
+
 struct rt_context {
   int device = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   WaveBuffers wave;
   rt_counters counters{};
+  StageTimer timer;
 };
 
 struct rt_scene {

@@ -147,6 +147,8 @@ RT_B200_SYMBOLS = {
     "rt_film_gather_p2p": (C.c_int, [P(C.c_void_p), C.c_int, C.c_double, P(C.c_float)]),
     "rt_get_counters": (C.c_int, [C.c_void_p, P(rt_counters)]),
     "rt_reset_counters": (C.c_int, [C.c_void_p]),
+    "rt_context_set_stage_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "rt_get_stage_times": (C.c_int, [C.c_void_p, P(C.c_double), P(C.c_uint64)]),
 }
 
 

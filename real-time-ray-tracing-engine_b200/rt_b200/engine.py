@@ -34,6 +34,16 @@ class Context:
         abi.check(self.lib, self.lib.rt_get_counters(self._h, C.byref(c)), "rt_get_counters")
         return c
 
+    def set_stage_timing(self, enable):
+        abi.check(self.lib, self.lib.rt_context_set_stage_timing(self._h, int(enable)), "rt_context_set_stage_timing")
+
+    def stage_times(self):
+        """(ms[4], launches[4]) for generate / extend / shade / accumulate since the last call."""
+        ms = (C.c_double * 4)()
+        n = (C.c_uint64 * 4)()
+        abi.check(self.lib, self.lib.rt_get_stage_times(self._h, ms, n), "rt_get_stage_times")
+        return list(ms), list(n)
+
     def reset_counters(self):
         abi.check(self.lib, self.lib.rt_reset_counters(self._h), "rt_reset_counters")
 

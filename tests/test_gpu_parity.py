@@ -1,0 +1,328 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (librt_b200.so), against the oracle and
+against the reference's own answers stored in tests/golden/.  Needs a GPU."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from conftest import array_from, load_golden, oracle_segments, struct_from
+from rt_b200 import abi, distributed, engine
+
+pytestmark = pytest.mark.gpu
+
+SCENES = [("spheres", 11, -1, 96), ("spheres", 40, -1, 64), ("spheres_textured", 12, -1, 64), ("cornell", 0, -1, 48),
+          ("cornell_smoke", 0, -1, 48), ("final", 5, 60, 64)]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = engine.Context(0)
+    yield c
+    c.close()
+
+
+def n_surface_prims(desc):
+    return desc.contents.n_spheres + desc.contents.n_quads
+
+
+@pytest.mark.parametrize("name", ["spheres", "spheres_textured", "cornell", "final"])
+def test_exact_trace_equals_the_reference(ctx, scene_index, host_scenes, name):
+    """Rays and answers both come from the unmodified reference (golden fixtures): primary rays of one
+    stratum and every segment of a small render.  FP64 parity mode must reproduce t, object and front face
+    bit for bit."""
+    g = load_golden(name)
+    meta = scene_index[name]
+    hs = host_scenes(meta["builtin"], meta["p0"], meta["p1"], meta["seed"])
+    scene = engine.Scene(ctx, hs.desc)
+    sets = [("primary_rays", "primary_hits_bvh0")]
+    if "segment_rays" in g.files:
+        sets.append(("segment_rays", "segment_hits"))
+    for rk, hk in sets:
+        rays = array_from(abi.rt_ray, g[rk])
+        want = ol.hits_to_numpy(array_from(abi.rt_hit, g[hk]))
+        got = ol.hits_to_numpy(scene.trace(rays, abi.RT_TRACE_EXACT_F64, 5))
+        if meta["counts"]["n_media"]:
+            keep = want["object"] >= 0  # media draw from another stream; compare where the reference hit a surface
+            med_objects = set()
+            d = hs.desc.contents
+            for m in range(d.n_media):
+                med_objects.add(d.media[m].object)
+            keep &= ~np.isin(want["object"], list(med_objects)) & ~np.isin(got["object"], list(med_objects))
+        else:
+            keep = np.ones(len(want), dtype=bool)
+        assert keep.sum() > 0
+        assert np.array_equal(got["t"][keep], want["t"][keep]), (name, rk)
+        assert np.array_equal(got["object"][keep], want["object"][keep]), (name, rk)
+        assert np.array_equal(got["front_face"][keep], want["front_face"][keep]), (name, rk)
+    scene.close()
+
+
+@pytest.mark.parametrize("name,p0,p1,width", SCENES)
+def test_trace_and_render_follow_the_oracle(ctx, oracle, host_scenes, name, p0, p1, width):
+    hs = host_scenes(name, p0, p1)
+    cfg = hs.camera_config(width, 4, 8)
+    osc = oracle.ora_scene_create(hs.desc)
+    img, rays, cnt = oracle_segments(oracle, osc, cfg, ol.ORA_RNG_PHILOX, ol.ORA_SAMPLER_POLAR, 42, 1)
+    n = len(rays)
+    want = (abi.rt_hit * n)()
+    oracle.ora_trace(osc, rays, n, 1, ol.ORA_RNG_PHILOX, 42, want)
+    a = ol.hits_to_numpy(want)
+    scene = engine.Scene(ctx, hs.desc)
+    info = scene.info()
+    assert info.n_nodes <= max(1, info.n_prims - 1)
+
+    # FP64 parity mode: primitive ids, objects, front faces bit-exact; t bit-exact for surfaces and within
+    # 1e-12 (relative) for constant media, whose free-flight distance goes through log()
+    b = ol.hits_to_numpy(scene.trace(rays, abi.RT_TRACE_EXACT_F64, 42))
+    assert np.array_equal(a["prim"], b["prim"])
+    assert np.array_equal(a["object"], b["object"])
+    assert np.array_equal(a["front_face"], b["front_face"])
+    medium = a["prim"] >= n_surface_prims(hs.desc)
+    assert np.array_equal(a["t"][~medium], b["t"][~medium])
+    if medium.any():
+        assert np.allclose(a["t"][medium], b["t"][medium], rtol=1e-12, atol=0)
+
+    # FP32 render mode: same primitive except for silhouette / grazing rays; t within FP32 accuracy
+    c = ol.hits_to_numpy(scene.trace(rays, abi.RT_TRACE_FAST_F32, 42))
+    same = a["prim"] == c["prim"]
+    assert (~same).mean() < 2e-3
+    hit = same & (a["prim"] >= 0)
+    rel = np.abs(a["t"][hit] - c["t"][hit]) / np.maximum(np.abs(a["t"][hit]), 1e-3)
+    assert np.median(rel) < 1e-5 and np.quantile(rel, 0.99) < 1e-3
+
+    # wavefront render with the oracle's Philox stream: the FP32 kernels follow the oracle's FP64 paths
+    cam = engine.camera_from_config(cfg)
+    film = engine.Film(ctx, cam.image_width, cam.image_height)
+    engine.render_static(scene, cam, film, 2, 8, 42)
+    got = film.read_rgb(0.25).astype(np.float64)
+    follows = np.abs(got - img).max(axis=1) < 2e-3
+    assert follows.mean() > 0.97, follows.mean()
+    assert abs(got.mean() - img.mean()) < 0.01 * img.mean()
+
+    # static render == sum of the progressive frames over all strata (same Philox keys)
+    film2 = engine.Film(ctx, cam.image_width, cam.image_height)
+    for s in range(4):
+        engine.render_accumulate(scene, cam, film2, s % 2, s // 2, 2, 8, 42)
+    assert film2.samples == 4
+    assert np.array_equal(film2.read_rgb(0.25), film.read_rgb(0.25))
+    film.close()
+    film2.close()
+    scene.close()
+    oracle.ora_scene_destroy(osc)
+
+
+def test_converged_image_matches_the_reference_algorithm(ctx, oracle, host_scenes):
+    """Converged-image parity (north_star): at equal spp the CUDA image must be as close to the oracle's
+    mt19937 (reference-algorithm) image as two oracle images with different seeds are to each other.
+    Tolerances: RMSE <= 1.25 x the oracle-vs-oracle RMSE, |mean relative luminance difference| <= 1 %."""
+    lum = np.array([0.2126, 0.7152, 0.0722])
+    for name, p0, width, spp_root, depth in [("spheres", 11, 64, 12, 12), ("cornell_smoke", 0, 40, 12, 12)]:
+        hs = host_scenes(name, p0, -1)
+        cfg = hs.camera_config(width, spp_root * spp_root, depth)
+        cam = engine.camera_from_config(cfg)
+        n = cam.image_width * cam.image_height
+        osc = oracle.ora_scene_create(hs.desc)
+        refs = []
+        for seed in (1, 2):
+            img = (C.c_double * (n * 3))()
+            oracle.ora_render(osc, C.byref(cfg), ol.ORA_RNG_MT19937, ol.ORA_SAMPLER_REJECTION, seed, 1, 0,
+                              cam.image_height, -1, img, None)
+            refs.append(np.nan_to_num(np.frombuffer(img, dtype=np.float64).reshape(-1, 3).copy()))
+        oracle.ora_scene_destroy(osc)
+        scene = engine.Scene(ctx, hs.desc)
+        film = engine.Film(ctx, cam.image_width, cam.image_height)
+        engine.render_static(scene, cam, film, spp_root, depth, 3)
+        got = film.read_rgb(1.0 / (spp_root * spp_root)).astype(np.float64)
+        clip = lambda x: np.minimum(x, 4.0)  # fireflies dominate an un-clipped RMSE at this sample count
+        floor = np.sqrt(np.mean((clip(refs[0]) - clip(refs[1])) ** 2))
+        rmse = max(np.sqrt(np.mean((clip(got) - clip(r)) ** 2)) for r in refs)
+        assert rmse <= 1.25 * floor, (name, rmse, floor)
+        l_ref = np.mean([(r @ lum).mean() for r in refs])
+        assert abs((got @ lum).mean() - l_ref) <= 0.01 * l_ref, (name, (got @ lum).mean(), l_ref)
+        film.close()
+        scene.close()
+
+
+def test_resolve_rgb8_is_byte_exact(ctx, oracle, host_scenes):
+    """to_byte(scale * sum) (ColorUtility.hpp:18-26, DynamicCamera.cpp:280-306) on the device."""
+    hs = host_scenes("cornell", 0, -1)
+    cfg = hs.camera_config(64, 4, 6)
+    cam = engine.camera_from_config(cfg)
+    scene = engine.Scene(ctx, hs.desc)
+    film = engine.Film(ctx, cam.image_width, cam.image_height)
+    engine.render_static(scene, cam, film, 2, 6, 9)
+    scale = 0.25
+    sums = film.read_rgb(1.0).astype(np.float64)  # the film's FP32 sums
+    want = np.array([oracle.ora_to_byte(float(scale * v)) for v in sums.reshape(-1)], dtype=np.uint8).reshape(-1, 3)
+    assert np.array_equal(film.resolve_rgb8(scale), want)
+    film.close()
+    scene.close()
+
+
+@pytest.mark.parametrize("n_ranks,tile_rows", [(2, 8), (3, 5), (8, 8)])
+def test_tile_partition_is_bit_identical(ctx, host_scenes, n_ranks, tile_rows):
+    """The image is the same for any GPU count: rank films assembled == single-rank film, bit for bit."""
+    hs = host_scenes("spheres", 11, -1)
+    cfg = hs.camera_config(160, 4, 8)
+    cam = engine.camera_from_config(cfg)
+    scene = engine.Scene(ctx, hs.desc)
+    W, H = cam.image_width, cam.image_height
+    full = engine.Film(ctx, W, H)
+    engine.render_static(scene, cam, full, 2, 8, 5)
+    want = full.read_rgb(1.0).reshape(H, W, 3)
+    parts = []
+    for r in range(n_ranks):
+        f = engine.Film(ctx, W, H, r, n_ranks, tile_rows)
+        assert f.owned_pixels == distributed.owned_pixels(W, H, r, n_ranks, tile_rows)
+        engine.render_static(scene, cam, f, 2, 8, 5)
+        parts.append(f.read_rgb(1.0))
+        f.close()
+    got = distributed.assemble_host(parts, W, H, tile_rows)
+    assert np.array_equal(got, want)
+    full.close()
+    scene.close()
+
+
+def test_scatter_gathered_kernel(ctx):
+    import torch
+
+    W, H, n_ranks, tile_rows = 37, 53, 3, 4
+    full = torch.arange(W * H * 4, dtype=torch.float32, device="cuda").reshape(H, W, 4)
+    parts = [full[torch.from_numpy(distributed.owned_rows(H, r, n_ranks, tile_rows)).cuda()].reshape(-1, 4)
+             for r in range(n_ranks)]
+    gathered = torch.cat(parts).contiguous()
+    out = torch.zeros_like(full)
+    torch.cuda.synchronize()
+    lib = ctx.lib
+    abi.check(lib, lib.rt_film_scatter_gathered(ctx._h, W, H, n_ranks, tile_rows, gathered.data_ptr(), out.data_ptr()),
+              "rt_film_scatter_gathered")
+    ctx.synchronize()
+    assert torch.equal(out, full)
+
+
+def test_external_accumulation_buffer(ctx, host_scenes):
+    """A film may accumulate into caller-owned device memory (a torch tensor)."""
+    import torch
+
+    hs = host_scenes("cornell", 0, -1)
+    cfg = hs.camera_config(48, 1, 4)
+    cam = engine.camera_from_config(cfg)
+    scene = engine.Scene(ctx, hs.desc)
+    buf = torch.full((cam.image_width * cam.image_height, 4), 7.0, device="cuda")
+    torch.cuda.synchronize()
+    film = engine.Film(ctx, cam.image_width, cam.image_height, external_accum=buf.data_ptr())
+    engine.render_accumulate(scene, cam, film, 0, 0, 1, 4, 1)
+    ctx.synchronize()
+    own = engine.Film(ctx, cam.image_width, cam.image_height)
+    engine.render_accumulate(scene, cam, own, 0, 0, 1, 4, 1)
+    assert np.array_equal(buf[:, :3].cpu().numpy(), own.read_rgb(1.0))
+    film.close()
+    own.close()
+    scene.close()
+
+
+def test_edge_cases(ctx):
+    # empty world: every path returns the background (Camera.cpp:242-243)
+    empty = abi.rt_scene_desc()
+    scene = engine.Scene(ctx, empty)
+    cfg = abi.rt_camera_config(image_width=33, samples_per_pixel=1, max_depth=3, aspect_ratio=1.5, vfov=40, focus_dist=1)
+    cfg.lookat[:] = (0, 0, -1)
+    cfg.vup[:] = (0, 1, 0)
+    cfg.background[:] = (0.25, 0.5, 0.75)
+    cam = engine.camera_from_config(cfg)
+    film = engine.Film(ctx, cam.image_width, cam.image_height)
+    engine.render_accumulate(scene, cam, film, 0, 0, 1, 3, 0)
+    img = film.read_rgb(1.0)
+    assert np.array_equal(img, np.tile(np.float32([0.25, 0.5, 0.75]), (img.shape[0], 1)))
+    rays = (abi.rt_ray * 2)()
+    for r in rays:
+        r.direction[:] = (0, 0, -1)
+        r.t_min, r.t_max = 0.001, float("inf")
+    for mode in (abi.RT_TRACE_EXACT_F64, abi.RT_TRACE_FAST_F32):
+        hits = scene.trace(rays, mode)
+        assert all(h.prim == -1 and h.t == float("inf") for h in hits)
+    film.close()
+    scene.close()
+
+    # a single emissive sphere: one BVH leaf, emission on the front face only, depth 1
+    sph = abi.rt_sphere(radius=0.5, material=0, xform=-1, object=0)
+    sph.center0[:] = (0, 0, -2)
+    mat = abi.rt_material(type=abi.RT_MAT_DIFFUSE_LIGHT, texture=0)
+    tex = abi.rt_texture(type=abi.RT_TEX_SOLID, even=-1, odd=-1, perlin=-1)
+    tex.color[:] = (2, 3, 4)
+    one = abi.rt_scene_desc(n_spheres=1, n_materials=1, n_textures=1, n_objects=1, spheres=C.pointer(sph),
+                            materials=C.pointer(mat), textures=C.pointer(tex))
+    scene = engine.Scene(ctx, one)
+    assert scene.info().n_prims == 1 and scene.info().n_nodes == 1
+    hits = scene.trace(rays, abi.RT_TRACE_EXACT_F64)
+    assert hits[0].prim == 0 and hits[0].t == 1.5 and hits[0].front_face == 1
+    film = engine.Film(ctx, cam.image_width, cam.image_height)
+    engine.render_accumulate(scene, cam, film, 0, 0, 1, 1, 0)
+    img = film.read_rgb(1.0)
+    centre = img[(cam.image_height // 2) * cam.image_width + cam.image_width // 2]
+    assert np.array_equal(centre, np.float32([2, 3, 4]))
+    assert np.array_equal(img[0], np.float32([0.25, 0.5, 0.75]))
+    film.close()
+    scene.close()
+
+    # malformed scenes are refused with RT_ERR_INVALID, not rendered
+    bad_sph = abi.rt_sphere(radius=0.5, material=5, xform=-1, object=0)
+    bad = abi.rt_scene_desc(n_spheres=1, n_objects=1, spheres=C.pointer(bad_sph))
+    with pytest.raises(abi.RtError):
+        engine.Scene(ctx, bad)
+    # zero rays is a no-op
+    assert len(engine.Scene(ctx, abi.rt_scene_desc()).trace((abi.rt_ray * 0)())) == 0
+
+
+def test_full_size_properties_1080p(ctx, host_scenes):
+    """BASELINE config 2 at full size (1920x1080, 1 spp, depth 8), checked through size-independent
+    properties: determinism, path and segment counts, mean radiance vs a low-resolution oracle-verified
+    render, and tile-partition invariance."""
+    hs = host_scenes("spheres", 11, -1)
+    cfg = hs.camera_config(1920, 1, 8)
+    cam = engine.camera_from_config(cfg)
+    assert (cam.image_width, cam.image_height) == (1920, 1080)
+    scene = engine.Scene(ctx, hs.desc)
+    film = engine.Film(ctx, 1920, 1080)
+    ctx.reset_counters()
+    engine.render_accumulate(scene, cam, film, 0, 0, 1, 8, 11)
+    a = film.read_rgb(1.0)
+    c = ctx.counters()
+    assert c.paths == 1920 * 1080
+    assert 2.3 < c.segments / c.paths < 2.8  # the reference traces 2.562 segments per path on this frame
+    film.clear()
+    engine.render_accumulate(scene, cam, film, 0, 0, 1, 8, 11)
+    assert np.array_equal(a, film.read_rgb(1.0))  # same seed, same image
+    assert np.isfinite(a).all() and (a >= 0).all()
+    assert abs(a.mean() - 0.3831) < 0.004  # mean radiance of the oracle-verified low-resolution renders
+    parts = []
+    for r in range(4):
+        f = engine.Film(ctx, 1920, 1080, r, 4, 8)
+        engine.render_accumulate(scene, cam, f, 0, 0, 1, 8, 11)
+        parts.append(f.read_rgb(1.0))
+        f.close()
+    assert np.array_equal(distributed.assemble_host(parts, 1920, 1080, 8).reshape(-1, 3), a)
+    film.close()
+    scene.close()
+
+
+def test_million_sphere_scene_builds_and_traces(ctx, oracle, host_scenes):
+    """BASELINE config 4 generator (a = b = -500..500): GPU LBVH over ~1M primitives; closest hits of a ray
+    sample checked bit for bit against the oracle."""
+    hs = host_scenes("spheres_textured", 500, -1)
+    n_prims = hs.desc.contents.n_objects
+    assert n_prims > 990000
+    scene = engine.Scene(ctx, hs.desc)
+    info = scene.info()
+    assert info.n_prims == n_prims and info.n_nodes < n_prims
+    cfg = hs.camera_config(96, 1, 4)
+    osc = oracle.ora_scene_create(hs.desc)
+    img, rays, cnt = oracle_segments(oracle, osc, cfg, ol.ORA_RNG_PHILOX, ol.ORA_SAMPLER_POLAR, 4, 1, single_stratum=0)
+    want = (abi.rt_hit * len(rays))()
+    oracle.ora_trace(osc, rays, len(rays), 1, ol.ORA_RNG_PHILOX, 4, want)
+    a = ol.hits_to_numpy(want)
+    b = ol.hits_to_numpy(scene.trace(rays, abi.RT_TRACE_EXACT_F64, 4))
+    assert np.array_equal(a["prim"], b["prim"]) and np.array_equal(a["t"], b["t"])
+    oracle.ora_scene_destroy(osc)
+    scene.close()

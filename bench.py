@@ -168,6 +168,8 @@ def run_ours(args):
     npix = W * H
     strata_per_step = world  # weak scaling: N strata of the whole frame per step
     sqrt_spp = 1
+    while sqrt_spp * sqrt_spp < strata_per_step:  # smallest stratification grid holding N strata
+        sqrt_spp += 1
 
     owned = distributed.owned_pixels(W, H, rank, world, TILE_ROWS)
     accum = torch.zeros((owned, 4), dtype=torch.float32, device="cuda")
@@ -181,8 +183,10 @@ def run_ours(args):
 
     def render_step(step):
         """One progressive step on the context stream: `strata_per_step` strata for this rank's tiles."""
-        for k in range(strata_per_step):
-            engine.render_accumulate(scene, cam, film, 0, 0, sqrt_spp, DEPTH, 1000 + step * strata_per_step + k)
+        if strata_per_step == 1:
+            engine.render_accumulate(scene, cam, film, 0, 0, 1, DEPTH, 1000 + step)
+        else:  # the step's strata in ONE wavefront pass (same launch count as a single-GPU frame)
+            engine.render_strata(scene, cam, film, 0, strata_per_step, sqrt_spp, DEPTH, 1000 + step)
 
     def assemble(step):
         """Frame assembly: gather the compact films to rank 0 and scatter them into the row-major frame."""
@@ -314,7 +318,7 @@ def run_ours(args):
                 "l2": "192 MiB buffer written between timed steps (flush time measured separately and subtracted)"},
             "frame_ms": ms_step / strata_per_step,
             "e2e": {"value": e2e_value, "unit": "Mpath-samples/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": C.sizeof(abi.rt_camera) * strata_per_step, "d2h_bytes_per_step": npix * 3,
+                    "h2d_bytes_per_step": C.sizeof(abi.rt_camera), "d2h_bytes_per_step": npix * 3,
                     "path": "rt_render_accumulate -> rt_film_resolve_rgb8_device -> pinned host RGB8, stream synchronised every step"},
             "gpu_launches": int(counters.kernel_launches),
             "roofline": {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",

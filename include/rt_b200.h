@@ -311,6 +311,12 @@ int64_t rt_film_samples(const rt_film *film);
 int rt_render_accumulate(rt_scene *scene, const rt_camera *camera, rt_film *film, int s_i, int s_j,
                          int sqrt_spp, int max_depth, uint64_t seed);
 
+/* n_strata consecutive strata (linear index s = s_j * sqrt_spp + s_i, starting at first_stratum) in one
+ * wavefront pass, ADDED to the film: the progressive step of a camera that takes several samples per
+ * displayed frame (e.g. one per GPU).  Asynchronous on the context stream. */
+int rt_render_strata(rt_scene *scene, const rt_camera *camera, rt_film *film, int first_stratum, int n_strata,
+                     int sqrt_spp, int max_depth, uint64_t seed);
+
 /* All sqrt_spp^2 strata (cuda_static_render_wrapper semantics).  Clears the film first. */
 int rt_render_static(rt_scene *scene, const rt_camera *camera, rt_film *film, int sqrt_spp,
                      int max_depth, uint64_t seed);

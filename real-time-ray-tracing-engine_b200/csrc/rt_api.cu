@@ -125,14 +125,14 @@ int render_pass(rt_scene *scene, const rt_camera *camera, rt_film *film, int fir
   pp.seed = seed;
   if (pp.n_paths == 0)
     return RT_OK;
-  int st = ensure_wave(ctx, (size_t)pp.n_paths, (size_t)max_depth + 2);
+  int st = ensure_wave(ctx, (size_t)pp.n_paths, 2 * ((size_t)max_depth + 2)); // queue lengths + fetch cursors
   if (st != RT_OK)
     return st;
   DScene sc = scene->d;
   for (int a = 0; a < 3; a++)
     sc.bg[a] = (float)camera->background[a];
   WaveBuffers &w = ctx->wave;
-  RT_CUDA(cudaMemsetAsync(w.counts, 0, ((size_t)max_depth + 2) * sizeof(unsigned int), ctx->stream));
+  RT_CUDA(cudaMemsetAsync(w.counts, 0, 2 * ((size_t)max_depth + 2) * sizeof(unsigned int), ctx->stream));
   {
     StageSpan span(ctx, RT_STAGE_GENERATE);
     launch_generate(ctx, pp, w);
@@ -456,6 +456,33 @@ int rt_render_accumulate(rt_scene *scene, const rt_camera *camera, rt_film *film
   return st;
 }
 
+// Strata [first, first + count) in passes of enough paths to fill the GPU several times over, bounded
+// so that the queues stay modest.
+static int render_strata(rt_scene *scene, const rt_camera *camera, rt_film *film, int first, int count, int sqrt_spp,
+                         int max_depth, uint64_t seed) {
+  const int64_t target_paths = (int64_t)4 << 20;
+  int per_pass = (int)std::max<int64_t>(1, std::min<int64_t>(count, target_paths / std::max<int64_t>(film->n_owned, 1)));
+  for (int s = first; s < first + count; s += per_pass) {
+    int n = std::min(per_pass, first + count - s);
+    int st = render_pass(scene, camera, film, s, n, sqrt_spp, max_depth, seed);
+    if (st != RT_OK)
+      return st;
+    film->samples += n;
+  }
+  return RT_OK;
+}
+
+int rt_render_strata(rt_scene *scene, const rt_camera *camera, rt_film *film, int first_stratum, int n_strata,
+                     int sqrt_spp, int max_depth, uint64_t seed) {
+  int st = check_render_args(scene, camera, film, sqrt_spp, max_depth);
+  if (st != RT_OK)
+    return st;
+  if (first_stratum < 0 || n_strata < 1 || first_stratum + n_strata > sqrt_spp * sqrt_spp)
+    return invalid("rt_render_strata: strata out of range");
+  RT_CUDA(cudaSetDevice(scene->ctx->device));
+  return render_strata(scene, camera, film, first_stratum, n_strata, sqrt_spp, max_depth, seed);
+}
+
 int rt_render_static(rt_scene *scene, const rt_camera *camera, rt_film *film, int sqrt_spp, int max_depth,
                      uint64_t seed) {
   int st = check_render_args(scene, camera, film, sqrt_spp, max_depth);
@@ -464,17 +491,7 @@ int rt_render_static(rt_scene *scene, const rt_camera *camera, rt_film *film, in
   RT_CUDA(cudaSetDevice(scene->ctx->device));
   if ((st = rt_film_clear(film)) != RT_OK)
     return st;
-  const int total = sqrt_spp * sqrt_spp;
-  // enough paths per pass to fill the GPU several times over, bounded so the queues stay modest
-  const int64_t target_paths = (int64_t)4 << 20;
-  int per_pass = (int)std::max<int64_t>(1, std::min<int64_t>(total, target_paths / std::max<int64_t>(film->n_owned, 1)));
-  for (int first = 0; first < total; first += per_pass) {
-    int n = std::min(per_pass, total - first);
-    if ((st = render_pass(scene, camera, film, first, n, sqrt_spp, max_depth, seed)) != RT_OK)
-      return st;
-    film->samples += n;
-  }
-  return RT_OK;
+  return render_strata(scene, camera, film, 0, sqrt_spp * sqrt_spp, sqrt_spp, max_depth, seed);
 }
 
 int rt_film_read_rgb(rt_film *film, double scale, float *host_rgb) {

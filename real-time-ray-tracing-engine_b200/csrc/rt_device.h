@@ -348,10 +348,17 @@ struct RayKey {
   uint32_t pixel, sample, bounce;
 };
 
+// Traversal statistics hooks: empty in the product, counters in the host test build (tests/emu).
+#ifndef RT_STAT_NODE
+#define RT_STAT_NODE()
+#define RT_STAT_LEAF()
+#endif
+
 RT_HD void leaf_test(const DScene &sc, int prim, const Ray &ray, float tmin, Hit &hit, int skip_prim,
                      const RayKey &key) {
   if (prim == skip_prim)
     return;
+  RT_STAT_LEAF();
   const float4 *rec = sc.prims + (size_t)prim * RT_PRIM_F4;
   float4 r0 = ldg4(rec), r3 = ldg4(rec + 3);
   int type = (uint32_t)f2i(r3.y) >> 28;
@@ -374,8 +381,8 @@ RT_HD void leaf_test(const DScene &sc, int prim, const Ray &ray, float tmin, Hit
 
 // ---------------------------------------------------------------------------------------------------
 // BVH4 traversal (FP32).  Slab test as AABB::hit (AABB.cpp:141-164) but with the reciprocal
-// direction hoisted, NaN-safe min/max, and the far plane widened by 2 ulp so that no box the FP64
-// reference would enter is culled (Ize, "Robust BVH ray traversal").
+// direction hoisted, NaN-safe min/max, and the far plane widened so that no box the FP64 reference
+// would enter is culled (Ize, "Robust BVH ray traversal"; see RayTrav below).
 // The stack holds (child ref, entry distance); `stack` is caller-provided storage of RT_STACK entries
 // (shared-memory short stack in the kernels, spilling to local memory beyond RT_STACK_SMEM).
 // ---------------------------------------------------------------------------------------------------
@@ -386,37 +393,63 @@ struct StackEntry {
   float t;
 };
 
+// Per-ray traversal constants.  The slab distances are evaluated as plane * inv - o * inv (one FMA per
+// plane); the near / far plane of every axis is picked by the direction's sign bit, which selects the
+// node row to load, so no per-axis min/max is needed.  `slack` bounds the absolute error of that form
+// (the rounding of o * inv, 2^-24 relative, enters every distance): a box is entered when
+// tnear <= tfar * (1 + 4e-7) + slack, i.e. the test can only enter more boxes than the exact one, never
+// fewer.  A zero direction component gives inf / NaN distances, which fminf / fmaxf drop (that axis
+// then does not constrain the interval: conservative as well).
+struct RayTrav {
+  f3 inv, oi;
+  float slack;
+  int nx, ny, nz; // row of the near plane: x 0/1, y 2/3, z 4/5
+};
+RT_HD bool sign_bit(float f) { return f2i(f) < 0; }
+RT_HD RayTrav make_trav(f3 o, f3 d) {
+  RayTrav t;
+  t.inv = F3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+  t.oi = F3(o.x * t.inv.x, o.y * t.inv.y, o.z * t.inv.z);
+  t.slack = 2.5e-7f * fmaxf(fabsf(t.oi.x), fmaxf(fabsf(t.oi.y), fabsf(t.oi.z)));
+  t.nx = sign_bit(d.x) ? 1 : 0;
+  t.ny = sign_bit(d.y) ? 3 : 2;
+  t.nz = sign_bit(d.z) ? 5 : 4;
+  return t;
+}
+RT_HD float fma_sub(float a, float b, float c) { // a * b - c in one rounding
+#if defined(__CUDA_ARCH__)
+  return __fmaf_rn(a, b, -c);
+#else
+  return fmaf(a, b, -c);
+#endif
+}
+
+// Visits inner node `node`: tests its four child boxes, pushes the hit children far-to-near and
+// returns the nearest one in `next` (false when no child is hit).
 template <class Stack>
-RT_HD void traverse(const DScene &sc, const Ray &ray, float tmin, Hit &hit, int skip_prim, const RayKey &key,
-                    Stack &stack) {
-  f3 inv = F3(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);
-  f3 o = ray.o;
-  int sp = 0;
-  int ref = 0; // root node
-  float ref_t = tmin;
-  for (;;) {
-    if (ref >= 0) {
-      const float4 *n = sc.nodes + (size_t)ref * RT_NODE_F4;
-      float4 lox = ldg4(n), hix = ldg4(n + 1), loy = ldg4(n + 2), hiy = ldg4(n + 3), loz = ldg4(n + 4),
-             hiz = ldg4(n + 5), cr = ldg4(n + 6);
-      float tn[4];
-      int cref[4] = {f2i(cr.x), f2i(cr.y), f2i(cr.z), f2i(cr.w)};
-      const float lx[4] = {lox.x, lox.y, lox.z, lox.w}, hx[4] = {hix.x, hix.y, hix.z, hix.w};
-      const float ly[4] = {loy.x, loy.y, loy.z, loy.w}, hy[4] = {hiy.x, hiy.y, hiy.z, hiy.w};
-      const float lz[4] = {loz.x, loz.y, loz.z, loz.w}, hz[4] = {hiz.x, hiz.y, hiz.z, hiz.w};
+RT_HD bool node_visit(const DScene &sc, int node, const RayTrav &rt, float tmin, float tmax, Stack &stack, int &sp,
+                      int &next) {
+  RT_STAT_NODE();
+  const float4 *n = sc.nodes + (size_t)node * RT_NODE_F4;
+  float4 nrx = ldg4(n + rt.nx), frx = ldg4(n + (rt.nx ^ 1)), nry = ldg4(n + rt.ny), fry = ldg4(n + (rt.ny ^ 1)),
+         nrz = ldg4(n + rt.nz), frz = ldg4(n + (rt.nz ^ 1)), cr = ldg4(n + 6);
+  float tn[4];
+  int cref[4] = {f2i(cr.x), f2i(cr.y), f2i(cr.z), f2i(cr.w)};
+  const float nx[4] = {nrx.x, nrx.y, nrx.z, nrx.w}, fx[4] = {frx.x, frx.y, frx.z, frx.w};
+  const float ny[4] = {nry.x, nry.y, nry.z, nry.w}, fy[4] = {fry.x, fry.y, fry.z, fry.w};
+  const float nz[4] = {nrz.x, nrz.y, nrz.z, nrz.w}, fz[4] = {frz.x, frz.y, frz.z, frz.w};
+  const float tmax_wide = tmax * 1.0000004f + rt.slack;
 #pragma unroll
-      for (int c = 0; c < 4; c++) {
-        // (bound - origin) * inv: the subtraction first, so a ray that starts close to a slab plane
-        // keeps full relative accuracy (an o * inv term would cancel catastrophically)
-        float t0x = (lx[c] - o.x) * inv.x, t1x = (hx[c] - o.x) * inv.x;
-        float t0y = (ly[c] - o.y) * inv.y, t1y = (hy[c] - o.y) * inv.y;
-        float t0z = (lz[c] - o.z) * inv.z, t1z = (hz[c] - o.z) * inv.z;
-        float tnear = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), tmin));
-        float tfar = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), hit.t));
-        bool ok = (tnear <= tfar * 1.0000004f) && (cref[c] != RT_EMPTY);
-        tn[c] = ok ? tnear : RT_INF_F;
-      }
-      // sort the four children by entry distance (ascending), 5-comparator network
+  for (int c = 0; c < 4; c++) {
+    float tnear = fmaxf(fmaxf(fma_sub(nx[c], rt.inv.x, rt.oi.x), fma_sub(ny[c], rt.inv.y, rt.oi.y)),
+                        fmaxf(fma_sub(nz[c], rt.inv.z, rt.oi.z), tmin));
+    float tfar = fminf(fminf(fma_sub(fx[c], rt.inv.x, rt.oi.x), fma_sub(fy[c], rt.inv.y, rt.oi.y)),
+                       fma_sub(fz[c], rt.inv.z, rt.oi.z));
+    tfar = fminf(tfar * 1.0000004f + rt.slack, tmax_wide);
+    bool ok = (tnear <= tfar) && (cref[c] != RT_EMPTY);
+    tn[c] = ok ? tnear : RT_INF_F;
+  }
+  // sort the four children by entry distance (ascending), 5-comparator network
 #define RT_CSWAP(a, b)                                                                                       \
   if (tn[b] < tn[a]) {                                                                                       \
     float tt = tn[a];                                                                                        \
@@ -426,38 +459,51 @@ RT_HD void traverse(const DScene &sc, const Ray &ray, float tmin, Hit &hit, int 
     cref[a] = cref[b];                                                                                       \
     cref[b] = ti;                                                                                            \
   }
-      RT_CSWAP(0, 1)
-      RT_CSWAP(2, 3)
-      RT_CSWAP(0, 2)
-      RT_CSWAP(1, 3)
-      RT_CSWAP(1, 2)
+  RT_CSWAP(0, 1)
+  RT_CSWAP(2, 3)
+  RT_CSWAP(0, 2)
+  RT_CSWAP(1, 3)
+  RT_CSWAP(1, 2)
 #undef RT_CSWAP
-      // push far-to-near, continue with the nearest
 #pragma unroll
-      for (int c = 3; c >= 1; c--)
-        if (tn[c] < RT_INF_F) {
-          if (sp < RT_STACK) {
-            stack.set(sp, cref[c], tn[c]);
-            sp++;
-          }
-        }
-      if (tn[0] < RT_INF_F) {
-        ref = cref[0];
-        ref_t = tn[0];
-        continue;
+  for (int c = 3; c >= 1; c--)
+    if (tn[c] < RT_INF_F) {
+      if (sp < RT_STACK) {
+        stack.set(sp, cref[c], tn[c]);
+        sp++;
       }
+    }
+  next = cref[0];
+  return tn[0] < RT_INF_F;
+}
+
+// Pops the next stack entry whose entry distance is still inside the interval.
+template <class Stack> RT_HD bool stack_pop(Stack &stack, int &sp, float tmax, int &ref) {
+  while (sp > 0) {
+    float t;
+    sp--;
+    stack.get(sp, ref, t);
+    if (t <= tmax)
+      return true;
+  }
+  return false;
+}
+
+template <class Stack>
+RT_HD void traverse(const DScene &sc, const Ray &ray, float tmin, Hit &hit, int skip_prim, const RayKey &key,
+                    Stack &stack) {
+  RayTrav rt = make_trav(ray.o, ray.d);
+  int sp = 0;
+  int ref = 0; // root node
+  for (;;) {
+    if (ref >= 0) {
+      if (node_visit(sc, ref, rt, tmin, hit.t, stack, sp, ref))
+        continue;
     } else {
       leaf_test(sc, ~ref, ray, tmin, hit, skip_prim, key);
     }
-    // pop
-    for (;;) {
-      if (sp == 0)
-        return;
-      sp--;
-      stack.get(sp, ref, ref_t);
-      if (ref_t <= hit.t)
-        break;
-    }
+    if (!stack_pop(stack, sp, hit.t, ref))
+      return;
   }
 }
 

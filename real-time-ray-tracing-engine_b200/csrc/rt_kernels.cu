@@ -13,6 +13,9 @@
 
 #include <cub/device/device_radix_sort.cuh>
 
+#include <cstdlib>
+#include <string>
+
 #define RT_BLOCK 128
 #define RT_STACK_SMEM 8
 
@@ -95,10 +98,115 @@ __global__ void __launch_bounds__(RT_BLOCK)
 // ---------------------------------------------------------------------------------------------------
 // extend
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(RT_BLOCK)
+// Persistent warps with dynamic ray fetch and a while-while traversal loop (Aila & Laine, "Understanding
+// the efficiency of ray traversal on GPUs"): every warp keeps pulling rays from the bounce's queue through a
+// device-side cursor; lanes first descend inner nodes only, then test leaves only, so a warp never
+// executes box code and primitive code in the same iteration; when fewer than RT_REFILL lanes still hold a
+// ray, the idle lanes fetch new ones (one atomicAdd per warp).
+#define RT_REFILL 22
+#define RT_DONE 0x7fffffff
+
+__global__ void __launch_bounds__(RT_BLOCK, 8)
     k_extend(const __grid_constant__ DScene sc, const __grid_constant__ PassParams pp,
              const float4 *__restrict__ ray_a, const float4 *__restrict__ ray_b, float2 *__restrict__ hit,
-             const unsigned int *__restrict__ counts, int bounce, int has_media, unsigned long long *stats) {
+             const unsigned int *__restrict__ counts, unsigned int *__restrict__ cursor, int bounce, int has_media,
+             unsigned long long *stats) {
+  __shared__ int s_ref[RT_STACK_SMEM * RT_BLOCK];
+  __shared__ float s_t[RT_STACK_SMEM * RT_BLOCK];
+  SmemStack stack;
+  stack.s_ref = s_ref + threadIdx.x;
+  stack.s_t = s_t + threadIdx.x;
+  const unsigned int n = counts[bounce];
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    atomicAdd(&stats[0], (unsigned long long)n);
+  const unsigned int lane = threadIdx.x & 31u;
+  const unsigned int lt_mask = (1u << lane) - 1u;
+
+  // Per-lane state kept in registers across node visits: the slab constants, the closest hit, the stack
+  // pointer and the current reference.  Origin, direction, time and the skip primitive are only needed by
+  // primitive tests (1.65 per segment vs 6.5 node visits), so they are re-read from the queue there.
+  RayTrav rt = make_trav(F3(0.f, 0.f, 0.f), F3(1.f, 1.f, 1.f));
+  Hit best;
+  int sp = 0, ref = RT_DONE;
+  unsigned int q = 0;
+  bool exhausted = false; // the queue has no more rays to hand out
+  best.t = -1.0f;         // no ray held
+  best.prim = -1;
+
+  for (;;) {
+    // ---- fetch: idle lanes take the next rays of the queue ----
+    unsigned int idle = __ballot_sync(0xffffffffu, ref == RT_DONE);
+    if (idle && !exhausted) {
+      unsigned int base = 0;
+      int leader = __ffs(idle) - 1;
+      if ((int)lane == leader)
+        base = atomicAdd(cursor, (unsigned int)__popc(idle));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (ref == RT_DONE) {
+        unsigned int mine = base + (unsigned int)__popc(idle & lt_mask);
+        if (mine < n) {
+          q = mine;
+          float4 a = ray_a[q], b = ray_b[q];
+          rt = make_trav(F3(a.x, a.y, a.z), F3(b.x, b.y, b.z));
+          best.t = RT_INF_F;
+          best.prim = -1;
+          sp = 0;
+          ref = 0; // root
+        }
+      }
+      exhausted = base + (unsigned int)__popc(idle) >= n;
+    }
+    if (__all_sync(0xffffffffu, ref == RT_DONE))
+      break;
+
+    // ---- traverse until too few lanes are busy ----
+    for (;;) {
+      // inner nodes only
+      while (ref >= 0 && ref != RT_DONE) {
+        if (!node_visit(sc, ref, rt, RT_T_MIN, best.t, stack, sp, ref))
+          if (!stack_pop(stack, sp, best.t, ref))
+            ref = RT_DONE;
+      }
+      // leaves only
+      if (ref < 0) {
+        float4 a = ray_a[q], b = ray_b[q];
+        Ray r;
+        r.o = F3(a.x, a.y, a.z);
+        r.d = F3(b.x, b.y, b.z);
+        r.time = a.w;
+        int skip = __float_as_int(hit[q].y);
+        RayKey key;
+        key.seed = pp.seed;
+        key.pixel = key.sample = 0;
+        key.bounce = (uint32_t)bounce;
+        if (has_media) {
+          int k;
+          path_to_key(pp, __float_as_int(b.w), bounce, key, k);
+        }
+        do {
+          leaf_test(sc, ~ref, r, RT_T_MIN, best, skip, key);
+          if (!stack_pop(stack, sp, best.t, ref))
+            ref = RT_DONE;
+        } while (ref < 0);
+      }
+      bool finished = ref == RT_DONE && best.t != -1.0f;
+      if (finished) { // write the result once
+        hit[q] = make_float2(best.t, __int_as_float(best.prim));
+        best.t = -1.0f; // marks "already written / no ray held"
+      }
+      unsigned int busy = __ballot_sync(0xffffffffu, ref != RT_DONE);
+      if (busy == 0 || (!exhausted && __popc(busy) < RT_REFILL))
+        break;
+    }
+  }
+}
+
+// The straightforward variant (one ray per thread, grid stride, single if/else loop); kept for A/B
+// measurements (RT_EXTEND=simple).
+__global__ void __launch_bounds__(RT_BLOCK)
+    k_extend_simple(const __grid_constant__ DScene sc, const __grid_constant__ PassParams pp,
+                    const float4 *__restrict__ ray_a, const float4 *__restrict__ ray_b, float2 *__restrict__ hit,
+                    const unsigned int *__restrict__ counts, int bounce, int has_media, unsigned long long *stats) {
   __shared__ int s_ref[RT_STACK_SMEM * RT_BLOCK];
   __shared__ float s_t[RT_STACK_SMEM * RT_BLOCK];
   SmemStack stack;
@@ -456,11 +564,22 @@ void launch_generate(const rt_context *ctx, const PassParams &pp, WaveBuffers &w
 }
 
 void launch_extend(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int bounce) {
+  int b = bounce & 1;
+  static const bool simple = getenv("RT_EXTEND") && std::string(getenv("RT_EXTEND")) == "simple";
+  if (simple) {
+    LaunchShape sh = rt_persistent_shape(ctx, RT_BLOCK, 8);
+    int need = ceil_div(pp.n_paths, RT_BLOCK);
+    k_extend_simple<<<need < sh.blocks ? need : sh.blocks, RT_BLOCK, 0, ctx->stream>>>(
+        sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b], w.counts, bounce, sc.n_media > 0, w.stats);
+    return;
+  }
+  // persistent warps: exactly the resident set (8 blocks of 4 warps per SM), each pulling rays from the queue
   LaunchShape sh = rt_persistent_shape(ctx, RT_BLOCK, 8);
   int need = ceil_div(pp.n_paths, RT_BLOCK);
-  int b = bounce & 1;
+  unsigned int *cursor = w.counts + (pp.max_depth + 2) + bounce;
   k_extend<<<need < sh.blocks ? need : sh.blocks, RT_BLOCK, 0, ctx->stream>>>(sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b],
-                                                                              w.counts, bounce, sc.n_media > 0, w.stats);
+                                                                              w.counts, cursor, bounce, sc.n_media > 0,
+                                                                              w.stats);
 }
 
 void launch_shade(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int bounce) {

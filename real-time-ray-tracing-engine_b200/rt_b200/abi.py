@@ -139,6 +139,8 @@ RT_B200_SYMBOLS = {
     "rt_film_samples": (C.c_int64, [C.c_void_p]),
     "rt_render_accumulate": (C.c_int, [C.c_void_p, P(rt_camera), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_uint64]),
+    "rt_render_strata": (C.c_int, [C.c_void_p, P(rt_camera), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_uint64]),
     "rt_render_static": (C.c_int, [C.c_void_p, P(rt_camera), C.c_void_p, C.c_int, C.c_int, C.c_uint64]),
     "rt_film_read_rgb": (C.c_int, [C.c_void_p, C.c_double, P(C.c_float)]),
     "rt_film_resolve_rgb8": (C.c_int, [C.c_void_p, C.c_double, P(C.c_uint8)]),

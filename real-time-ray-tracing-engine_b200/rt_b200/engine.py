@@ -152,3 +152,9 @@ def render_static(scene, camera, film, sqrt_spp, max_depth, seed):
     """All sqrt_spp^2 strata (cuda_static_render_wrapper semantics).  Asynchronous."""
     abi.check(scene.lib, scene.lib.rt_render_static(scene._h, C.byref(camera), film._h, sqrt_spp, max_depth, seed),
               "rt_render_static")
+
+
+def render_strata(scene, camera, film, first_stratum, n_strata, sqrt_spp, max_depth, seed):
+    """n_strata consecutive strata in one wavefront pass, added to the film.  Asynchronous."""
+    abi.check(scene.lib, scene.lib.rt_render_strata(scene._h, C.byref(camera), film._h, first_stratum, n_strata,
+                                                    sqrt_spp, max_depth, seed), "rt_render_strata")

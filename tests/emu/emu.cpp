@@ -3,6 +3,10 @@
 // the flattening, the LBVH build logic, both traversals and the shading arithmetic can be checked
 // against the oracle in a container without a GPU.  Nothing here is part of librt_b200.so, and no
 // product code path can reach it; the GPU tests exercise the real kernels through the C ABI.
+#include <cstdint>
+static uint64_t g_stat_nodes = 0, g_stat_leaves = 0;
+#define RT_STAT_NODE() (++g_stat_nodes)
+#define RT_STAT_LEAF() (++g_stat_leaves)
 #include "../../real-time-ray-tracing-engine_b200/csrc/rt_flatten.h"
 
 #include <algorithm>
@@ -144,6 +148,12 @@ EmuScene *emu_scene_create(const rt_scene_desc *desc) {
 }
 
 void emu_scene_destroy(EmuScene *s) { delete s; }
+void emu_stats(uint64_t *nodes, uint64_t *leaves, int reset) {
+  *nodes = g_stat_nodes;
+  *leaves = g_stat_leaves;
+  if (reset)
+    g_stat_nodes = g_stat_leaves = 0;
+}
 int emu_scene_nodes(const EmuScene *s) { return s->n_wide; }
 int emu_scene_leaves(const EmuScene *s) { return s->d.n_prims; }
 

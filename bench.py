@@ -278,7 +278,8 @@ def run_ours(args):
         render_step(s)
     stage_ms, stage_n = ctx.stage_times()
     ctx.set_stage_timing(False)
-    seg = ctx.counters().segments
+    roof_counters = ctx.counters()
+    seg = roof_counters.segments - roof_counters.nodes_visited  # segments of the k_extend launches (tail excluded)
     if rank == 0:
         sampler.stop_flag.set()
         sampler.join()
@@ -330,7 +331,8 @@ def run_ours(args):
                                  "fetches + queue traffic, so this is an L1/L2 figure set against the HBM copy peak",
                          "fp32": {"achieved_tflops": flops, "peak_tflops": fp32_peak, "frac": flops / fp32_peak},
                          "stage_ms_per_frame": {k: stage_ms[i] / roof_steps / strata_per_step
-                                                for i, k in enumerate(["generate", "extend", "shade", "accumulate"])}},
+                                                for i, k in enumerate(["generate", "extend", "shade", "accumulate", "tail"])},
+                         "tail_segments_per_frame": roof_counters.nodes_visited / roof_steps / strata_per_step},
             "cpu_baseline": dict(cpu_desc, value=cpu_value, unit="Mpath-samples/s"),
             "clocks": sampler.summary(),
         }

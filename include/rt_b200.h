@@ -347,7 +347,7 @@ typedef struct rt_counters {
   uint64_t paths;          /* camera samples generated */
   uint64_t segments;       /* rays traced by extend */
   uint64_t kernel_launches;/* kernels launched by this library since the last reset */
-  uint64_t nodes_visited;  /* only filled when the library is built with RT_COUNTERS */
+  uint64_t nodes_visited;  /* segments traced by the tail kernel (part of `segments`) */
   uint64_t prim_tests;
 } rt_counters;
 int rt_get_counters(rt_context *ctx, rt_counters *out);
@@ -356,7 +356,8 @@ int rt_reset_counters(rt_context *ctx);
 /* Per-stage device timing (profiling aid): while enabled, every kernel launch of the render loop is
  * bracketed by CUDA events on the context stream.  rt_get_stage_times synchronises, adds the elapsed
  * milliseconds and launch counts per stage since the last call and resets them. */
-enum { RT_STAGE_GENERATE = 0, RT_STAGE_EXTEND = 1, RT_STAGE_SHADE = 2, RT_STAGE_ACCUMULATE = 3, RT_STAGE_COUNT = 4 };
+enum { RT_STAGE_GENERATE = 0, RT_STAGE_EXTEND = 1, RT_STAGE_SHADE = 2, RT_STAGE_ACCUMULATE = 3, RT_STAGE_TAIL = 4,
+       RT_STAGE_COUNT = 5 };
 int rt_context_set_stage_timing(rt_context *ctx, int enable);
 int rt_get_stage_times(rt_context *ctx, double ms[RT_STAGE_COUNT], uint64_t launches[RT_STAGE_COUNT]);
 

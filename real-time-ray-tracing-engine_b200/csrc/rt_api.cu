@@ -137,7 +137,10 @@ int render_pass(rt_scene *scene, const rt_camera *camera, rt_film *film, int fir
     StageSpan span(ctx, RT_STAGE_GENERATE);
     launch_generate(ctx, pp, w);
   }
-  for (int bounce = 0; bounce < max_depth; bounce++) {
+  // wavefront launches while the path population is large, then one tail kernel that runs whatever is
+  // left to completion (rt_kernels.cu, k_tail)
+  const int wave_bounces = std::min(max_depth, ctx->wave_bounces);
+  for (int bounce = 0; bounce < wave_bounces; bounce++) {
     {
       StageSpan span(ctx, RT_STAGE_EXTEND);
       launch_extend(ctx, sc, pp, w, bounce);
@@ -147,11 +150,15 @@ int render_pass(rt_scene *scene, const rt_camera *camera, rt_film *film, int fir
       launch_shade(ctx, sc, pp, w, bounce);
     }
   }
+  if (wave_bounces < max_depth) {
+    StageSpan span(ctx, RT_STAGE_TAIL);
+    launch_tail(ctx, sc, pp, w, wave_bounces);
+  }
   {
     StageSpan span(ctx, RT_STAGE_ACCUMULATE);
     launch_accumulate(ctx, pp, w, film->accum);
   }
-  ctx->counters.kernel_launches += 2 + 2 * (uint64_t)max_depth;
+  ctx->counters.kernel_launches += 2 + 2 * (uint64_t)wave_bounces + (wave_bounces < max_depth ? 1 : 0);
   ctx->counters.paths += (uint64_t)pp.n_paths;
   RT_CUDA(cudaGetLastError());
   return RT_OK;
@@ -256,6 +263,8 @@ int rt_context_create(int device, rt_context **out) {
   cudaDeviceProp prop;
   RT_CUDA(cudaGetDeviceProperties(&prop, device));
   ctx->sm_count = prop.multiProcessorCount;
+  if (const char *env = std::getenv("RT_WAVE_BOUNCES")) // tuning / A-B aid: bounces run as wavefront launches
+    ctx->wave_bounces = std::max(0, std::atoi(env));
   RT_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   *out = ctx;
   return RT_OK;
@@ -621,8 +630,8 @@ int rt_get_counters(rt_context *ctx, rt_counters *out) {
     RT_CUDA(cudaMemcpy(stats, ctx->wave.stats, sizeof stats, cudaMemcpyDeviceToHost));
   }
   *out = ctx->counters;
-  out->segments = stats[0];
-  out->nodes_visited = stats[1];
+  out->segments = stats[0] + stats[3]; // wavefront extend launches + tail kernel
+  out->nodes_visited = stats[3];
   out->prim_tests = stats[2];
   return RT_OK;
 }

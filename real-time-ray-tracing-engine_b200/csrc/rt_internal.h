@@ -49,6 +49,7 @@ struct StageTimer {
 struct rt_context {
   int device = 0;
   int sm_count = 0;
+  int wave_bounces = 3; // bounces run as separate extend / shade launches before the tail kernel takes over
   cudaStream_t stream = nullptr;
   WaveBuffers wave;
   rt_counters counters{};
@@ -115,6 +116,7 @@ void launch_gather_records(cudaStream_t s, const void *in, const uint32_t *index
 void launch_generate(const rt_context *ctx, const PassParams &pp, WaveBuffers &w);
 void launch_extend(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int bounce);
 void launch_shade(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int bounce);
+void launch_tail(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int first_bounce);
 void launch_accumulate(const rt_context *ctx, const PassParams &pp, WaveBuffers &w, float4 *film);
 void launch_resolve_rgb8(cudaStream_t s, const float4 *film, int64_t n, double scale, uint8_t *out);
 void launch_resolve_rgb(cudaStream_t s, const float4 *film, int64_t n, double scale, float *out);

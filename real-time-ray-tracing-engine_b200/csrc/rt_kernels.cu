@@ -294,6 +294,139 @@ __global__ void __launch_bounds__(RT_BLOCK)
 }
 
 // ---------------------------------------------------------------------------------------------------
+// tail: the thin end of the path population in ONE launch
+// ---------------------------------------------------------------------------------------------------
+// After the first few bounces only a small fraction of the paths is alive (C2: 4 % at bounce 3, 0.5 % at
+// bounce 7), and a wavefront launch per stage is then pure latency: ~30 us per extend launch for a few
+// ten-thousand rays.  k_tail takes the queue of bounce `first_bounce` and runs every remaining path to
+// its end inside the kernel: persistent warps fetch paths dynamically, traverse (same while-while loop as
+// k_extend) and, when too few lanes are still traversing, shade the finished segments in place; a lane
+// whose path continues re-enters traversal with the scattered ray (written back to its own queue slot), a
+// lane whose path ended fetches the next path.  Philox keys carry the lane's own bounce index, so the
+// image is identical to the all-wavefront schedule.
+__global__ void __launch_bounds__(RT_BLOCK, 4)
+    k_tail(const __grid_constant__ DScene sc, const __grid_constant__ PassParams pp, float4 *__restrict__ ray_a,
+           float4 *__restrict__ ray_b, float2 *__restrict__ hit, float4 *__restrict__ throughput,
+           float4 *__restrict__ radiance, const unsigned int *__restrict__ counts, unsigned int *__restrict__ cursor,
+           int first_bounce, int has_media, unsigned long long *stats) {
+  __shared__ int s_ref[RT_STACK_SMEM * RT_BLOCK];
+  __shared__ float s_t[RT_STACK_SMEM * RT_BLOCK];
+  SmemStack stack;
+  stack.s_ref = s_ref + threadIdx.x;
+  stack.s_t = s_t + threadIdx.x;
+  const unsigned int n = counts[first_bounce];
+  const unsigned int lane = threadIdx.x & 31u;
+  const unsigned int lt_mask = (1u << lane) - 1u;
+
+  RayTrav rt = make_trav(F3(0.f, 0.f, 0.f), F3(1.f, 1.f, 1.f));
+  Hit best;
+  int sp = 0, ref = RT_DONE, bounce = first_bounce;
+  unsigned int q = 0, segments = 0;
+  bool exhausted = false;
+  best.t = -1.0f; // no segment held
+  best.prim = -1;
+
+  for (;;) {
+    // ---- fetch: lanes without a path take the next ones of the queue ----
+    unsigned int idle = __ballot_sync(0xffffffffu, ref == RT_DONE && best.t == -1.0f);
+    if (idle && !exhausted) {
+      unsigned int base = 0;
+      int leader = __ffs(idle) - 1;
+      if ((int)lane == leader)
+        base = atomicAdd(cursor, (unsigned int)__popc(idle));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (ref == RT_DONE && best.t == -1.0f) {
+        unsigned int mine = base + (unsigned int)__popc(idle & lt_mask);
+        if (mine < n) {
+          q = mine;
+          float4 a = ray_a[q], b = ray_b[q];
+          rt = make_trav(F3(a.x, a.y, a.z), F3(b.x, b.y, b.z));
+          best.t = RT_INF_F;
+          best.prim = -1;
+          sp = 0;
+          ref = 0;
+          bounce = first_bounce;
+          segments++;
+        }
+      }
+      exhausted = base + (unsigned int)__popc(idle) >= n;
+    }
+    if (__all_sync(0xffffffffu, ref == RT_DONE && best.t == -1.0f))
+      break;
+
+    // ---- traverse until too few lanes are still inside the tree ----
+    for (;;) {
+      while (ref >= 0 && ref != RT_DONE) {
+        if (!node_visit(sc, ref, rt, RT_T_MIN, best.t, stack, sp, ref))
+          if (!stack_pop(stack, sp, best.t, ref))
+            ref = RT_DONE;
+      }
+      if (ref < 0) {
+        float4 a = ray_a[q], b = ray_b[q];
+        Ray r;
+        r.o = F3(a.x, a.y, a.z);
+        r.d = F3(b.x, b.y, b.z);
+        r.time = a.w;
+        int skip = __float_as_int(hit[q].y);
+        RayKey key;
+        key.seed = pp.seed;
+        key.pixel = key.sample = 0;
+        key.bounce = (uint32_t)bounce;
+        if (has_media) {
+          int k;
+          path_to_key(pp, __float_as_int(b.w), bounce, key, k);
+        }
+        do {
+          leaf_test(sc, ~ref, r, RT_T_MIN, best, skip, key);
+          if (!stack_pop(stack, sp, best.t, ref))
+            ref = RT_DONE;
+        } while (ref < 0);
+      }
+      unsigned int busy = __ballot_sync(0xffffffffu, ref != RT_DONE);
+      if (__popc(busy) < RT_REFILL)
+        break;
+    }
+
+    // ---- shade the segments whose traversal is complete ----
+    if (ref == RT_DONE && best.t != -1.0f) {
+      float4 a = ray_a[q], b = ray_b[q];
+      int path = __float_as_int(b.w);
+      Ray r;
+      r.o = F3(a.x, a.y, a.z);
+      r.d = F3(b.x, b.y, b.z);
+      r.time = a.w;
+      RayKey key;
+      int k;
+      path_to_key(pp, path, bounce, key, k);
+      float4 tp = throughput[path];
+      ShadeResult res;
+      bool cont = shade_segment(sc, r, best, F3(tp.x, tp.y, tp.z), key, bounce + 1 >= pp.max_depth, res);
+      if (cont) {
+        ray_a[q] = make_float4(res.next.o.x, res.next.o.y, res.next.o.z, res.next.time);
+        ray_b[q] = make_float4(res.next.d.x, res.next.d.y, res.next.d.z, __int_as_float(path));
+        hit[q] = make_float2(0.f, __int_as_float(res.next_skip_prim));
+        throughput[path] = make_float4(res.throughput.x, res.throughput.y, res.throughput.z, 0.f);
+        rt = make_trav(res.next.o, res.next.d);
+        best.t = RT_INF_F;
+        best.prim = -1;
+        sp = 0;
+        ref = 0;
+        bounce++;
+        segments++;
+      } else {
+        radiance[path] = make_float4(res.radiance.x, res.radiance.y, res.radiance.z, 0.f);
+        best.t = -1.0f;
+      }
+    }
+  }
+  // segments traced by this warp -> stats[3]
+  for (int o = 16; o > 0; o >>= 1)
+    segments += __shfl_xor_sync(0xffffffffu, segments, o);
+  if (lane == 0 && segments)
+    atomicAdd(&stats[3], (unsigned long long)segments);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // accumulate / resolve
 // ---------------------------------------------------------------------------------------------------
 __global__ void k_accumulate(const float4 *__restrict__ radiance, int n_owned, int n_samples, float4 *__restrict__ film) {
@@ -589,6 +722,16 @@ void launch_shade(const rt_context *ctx, const DScene &sc, const PassParams &pp,
   k_shade<<<need < sh.blocks ? need : sh.blocks, RT_BLOCK, 0, ctx->stream>>>(sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b],
                                                                              w.ray_a[nb], w.ray_b[nb], w.hit[nb],
                                                                              w.throughput, w.radiance, w.counts, bounce);
+}
+
+void launch_tail(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int first_bounce) {
+  LaunchShape sh = rt_persistent_shape(ctx, RT_BLOCK, 4);
+  int need = ceil_div(pp.n_paths, RT_BLOCK);
+  int b = first_bounce & 1;
+  unsigned int *cursor = w.counts + (pp.max_depth + 2) + first_bounce;
+  k_tail<<<need < sh.blocks ? need : sh.blocks, RT_BLOCK, 0, ctx->stream>>>(sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b],
+                                                                            w.throughput, w.radiance, w.counts, cursor,
+                                                                            first_bounce, sc.n_media > 0, w.stats);
 }
 
 void launch_accumulate(const rt_context *ctx, const PassParams &pp, WaveBuffers &w, float4 *film) {

@@ -38,9 +38,9 @@ class Context:
         abi.check(self.lib, self.lib.rt_context_set_stage_timing(self._h, int(enable)), "rt_context_set_stage_timing")
 
     def stage_times(self):
-        """(ms[4], launches[4]) for generate / extend / shade / accumulate since the last call."""
-        ms = (C.c_double * 4)()
-        n = (C.c_uint64 * 4)()
+        """(ms[5], launches[5]) for generate / extend / shade / accumulate / tail since the last call."""
+        ms = (C.c_double * 5)()
+        n = (C.c_uint64 * 5)()
         abi.check(self.lib, self.lib.rt_get_stage_times(self._h, ms, n), "rt_get_stage_times")
         return list(ms), list(n)
 

@@ -150,15 +150,18 @@ int render_pass(rt_scene *scene, const rt_camera *camera, rt_film *film, int fir
       launch_shade(ctx, sc, pp, w, bounce);
     }
   }
-  if (wave_bounces < max_depth) {
+  // each tail launch covers at most tail_span bounces and queues its survivors for the next one
+  int tail_launches = 0;
+  for (int first = wave_bounces, buffer = wave_bounces & 1; first < max_depth; first += ctx->tail_span, buffer ^= 1) {
     StageSpan span(ctx, RT_STAGE_TAIL);
-    launch_tail(ctx, sc, pp, w, wave_bounces);
+    launch_tail(ctx, sc, pp, w, first, std::min(max_depth, first + ctx->tail_span), buffer);
+    tail_launches++;
   }
   {
     StageSpan span(ctx, RT_STAGE_ACCUMULATE);
     launch_accumulate(ctx, pp, w, film->accum);
   }
-  ctx->counters.kernel_launches += 2 + 2 * (uint64_t)wave_bounces + (wave_bounces < max_depth ? 1 : 0);
+  ctx->counters.kernel_launches += 2 + 2 * (uint64_t)wave_bounces + (uint64_t)tail_launches;
   ctx->counters.paths += (uint64_t)pp.n_paths;
   RT_CUDA(cudaGetLastError());
   return RT_OK;
@@ -265,6 +268,8 @@ int rt_context_create(int device, rt_context **out) {
   ctx->sm_count = prop.multiProcessorCount;
   if (const char *env = std::getenv("RT_WAVE_BOUNCES")) // tuning / A-B aid: bounces run as wavefront launches
     ctx->wave_bounces = std::max(0, std::atoi(env));
+  if (const char *env = std::getenv("RT_TAIL_SPAN"))
+    ctx->tail_span = std::max(1, std::atoi(env));
   RT_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   *out = ctx;
   return RT_OK;

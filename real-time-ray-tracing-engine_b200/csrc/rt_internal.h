@@ -50,6 +50,8 @@ struct rt_context {
   int device = 0;
   int sm_count = 0;
   int wave_bounces = 3; // bounces run as separate extend / shade launches before the tail kernel takes over
+  int tail_span = 1 << 20; // bounces covered by one tail launch (measured: one launch for the whole tail is
+                           // fastest, even at depth 50; shorter spans chain launches through the queues)
   cudaStream_t stream = nullptr;
   WaveBuffers wave;
   rt_counters counters{};
@@ -116,7 +118,8 @@ void launch_gather_records(cudaStream_t s, const void *in, const uint32_t *index
 void launch_generate(const rt_context *ctx, const PassParams &pp, WaveBuffers &w);
 void launch_extend(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int bounce);
 void launch_shade(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int bounce);
-void launch_tail(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int first_bounce);
+void launch_tail(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int first_bounce,
+                 int end_bounce, int buffer);
 void launch_accumulate(const rt_context *ctx, const PassParams &pp, WaveBuffers &w, float4 *film);
 void launch_resolve_rgb8(cudaStream_t s, const float4 *film, int64_t n, double scale, uint8_t *out);
 void launch_resolve_rgb(cudaStream_t s, const float4 *film, int64_t n, double scale, float *out);

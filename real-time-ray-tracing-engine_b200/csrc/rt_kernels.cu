@@ -306,9 +306,10 @@ __global__ void __launch_bounds__(RT_BLOCK)
 // image is identical to the all-wavefront schedule.
 __global__ void __launch_bounds__(RT_BLOCK, 4)
     k_tail(const __grid_constant__ DScene sc, const __grid_constant__ PassParams pp, float4 *__restrict__ ray_a,
-           float4 *__restrict__ ray_b, float2 *__restrict__ hit, float4 *__restrict__ throughput,
-           float4 *__restrict__ radiance, const unsigned int *__restrict__ counts, unsigned int *__restrict__ cursor,
-           int first_bounce, int has_media, unsigned long long *stats) {
+           float4 *__restrict__ ray_b, float2 *__restrict__ hit, float4 *__restrict__ next_a,
+           float4 *__restrict__ next_b, float2 *__restrict__ next_hit, float4 *__restrict__ throughput,
+           float4 *__restrict__ radiance, unsigned int *__restrict__ counts, unsigned int *__restrict__ cursor,
+           int first_bounce, int end_bounce, int has_media, unsigned long long *stats) {
   __shared__ int s_ref[RT_STACK_SMEM * RT_BLOCK];
   __shared__ float s_t[RT_STACK_SMEM * RT_BLOCK];
   SmemStack stack;
@@ -401,7 +402,16 @@ __global__ void __launch_bounds__(RT_BLOCK, 4)
       float4 tp = throughput[path];
       ShadeResult res;
       bool cont = shade_segment(sc, r, best, F3(tp.x, tp.y, tp.z), key, bounce + 1 >= pp.max_depth, res);
-      if (cont) {
+      if (cont && bounce + 1 >= end_bounce) {
+        // the launch covers bounces [first_bounce, end_bounce): survivors are queued for the next launch,
+        // so one very long path (glass, mirrors) cannot keep a whole launch waiting on a single lane
+        unsigned int slot = atomicAdd(&counts[end_bounce], 1u);
+        next_a[slot] = make_float4(res.next.o.x, res.next.o.y, res.next.o.z, res.next.time);
+        next_b[slot] = make_float4(res.next.d.x, res.next.d.y, res.next.d.z, __int_as_float(path));
+        next_hit[slot] = make_float2(0.f, __int_as_float(res.next_skip_prim));
+        throughput[path] = make_float4(res.throughput.x, res.throughput.y, res.throughput.z, 0.f);
+        best.t = -1.0f;
+      } else if (cont) {
         ray_a[q] = make_float4(res.next.o.x, res.next.o.y, res.next.o.z, res.next.time);
         ray_b[q] = make_float4(res.next.d.x, res.next.d.y, res.next.d.z, __int_as_float(path));
         hit[q] = make_float2(0.f, __int_as_float(res.next_skip_prim));
@@ -724,14 +734,15 @@ void launch_shade(const rt_context *ctx, const DScene &sc, const PassParams &pp,
                                                                              w.throughput, w.radiance, w.counts, bounce);
 }
 
-void launch_tail(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int first_bounce) {
+void launch_tail(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int first_bounce,
+                 int end_bounce, int buffer) {
   LaunchShape sh = rt_persistent_shape(ctx, RT_BLOCK, 4);
   int need = ceil_div(pp.n_paths, RT_BLOCK);
-  int b = first_bounce & 1;
+  int b = buffer, nb = buffer ^ 1;
   unsigned int *cursor = w.counts + (pp.max_depth + 2) + first_bounce;
-  k_tail<<<need < sh.blocks ? need : sh.blocks, RT_BLOCK, 0, ctx->stream>>>(sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b],
-                                                                            w.throughput, w.radiance, w.counts, cursor,
-                                                                            first_bounce, sc.n_media > 0, w.stats);
+  k_tail<<<need < sh.blocks ? need : sh.blocks, RT_BLOCK, 0, ctx->stream>>>(
+      sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b], w.ray_a[nb], w.ray_b[nb], w.hit[nb], w.throughput, w.radiance, w.counts,
+      cursor, first_bounce, end_bounce, sc.n_media > 0, w.stats);
 }
 
 void launch_accumulate(const rt_context *ctx, const PassParams &pp, WaveBuffers &w, float4 *film) {

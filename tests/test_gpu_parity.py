@@ -326,3 +326,31 @@ def test_million_sphere_scene_builds_and_traces(ctx, oracle, host_scenes):
     assert np.array_equal(a["prim"], b["prim"]) and np.array_equal(a["t"], b["t"])
     oracle.ora_scene_destroy(osc)
     scene.close()
+
+
+def test_schedule_does_not_change_the_paths(host_scenes, monkeypatch):
+    """All-wavefront, wavefront + tail kernel, and chained short tail launches trace the same paths: the Philox
+    key of a segment is (pixel, sample, bounce) whatever kernel traces it.  The shading arithmetic is inlined
+    into two kernels (k_shade, k_tail), so the compiler may contract multiply-adds differently: pixels agree
+    to FP32 rounding, not necessarily bit for bit, and a rare path may flip at a silhouette."""
+    hs = host_scenes("cornell_smoke", 0, -1)
+    cfg = hs.camera_config(96, 4, 20)
+    cam = engine.camera_from_config(cfg)
+    images, segments = [], []
+    for wave, span in [("20", "6"), ("3", "6"), ("1", "2"), ("0", "50")]:
+        monkeypatch.setenv("RT_WAVE_BOUNCES", wave)
+        monkeypatch.setenv("RT_TAIL_SPAN", span)
+        c = engine.Context(0)
+        scene = engine.Scene(c, hs.desc)
+        film = engine.Film(c, cam.image_width, cam.image_height)
+        engine.render_static(scene, cam, film, 2, 20, 77)
+        images.append(film.read_rgb(0.25).astype(np.float64))
+        segments.append(c.counters().segments)
+        film.close()
+        scene.close()
+        c.close()
+    for img, seg in zip(images[1:], segments[1:]):
+        close = np.abs(img - images[0]).max(axis=1) <= 1e-4 * np.maximum(1.0, images[0].max(axis=1))
+        assert close.mean() > 0.995
+        assert abs(img.mean() - images[0].mean()) < 1e-3 * images[0].mean()
+        assert abs(seg - segments[0]) < 2e-3 * segments[0]

@@ -182,6 +182,7 @@ def main():
             render(ctx, stream, sc, cam, 1, 8, 1, world, rank, frames=3, dynamic=True)
             ms, img, spp_seg = render(ctx, stream, sc, cam, 1, 8, 100, world, rank, frames=20, dynamic=True)
             cam2 = engine.camera_from_config(hs.camera_config(1920, 64, 50))
+            render(ctx, stream, sc, cam2, 2, 50, 1, world, rank)  # warm-up: sizes the queues for full passes
             ms2, img2, spp_seg2 = render(ctx, stream, sc, cam2, 8, 50, 5, world, rank)
             emit({"config": "c4 1M textured moving spheres 1920x1080", "frame_1spp_depth8_ms": ms / 20,
                   "frame_mpath_s": 1920 * 1080 / (ms / 20) / 1e3, "segments_per_path": spp_seg,

@@ -87,9 +87,8 @@ __global__ void __launch_bounds__(RT_BLOCK)
     Ray r = camera_ray(pp.cam, col, row, s_i, s_j, pp.recip_sqrt_spp, u0, u1);
     ray_a[p] = make_float4(r.o.x, r.o.y, r.o.z, r.time);
     ray_b[p] = make_float4(r.d.x, r.d.y, r.d.z, __int_as_float(p));
-    hit[p] = make_float2(0.f, __int_as_float(-1));
-    throughput[p] = make_float4(1.f, 1.f, 1.f, 0.f);
-    radiance[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // no per-path initialisation is written: at bounce 0 the throughput is 1 and no primitive is skipped
+    // (the kernels know), and every path writes its radiance exactly once when it ends
   }
   if (blockIdx.x == 0 && threadIdx.x == 0)
     counts[0] = (unsigned int)pp.n_paths;
@@ -174,7 +173,7 @@ __global__ void __launch_bounds__(RT_BLOCK, 8)
         r.o = F3(a.x, a.y, a.z);
         r.d = F3(b.x, b.y, b.z);
         r.time = a.w;
-        int skip = __float_as_int(hit[q].y);
+        int skip = bounce == 0 ? -1 : __float_as_int(hit[q].y);
         RayKey key;
         key.seed = pp.seed;
         key.pixel = key.sample = 0;
@@ -234,7 +233,7 @@ __global__ void __launch_bounds__(RT_BLOCK)
     Hit best;
     best.t = RT_INF_F;
     best.prim = -1;
-    traverse(sc, r, RT_T_MIN, best, __float_as_int(h.y), key, stack);
+    traverse(sc, r, RT_T_MIN, best, bounce == 0 ? -1 : __float_as_int(h.y), key, stack);
     hit[q] = make_float2(best.t, __int_as_float(best.prim));
   }
 }
@@ -271,7 +270,7 @@ __global__ void __launch_bounds__(RT_BLOCK)
       RayKey key;
       int k;
       path_to_key(pp, path, bounce, key, k);
-      float4 tp = throughput[path];
+      float4 tp = bounce == 0 ? make_float4(1.f, 1.f, 1.f, 0.f) : throughput[path];
       cont = shade_segment(sc, r, ht, F3(tp.x, tp.y, tp.z), key, last_bounce, res);
       if (!cont)
         radiance[path] = make_float4(res.radiance.x, res.radiance.y, res.radiance.z, 0.f);
@@ -368,7 +367,7 @@ __global__ void __launch_bounds__(RT_BLOCK, 4)
         r.o = F3(a.x, a.y, a.z);
         r.d = F3(b.x, b.y, b.z);
         r.time = a.w;
-        int skip = __float_as_int(hit[q].y);
+        int skip = bounce == 0 ? -1 : __float_as_int(hit[q].y);
         RayKey key;
         key.seed = pp.seed;
         key.pixel = key.sample = 0;
@@ -399,7 +398,7 @@ __global__ void __launch_bounds__(RT_BLOCK, 4)
       RayKey key;
       int k;
       path_to_key(pp, path, bounce, key, k);
-      float4 tp = throughput[path];
+      float4 tp = bounce == 0 ? make_float4(1.f, 1.f, 1.f, 0.f) : throughput[path];
       ShadeResult res;
       bool cont = shade_segment(sc, r, best, F3(tp.x, tp.y, tp.z), key, bounce + 1 >= pp.max_depth, res);
       if (cont && bounce + 1 >= end_bounce) {

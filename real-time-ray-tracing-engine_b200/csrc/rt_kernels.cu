@@ -102,7 +102,12 @@ __global__ void __launch_bounds__(RT_BLOCK)
 // device-side cursor; lanes first descend inner nodes only, then test leaves only, so a warp never
 // executes box code and primitive code in the same iteration; when fewer than RT_REFILL lanes still hold a
 // ray, the idle lanes fetch new ones (one atomicAdd per warp).
-#define RT_REFILL 22
+#ifndef RT_REFILL
+#define RT_REFILL 16 // measured: 16 beats 22 and 28 by 1-2 %
+#endif
+#ifndef RT_TAIL_BLOCKS
+#define RT_TAIL_BLOCKS 4 // resident blocks per SM of k_tail (register budget = 65536 / (128 * RT_TAIL_BLOCKS))
+#endif
 #define RT_DONE 0x7fffffff
 
 __global__ void __launch_bounds__(RT_BLOCK, 8)
@@ -241,7 +246,10 @@ __global__ void __launch_bounds__(RT_BLOCK)
 // ---------------------------------------------------------------------------------------------------
 // shade + queue compaction
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(RT_BLOCK)
+#ifndef RT_SHADE_BLOCKS
+#define RT_SHADE_BLOCKS 8 // resident blocks per SM (64 registers): k_shade is latency bound, occupancy wins over a few spills
+#endif
+__global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_BLOCKS)
     k_shade(const __grid_constant__ DScene sc, const __grid_constant__ PassParams pp, const float4 *__restrict__ ray_a,
             const float4 *__restrict__ ray_b, const float2 *__restrict__ hit, float4 *__restrict__ next_a,
             float4 *__restrict__ next_b, float2 *__restrict__ next_hit, float4 *__restrict__ throughput,
@@ -303,7 +311,7 @@ __global__ void __launch_bounds__(RT_BLOCK)
 // whose path continues re-enters traversal with the scattered ray (written back to its own queue slot), a
 // lane whose path ended fetches the next path.  Philox keys carry the lane's own bounce index, so the
 // image is identical to the all-wavefront schedule.
-__global__ void __launch_bounds__(RT_BLOCK, 4)
+__global__ void __launch_bounds__(RT_BLOCK, RT_TAIL_BLOCKS)
     k_tail(const __grid_constant__ DScene sc, const __grid_constant__ PassParams pp, float4 *__restrict__ ray_a,
            float4 *__restrict__ ray_b, float2 *__restrict__ hit, float4 *__restrict__ next_a,
            float4 *__restrict__ next_b, float2 *__restrict__ next_hit, float4 *__restrict__ throughput,
@@ -735,7 +743,7 @@ void launch_shade(const rt_context *ctx, const DScene &sc, const PassParams &pp,
 
 void launch_tail(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int first_bounce,
                  int end_bounce, int buffer) {
-  LaunchShape sh = rt_persistent_shape(ctx, RT_BLOCK, 4);
+  LaunchShape sh = rt_persistent_shape(ctx, RT_BLOCK, RT_TAIL_BLOCKS);
   int need = ceil_div(pp.n_paths, RT_BLOCK);
   int b = buffer, nb = buffer ^ 1;
   unsigned int *cursor = w.counts + (pp.max_depth + 2) + first_bounce;

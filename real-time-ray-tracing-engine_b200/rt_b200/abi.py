@@ -8,7 +8,7 @@ import os
 
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REPO_DIR = os.path.dirname(PKG_DIR)
-LIB_PATH = os.path.join(PKG_DIR, "csrc", "librt_b200.so")
+LIB_PATH = os.environ.get("RT_B200_LIB") or os.path.join(PKG_DIR, "csrc", "librt_b200.so")  # override: A/B builds
 HOST_LIB_PATH = os.path.join(PKG_DIR, "host", "librt_host.so")
 
 RT_OK, RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_NO_DEVICE, RT_ERR_UNSUPPORTED = range(5)

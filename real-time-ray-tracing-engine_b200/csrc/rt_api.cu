@@ -270,6 +270,8 @@ int rt_context_create(int device, rt_context **out) {
     ctx->wave_bounces = std::max(0, std::atoi(env));
   if (const char *env = std::getenv("RT_TAIL_SPAN"))
     ctx->tail_span = std::max(1, std::atoi(env));
+  if (const char *env = std::getenv("RT_PASS_PATHS"))
+    ctx->pass_paths = std::max<int64_t>(1, std::atoll(env));
   RT_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   *out = ctx;
   return RT_OK;
@@ -474,7 +476,7 @@ int rt_render_accumulate(rt_scene *scene, const rt_camera *camera, rt_film *film
 // so that the queues stay modest.
 static int render_strata(rt_scene *scene, const rt_camera *camera, rt_film *film, int first, int count, int sqrt_spp,
                          int max_depth, uint64_t seed) {
-  const int64_t target_paths = (int64_t)4 << 20;
+  const int64_t target_paths = scene->ctx->pass_paths;
   int per_pass = (int)std::max<int64_t>(1, std::min<int64_t>(count, target_paths / std::max<int64_t>(film->n_owned, 1)));
   for (int s = first; s < first + count; s += per_pass) {
     int n = std::min(per_pass, first + count - s);

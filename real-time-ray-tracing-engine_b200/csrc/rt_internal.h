@@ -52,6 +52,8 @@ struct rt_context {
   int wave_bounces = 3; // bounces run as separate extend / shade launches before the tail kernel takes over
   int tail_span = 1 << 20; // bounces covered by one tail launch (measured: one launch for the whole tail is
                            // fastest, even at depth 50; shorter spans chain launches through the queues)
+  int64_t pass_paths = (int64_t)16 << 20; // static renders: paths per wavefront pass (queue storage ~110 B per
+                                          // path; measured 4 M / 8 M / 16 M / 32 M: 16 M is fastest on C1 and C3)
   cudaStream_t stream = nullptr;
   WaveBuffers wave;
   rt_counters counters{};

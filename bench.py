@@ -8,7 +8,7 @@ Workload (BASELINE.json configs[1]): the reference's random-spheres scene (485 o
 pixel.  With N GPUs the image is cut into 8-scanline tiles interleaved over the ranks and per-GPU work is
 kept constant (weak scaling): a step renders N strata of the whole frame, each rank tracing N strata of
 its own 1/N of the tiles, and the compact films are gathered to rank 0 (NCCL over NVLink) and scattered
-into the full frame at the end of every step.
+into the full frame at the end of every step (RGB8, after the device tone map).
 
 Printed JSON (one line, rank 0):
   value      whole-job Mpath-samples/s with the scene resident in HBM, device-timed (CUDA events, max over ranks)
@@ -173,12 +173,11 @@ def run_ours(args):
 
     owned = distributed.owned_pixels(W, H, rank, world, TILE_ROWS)
     accum = torch.zeros((owned, 4), dtype=torch.float32, device="cuda")
-    full = torch.zeros((npix, 4), dtype=torch.float32, device="cuda") if rank == 0 else None
+    own_rgb8 = torch.zeros((owned, 3), dtype=torch.uint8, device="cuda")  # this rank's tiles, tone-mapped
     rgb8_dev = torch.zeros((npix, 3), dtype=torch.uint8, device="cuda") if rank == 0 else None
     rgb8_host = torch.zeros((npix, 3), dtype=torch.uint8).pin_memory() if rank == 0 else None
     torch.cuda.synchronize()
     film = engine.Film(ctx, W, H, rank, world, TILE_ROWS, external_accum=accum.data_ptr())
-    full_film = engine.Film(ctx, W, H, external_accum=full.data_ptr()) if rank == 0 else None
     l2_flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
     def render_step(step):
@@ -188,15 +187,23 @@ def run_ours(args):
         else:  # the step's strata in ONE wavefront pass (same launch count as a single-GPU frame)
             engine.render_strata(scene, cam, film, 0, strata_per_step, sqrt_spp, DEPTH, 1000 + step)
 
-    def assemble(step):
-        """Frame assembly: gather the compact films to rank 0 and scatter them into the row-major frame."""
+    def present(step, frame_dev):
+        """The displayed frame: every rank tone-maps its own tiles to RGB8 on the device (DynamicCamera::
+        update_texture, to_byte); with several GPUs the RGB8 tiles (3 bytes per pixel) are gathered to rank 0 over
+        NCCL / NVLink and scattered into the row-major frame."""
+        scale = 1.0 / max(1, film.samples)
         if world == 1:
+            abi.check(ctx.lib, ctx.lib.rt_film_resolve_rgb8_device(film._h, scale, frame_dev.data_ptr()),
+                      "rt_film_resolve_rgb8_device")
             return
+        abi.check(ctx.lib, ctx.lib.rt_film_resolve_rgb8_device(film._h, scale, own_rgb8.data_ptr()),
+                  "rt_film_resolve_rgb8_device")
         with torch.cuda.stream(stream):
-            gathered = distributed.gather_film(accum, W, H, TILE_ROWS, dst=0)
+            gathered = distributed.gather_film(own_rgb8, W, H, TILE_ROWS, dst=0)
             if rank == 0:
-                abi.check(ctx.lib, ctx.lib.rt_film_scatter_gathered(ctx._h, W, H, world, TILE_ROWS, gathered.data_ptr(),
-                                                                    full.data_ptr()), "rt_film_scatter_gathered")
+                abi.check(ctx.lib, ctx.lib.rt_film_scatter_gathered_rgb8(ctx._h, W, H, world, TILE_ROWS,
+                                                                         gathered.data_ptr(), frame_dev.data_ptr()),
+                          "rt_film_scatter_gathered_rgb8")
 
     def barrier():
         if world > 1:
@@ -221,7 +228,7 @@ def run_ours(args):
         with torch.cuda.stream(stream):
             l2_flush.fill_(s & 0xFF)  # evict the scene and queues from L2 between timed steps
         render_step(s)
-        assemble(s)
+        present(s, rgb8_dev)
 
     def flush_only(s):
         with torch.cuda.stream(stream):
@@ -244,14 +251,10 @@ def run_ours(args):
     # ---- end to end through the reference-facing calls, host buffers ----
     # (what DynamicCamera::render_gpu does per frame: launch, synchronise, copy the frame back, tone-map -
     #  here the tone map runs on the device and 3 bytes per pixel cross PCIe instead of 24)
-    target = full_film if world > 1 else film
-
     def e2e_step(s):
         render_step(s)
-        assemble(s)
+        present(s, rgb8_dev)
         if rank == 0:
-            abi.check(ctx.lib, ctx.lib.rt_film_resolve_rgb8_device(target._h, 1.0 / max(1, film.samples),
-                                                                   rgb8_dev.data_ptr()), "rt_film_resolve_rgb8_device")
             with torch.cuda.stream(stream):
                 rgb8_host.copy_(rgb8_dev, non_blocking=True)
         ctx.synchronize()
@@ -287,12 +290,11 @@ def run_ours(args):
 
     def e2e_pipelined_step(s):
         render_step(s)
-        assemble(s)
+        k = s & 1
         if rank == 0:
-            k = s & 1
             stream.wait_event(copied[k])  # the buffer's previous frame has left the device
-            abi.check(ctx.lib, ctx.lib.rt_film_resolve_rgb8_device(target._h, 1.0 / max(1, film.samples),
-                                                                   rgb8_dev2[k].data_ptr()), "rt_film_resolve_rgb8_device")
+        present(s, rgb8_dev2[k] if rank == 0 else None)
+        if rank == 0:
             resolved[k].record(stream)
             copy_stream.wait_event(resolved[k])
             with torch.cuda.stream(copy_stream):
@@ -346,8 +348,9 @@ def run_ours(args):
             "config": {
                 "workload": f"spheres scene (485 objects, seed 1234) 1920x1080, depth 8, dynamic-mode frames: "
                             f"{strata_per_step} stratum/strata of the whole frame per step (= 1 per GPU), "
-                            f"{TILE_ROWS}-scanline tiles interleaved over {world} GPU(s), scene replicated, compact films "
-                            f"gathered to rank 0 and scattered into the frame every step",
+                            f"{TILE_ROWS}-scanline tiles interleaved over {world} GPU(s), scene replicated; every step ends with "
+                            f"the displayed frame: device to_byte resolve of each rank's tiles, RGB8 tiles gathered to rank 0 "
+                            f"(NCCL) and scattered into the row-major frame",
                 "paths_per_step": paths_per_step, "segments_per_path": counters.segments / max(1, counters.paths),
                 "bvh": {"primitives": info.n_prims, "nodes4": info.n_nodes, "device_build_ms": info.build_ms},
                 "l2": "192 MiB buffer written between timed steps (flush time measured separately and subtracted)"},
@@ -385,11 +388,9 @@ def run_ours(args):
     # pinned-memory allocator records an event on that stream when a block is released)
     barrier()
     film.close()
-    if full_film:
-        full_film.close()
     if rank == 0:
         del rgb8_dev2, rgb8_host2, resolved, copied
-    del accum, full, rgb8_dev, rgb8_host, l2_flush, copy_stream
+    del accum, own_rgb8, rgb8_dev, rgb8_host, l2_flush, copy_stream
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
     scene.close()

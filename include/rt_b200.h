@@ -333,6 +333,10 @@ int rt_film_resolve_rgb8_device(rt_film *film, double scale, void *device_rgb8);
  * row-major width x height float4 image on the device. */
 int rt_film_scatter_gathered(rt_context *ctx, int width, int height, int n_ranks, int tile_rows,
                              const void *device_gathered, void *device_full_image);
+/* The same for frames that every rank already resolved to RGB8 (rt_film_resolve_rgb8_device): 3 bytes per
+ * pixel cross NVLink instead of 16 - what a displayed progressive frame needs. */
+int rt_film_scatter_gathered_rgb8(rt_context *ctx, int width, int height, int n_ranks, int tile_rows,
+                                  const void *device_gathered, void *device_full_image);
 
 /* Single-process multi-GPU gather: copy each film's owned tiles into rank 0's full image over
  * NVLink peer copies.  films[r] must be rank r of n_ranks.  host_rgb (width*height*3 floats) gets

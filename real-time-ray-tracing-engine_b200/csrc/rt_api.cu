@@ -564,16 +564,27 @@ int rt_film_resolve_rgb8(rt_film *film, double scale, uint8_t *host_rgb8) {
   return RT_OK;
 }
 
-int rt_film_scatter_gathered(rt_context *ctx, int width, int height, int n_ranks, int tile_rows,
-                             const void *device_gathered, void *device_full_image) {
-  if (!ctx || !device_gathered || !device_full_image || width < 1 || height < 1 || n_ranks < 1 || tile_rows < 1)
-    return invalid("rt_film_scatter_gathered: bad argument");
+static int scatter_gathered(rt_context *ctx, int width, int height, int n_ranks, int tile_rows, const void *device_gathered,
+                            void *device_full_image, int bytes_per_pixel) {
+  if (!ctx || !device_gathered || !device_full_image || width < 1 || height < 1 || n_ranks < 1 || n_ranks > 64 ||
+      tile_rows < 1)
+    return invalid("rt_film_scatter_gathered: bad argument (1..64 ranks)");
   RT_CUDA(cudaSetDevice(ctx->device));
-  launch_scatter_gathered(ctx->stream, width, height, n_ranks, tile_rows, (const float4 *)device_gathered,
-                          (float4 *)device_full_image);
+  launch_scatter_gathered(ctx->stream, width, height, n_ranks, tile_rows, device_gathered, device_full_image,
+                          bytes_per_pixel);
   ctx->counters.kernel_launches += 1;
   RT_CUDA(cudaGetLastError());
   return RT_OK;
+}
+
+int rt_film_scatter_gathered(rt_context *ctx, int width, int height, int n_ranks, int tile_rows,
+                             const void *device_gathered, void *device_full_image) {
+  return scatter_gathered(ctx, width, height, n_ranks, tile_rows, device_gathered, device_full_image, 16);
+}
+
+int rt_film_scatter_gathered_rgb8(rt_context *ctx, int width, int height, int n_ranks, int tile_rows,
+                                  const void *device_gathered, void *device_full_image) {
+  return scatter_gathered(ctx, width, height, n_ranks, tile_rows, device_gathered, device_full_image, 3);
 }
 
 // Single-process multi-GPU gather: every rank's compact film is copied over NVLink (peer copy) into
@@ -612,7 +623,7 @@ int rt_film_gather_p2p(rt_film **films, int n_ranks, double scale, float *host_r
   }
   int st = RT_OK;
   if (e == cudaSuccess) {
-    launch_scatter_gathered(ctx0->stream, W, H, n_ranks, films[0]->map.tile_rows, gathered, full);
+    launch_scatter_gathered(ctx0->stream, W, H, n_ranks, films[0]->map.tile_rows, gathered, full, 16);
     rt_film tmp;
     tmp.ctx = ctx0;
     tmp.accum = full;

@@ -125,8 +125,8 @@ void launch_tail(const rt_context *ctx, const DScene &sc, const PassParams &pp, 
 void launch_accumulate(const rt_context *ctx, const PassParams &pp, WaveBuffers &w, float4 *film);
 void launch_resolve_rgb8(cudaStream_t s, const float4 *film, int64_t n, double scale, uint8_t *out);
 void launch_resolve_rgb(cudaStream_t s, const float4 *film, int64_t n, double scale, float *out);
-void launch_scatter_gathered(cudaStream_t s, int width, int height, int n_ranks, int tile_rows, const float4 *gathered,
-                             float4 *full);
+void launch_scatter_gathered(cudaStream_t s, int width, int height, int n_ranks, int tile_rows, const void *gathered,
+                             void *full, int bytes_per_pixel); // 16: float4 sums, 3: RGB8
 
 // parity hook
 void launch_trace_fast(const rt_context *ctx, const DScene &sc, const rt_ray *d_rays, int64_t n, uint64_t seed,

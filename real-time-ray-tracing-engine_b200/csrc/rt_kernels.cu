@@ -482,9 +482,18 @@ __global__ void k_resolve_rgb(const float4 *__restrict__ film, long long n, doub
   }
 }
 
-// Rank-major gathered compact films -> one row-major image.
-__global__ void k_scatter_gathered(int width, int height, int n_ranks, int tile_rows,
-                                   const float4 *__restrict__ gathered, float4 *__restrict__ full) {
+// Rank-major gathered compact films -> one row-major image (float4 radiance sums or RGB8 frames).
+#define RT_MAX_RANKS 64
+struct RankBases {
+  long long first_pixel[RT_MAX_RANKS]; // offset of rank r's block in the gathered buffer, in pixels
+};
+struct Rgb8 {
+  unsigned char r, g, b;
+};
+
+template <class Pixel>
+__global__ void k_scatter_gathered(int width, int height, int n_ranks, int tile_rows, const __grid_constant__ RankBases bases,
+                                   const Pixel *__restrict__ gathered, Pixel *__restrict__ full) {
   long long total = (long long)width * height;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride) {
@@ -494,10 +503,7 @@ __global__ void k_scatter_gathered(int width, int height, int n_ranks, int tile_
     int tile_local = tile / n_ranks;
     // rows this rank owns before `row`: full tiles before tile_local (only the image's last tile can be short)
     int local_row = tile_local * tile_rows + (row - tile * tile_rows);
-    long long base = 0;
-    for (int r = 0; r < rank; r++)
-      base += (long long)owned_rows(height, r, n_ranks, tile_rows) * width;
-    full[g] = gathered[base + (long long)local_row * width + col];
+    full[g] = gathered[bases.first_pixel[rank] + (long long)local_row * width + col];
   }
 }
 
@@ -768,12 +774,24 @@ void launch_resolve_rgb(cudaStream_t s, const float4 *film, int64_t n, double sc
     k_resolve_rgb<<<ceil_div(n, 256) < 4096 ? ceil_div(n, 256) : 4096, 256, 0, s>>>(film, n, scale, out);
 }
 
-void launch_scatter_gathered(cudaStream_t s, int width, int height, int n_ranks, int tile_rows, const float4 *gathered,
-                             float4 *full) {
+void launch_scatter_gathered(cudaStream_t s, int width, int height, int n_ranks, int tile_rows, const void *gathered,
+                             void *full, int bytes_per_pixel) {
   long long total = (long long)width * height;
-  if (total > 0)
-    k_scatter_gathered<<<ceil_div(total, 256) < 4096 ? ceil_div(total, 256) : 4096, 256, 0, s>>>(
-        width, height, n_ranks, tile_rows, gathered, full);
+  if (total <= 0)
+    return;
+  RankBases bases;
+  long long first = 0;
+  for (int r = 0; r < n_ranks; r++) {
+    bases.first_pixel[r] = first;
+    first += (long long)owned_rows(height, r, n_ranks, tile_rows) * width;
+  }
+  int blocks = ceil_div(total, 256) < 4096 ? ceil_div(total, 256) : 4096;
+  if (bytes_per_pixel == 16)
+    k_scatter_gathered<float4><<<blocks, 256, 0, s>>>(width, height, n_ranks, tile_rows, bases, (const float4 *)gathered,
+                                                       (float4 *)full);
+  else
+    k_scatter_gathered<Rgb8><<<blocks, 256, 0, s>>>(width, height, n_ranks, tile_rows, bases, (const Rgb8 *)gathered,
+                                                     (Rgb8 *)full);
 }
 
 void launch_trace_fast(const rt_context *ctx, const DScene &sc, const rt_ray *d_rays, int64_t n, uint64_t seed,

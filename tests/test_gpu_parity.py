@@ -354,3 +354,19 @@ def test_schedule_does_not_change_the_paths(host_scenes, monkeypatch):
         assert close.mean() > 0.995
         assert abs(img.mean() - images[0].mean()) < 1e-3 * images[0].mean()
         assert abs(seg - segments[0]) < 2e-3 * segments[0]
+
+
+def test_scatter_gathered_rgb8_kernel(ctx):
+    import torch
+
+    W, H, n_ranks, tile_rows = 41, 29, 4, 3
+    full = (torch.arange(W * H * 3, device="cuda") % 251).to(torch.uint8).reshape(H, W, 3)
+    parts = [full[torch.from_numpy(distributed.owned_rows(H, r, n_ranks, tile_rows)).cuda()].reshape(-1, 3)
+             for r in range(n_ranks)]
+    gathered = torch.cat(parts).contiguous()
+    out = torch.zeros_like(full)
+    torch.cuda.synchronize()
+    abi.check(ctx.lib, ctx.lib.rt_film_scatter_gathered_rgb8(ctx._h, W, H, n_ranks, tile_rows, gathered.data_ptr(),
+                                                             out.data_ptr()), "rt_film_scatter_gathered_rgb8")
+    ctx.synchronize()
+    assert torch.equal(out, full)

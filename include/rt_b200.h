@@ -55,7 +55,8 @@ typedef enum rt_status {
 
 enum { RT_MAT_LAMBERTIAN = 0, RT_MAT_METAL = 1, RT_MAT_DIELECTRIC = 2, RT_MAT_DIFFUSE_LIGHT = 3,
        RT_MAT_ISOTROPIC = 4 };
-enum { RT_TEX_SOLID = 0, RT_TEX_CHECKER = 1, RT_TEX_NOISE = 2 };
+enum { RT_TEX_SOLID = 0, RT_TEX_CHECKER = 1, RT_TEX_NOISE = 2,
+       RT_TEX_IMAGE = 3 /* not in the reference (it has no image texture); named by the north star */ };
 enum { RT_XF_TRANSLATE = 0, RT_XF_ROTATE_Y = 1 };
 enum { RT_SHAPE_SPHERE = 0, RT_SHAPE_QUAD = 1 };
 /* rt_sphere.flags / rt_quad.flags */
@@ -126,7 +127,7 @@ typedef struct rt_texture {
   int32_t type;    /* RT_TEX_* */
   int32_t even;    /* checker: texture indices */
   int32_t odd;
-  int32_t perlin;  /* noise: index into perlins */
+  int32_t perlin;  /* noise: index into perlins; image: index into images */
   double color[3]; /* solid */
   double scale;    /* checker / noise */
 } rt_texture;
@@ -137,6 +138,16 @@ typedef struct rt_perlin {
   int32_t perm_y[RT_PERLIN_POINTS];
   int32_t perm_z[RT_PERLIN_POINTS];
 } rt_perlin;
+
+/* Image texture data: width x height texels, 3 bytes each (linear RGB, row 0 = top).  Looked up with the
+ * surface coordinates the reference's primitives compute (sphere: Sphere.cpp:136-140, quad: Plane.cpp:93-104):
+ * texel (int(u * width), int((1 - v) * height)), clamped; colour = byte / 255 ("Ray Tracing: The Next Week"
+ * image_texture, which the reference's texture set stops short of). */
+typedef struct rt_image {
+  int32_t width;
+  int32_t height;
+  const uint8_t *rgb;
+} rt_image;
 
 /* Light-sampling proxy (geometry only; main.cpp:57-61).  Sphere: a=center, radius.  Quad:
  * a=corner, b=u, c=v. */
@@ -169,6 +180,10 @@ typedef struct rt_scene_desc {
   const rt_texture *textures;
   const rt_perlin *perlins;
   const rt_light *lights;
+  /* appended in ABI version 1.1: image textures (zero-initialised descriptions have none) */
+  int32_t n_images;
+  int32_t pad_;
+  const rt_image *images;
 } rt_scene_desc;
 
 /* Unified primitive ids reported by rt_trace_rays:

@@ -34,6 +34,7 @@ const char *rth_last_error(void);
  *   "cornell_smoke"     Cornell box with two constant-density media (config 3)
  *   "final"             boxes + light + media + textured spheres + sphere cluster (config 5);
  *                       p0 = boxes per side (<= 0: 20), p1 = cluster spheres (< 0: 1000)
+ *   "earth"             a globe and a picture quad with an image texture (not in the reference)
  * Returns NULL (and sets rth_last_error) for an unknown name. */
 rth_scene *rth_scene_builtin(const char *name, uint64_t seed, int p0, int p1);
 rth_scene *rth_scene_load_json(const char *path);

@@ -389,6 +389,11 @@ ora_scene *ora_scene_create(const rt_scene_desc *desc) {
   s->d.textures = (const rt_texture *)dup_array(desc->textures, (size_t)desc->n_textures, sizeof(rt_texture));
   s->d.perlins = (const rt_perlin *)dup_array(desc->perlins, (size_t)desc->n_perlins, sizeof(rt_perlin));
   s->d.lights = (const rt_light *)dup_array(desc->lights, (size_t)desc->n_lights, sizeof(rt_light));
+  rt_image *images = (rt_image *)dup_array(desc->images, (size_t)desc->n_images, sizeof(rt_image));
+  for (int i = 0; i < desc->n_images; i++)
+    images[i].rgb = (const uint8_t *)dup_array(desc->images[i].rgb,
+                                               (size_t)desc->images[i].width * (size_t)desc->images[i].height, 3);
+  s->d.images = images;
 
   int ns = desc->n_spheres, nq = desc->n_quads;
   s->spheres = (osphere *)calloc((size_t)(ns ? ns : 1), sizeof(osphere));
@@ -482,6 +487,9 @@ void ora_scene_destroy(ora_scene *s) {
   free((void *)s->d.textures);
   free((void *)s->d.perlins);
   free((void *)s->d.lights);
+  for (int i = 0; i < s->d.n_images; i++)
+    free((void *)s->d.images[i].rgb);
+  free((void *)s->d.images);
   free(s->spheres);
   free(s->quads);
   free(s->objects);
@@ -805,6 +813,23 @@ static v3 texture_value(const ora_scene *s, int tex, double u, double v, v3 p) {
     int xi = (int)floor(inv_scale * p.x), yi = (int)floor(inv_scale * p.y), zi = (int)floor(inv_scale * p.z);
     int even = (xi + yi + zi) % 2 == 0;
     return texture_value(s, even ? t->even : t->odd, u, v, p);
+  }
+  if (t->type == RT_TEX_IMAGE) {
+    /* not in the reference: "Ray Tracing: The Next Week" image_texture::value over the (u, v) the
+     * reference's primitives compute (Sphere.cpp:136-140, Plane.cpp:101-102) */
+    const rt_image *im = &s->d.images[t->perlin];
+    if (im->height <= 0 || im->width <= 0)
+      return V(0, 1, 1);
+    double uc = u < 0 ? 0 : (u > 1 ? 1 : u);
+    double vc = 1.0 - (v < 0 ? 0 : (v > 1 ? 1 : v));
+    int i = (int)(uc * im->width), j = (int)(vc * im->height);
+    if (i > im->width - 1)
+      i = im->width - 1;
+    if (j > im->height - 1)
+      j = im->height - 1;
+    const uint8_t *px = im->rgb + 3 * ((size_t)j * (size_t)im->width + (size_t)i);
+    const double color_scale = 1.0 / 255.0;
+    return V(color_scale * px[0], color_scale * px[1], color_scale * px[2]);
   }
   double f = 1 + sin(t->scale * p.z + 10 * perlin_turb(&s->d.perlins[t->perlin], p, 7));
   return vscale(f, V(0.5, 0.5, 0.5));

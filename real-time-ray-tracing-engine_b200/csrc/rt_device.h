@@ -177,6 +177,7 @@ struct DScene {
   const float4 *lights;
   const float4 *perlin_grad;        // 256 float4 per table
   const unsigned char *perlin_perm; // 3 x 256 bytes per table (x, y, z)
+  const uint32_t *texels;           // image textures, one 0x00BBGGRR word per texel, all images back to back
   int n_prims;
   int n_lights;
   int n_media;
@@ -557,11 +558,21 @@ RT_HD float perlin_turb(const DScene &sc, int table, f3 p, int depth) {
   return fabsf(accum);
 }
 
-enum { RT_DTEX_SOLID = 0, RT_DTEX_CHECKER = 1, RT_DTEX_NOISE = 2 };
+enum { RT_DTEX_SOLID = 0, RT_DTEX_CHECKER = 1, RT_DTEX_NOISE = 2, RT_DTEX_IMAGE = 3 };
+
+// Surface coordinates of a hit, as the reference's primitives compute them (Sphere.cpp:136-140 from the
+// outward unit normal; Plane.cpp:93-102: the planar coordinates).  Only image textures read them.
+RT_HD void sphere_uv(f3 outward, float &u, float &v) {
+  float theta = acosf(fminf(fmaxf(-outward.y, -1.f), 1.f));
+  float phi = atan2f(-outward.z, outward.x) + RT_PI_F;
+  u = phi * (0.5f / RT_PI_F);
+  v = theta * (1.0f / RT_PI_F);
+}
 
 // Texture::value for the material's texture (SolidColorTexture.cpp:8-10, CheckerTexture.cpp:43-54,
-// NoiseTexture.cpp:29-30).  None of the reference's textures reads (u, v).
-RT_HD f3 material_texture(const DScene &sc, const float4 *m, float4 m0, f3 p) {
+// NoiseTexture.cpp:29-30).  None of the reference's textures reads (u, v); the image texture (not in the
+// reference, "The Next Week" image_texture::value) does.
+RT_HD f3 material_texture(const DScene &sc, const float4 *m, float4 m0, f3 p, float u, float v) {
   int tex = f2i(m0.y);
   if (tex == RT_DTEX_SOLID)
     return F3(ldg4(m + 1));
@@ -570,6 +581,18 @@ RT_HD f3 material_texture(const DScene &sc, const float4 *m, float4 m0, f3 p) {
     int xi = (int)floorf(inv_scale * p.x), yi = (int)floorf(inv_scale * p.y), zi = (int)floorf(inv_scale * p.z);
     bool even = ((xi + yi + zi) % 2) == 0;
     return F3(ldg4(m + (even ? 1 : 2)));
+  }
+  if (tex == RT_DTEX_IMAGE) {
+    int width = f2i(m0.z), height = f2i(m0.w);
+    if (width <= 0 || height <= 0)
+      return F3(0.f, 1.f, 1.f);
+    float uc = fminf(fmaxf(u, 0.f), 1.f), vc = 1.0f - fminf(fmaxf(v, 0.f), 1.f);
+    int i = (int)(uc * (float)width), j = (int)(vc * (float)height);
+    i = i > width - 1 ? width - 1 : i;
+    j = j > height - 1 ? height - 1 : j;
+    uint32_t texel = sc.texels[(size_t)f2i(ldg4(m + 1).x) + (size_t)j * (size_t)width + (size_t)i]; // 0x00BBGGRR
+    const float s = 1.0f / 255.0f;
+    return F3(s * (float)(texel & 255u), s * (float)((texel >> 8) & 255u), s * (float)((texel >> 16) & 255u));
   }
   float f = 1.f + sinf(m0.z * p.z + 10.f * perlin_turb(sc, f2i(m0.w), p, 7));
   return F3(0.5f * f, 0.5f * f, 0.5f * f);
@@ -700,6 +723,8 @@ RT_HD bool shade_segment(const DScene &sc, const Ray &ray, Hit hit, f3 throughpu
   f3 p = ray.o + hit.t * ray.d;
   f3 normal;
   bool front;
+  float tex_u = 0.f, tex_v = 0.f; // surface coordinates, only computed for image textures
+  const bool wants_uv = f2i(m0.y) == RT_DTEX_IMAGE;
   if (type == RT_PT_SPHERE) {
     float4 r1 = ldg4(rec + 1);
     f3 center = F3(r0) + ray.time * F3(r1);
@@ -708,11 +733,19 @@ RT_HD bool shade_segment(const DScene &sc, const Ray &ray, Hit hit, f3 throughpu
     p = center + r0.w * outward; // keep the point on the surface (FP32 drift on large spheres)
     front = dot(ray.d, outward) < 0.f;
     normal = front ? outward : -outward;
+    if (wants_uv)
+      sphere_uv(outward, tex_u, tex_v);
   } else if (type == RT_PT_QUAD) {
     f3 outward = F3(r0);
     front = dot(ray.d, outward) < 0.f;
     normal = front ? outward : -outward;
     out.next_skip_prim = hit.prim; // a ray leaving a flat primitive cannot hit it again
+    if (wants_uv) {
+      float4 r1 = ldg4(rec + 1), r2 = ldg4(rec + 2);
+      f3 hp = p - F3(r1.w, r2.w, r3.x);
+      tex_u = dot(F3(r1), hp);
+      tex_v = dot(F3(r2), hp);
+    }
   } else {
     normal = F3(1.f, 0.f, 0.f); // ConstantMedium.cpp:86-88
     front = true;
@@ -720,7 +753,7 @@ RT_HD bool shade_segment(const DScene &sc, const Ray &ray, Hit hit, f3 throughpu
 
   if (mtype == 3) { // diffuse light: emits on the front face, never scatters (DiffuseLightMaterial.cpp:12-19)
     if (front)
-      out.radiance = throughput * material_texture(sc, m, m0, p);
+      out.radiance = throughput * material_texture(sc, m, m0, p, tex_u, tex_v);
     return false;
   }
   if (last_bounce) // the scattered ray would be traced with depth 0 and contribute nothing
@@ -760,7 +793,7 @@ RT_HD bool shade_segment(const DScene &sc, const Ray &ray, Hit hit, f3 throughpu
 
   // lambertian (LambertianMaterial.cpp:15-59) / isotropic (IsotropicMaterial.cpp:12-31)
   bool lambert = mtype == 0;
-  f3 attenuation = material_texture(sc, m, m0, p);
+  f3 attenuation = material_texture(sc, m, m0, p, tex_u, tex_v);
   Onb uvw;
   if (lambert)
     uvw = onb_make(normal);

@@ -124,6 +124,7 @@ inline float ibits(int i) {
 struct Flat {
   std::vector<float4> prims, bprims, mats, lights, perlin_grad;
   std::vector<unsigned char> perlin_perm;
+  std::vector<uint32_t> texels; // image textures, 0x00BBGGRR per texel
   std::vector<PrimExact> ex_prims, ex_bprims;
   std::vector<XformOpExact> ops;
   std::vector<int> chain_first, chain_count;
@@ -298,6 +299,22 @@ inline int flatten(const rt_scene_desc *d, Flat &f) {
     f.boxes.push_back(box);
   }
 
+  // image textures: every image repacked to one 32-bit word per texel, all images back to back
+  std::vector<size_t> image_offset;
+  if (d->n_images < 0)
+    return fail_invalid("negative image count");
+  for (int i = 0; i < d->n_images; i++) {
+    const rt_image &im = d->images[i];
+    if (im.width < 0 || im.height < 0 || ((int64_t)im.width * im.height > 0 && !im.rgb) ||
+        (int64_t)im.width * im.height > ((int64_t)1 << 28))
+      return fail_invalid("image texture size / data");
+    image_offset.push_back(f.texels.size());
+    for (int64_t k = 0; k < (int64_t)im.width * im.height; k++)
+      f.texels.push_back((uint32_t)im.rgb[3 * k] | ((uint32_t)im.rgb[3 * k + 1] << 8) | ((uint32_t)im.rgb[3 * k + 2] << 16));
+  }
+  if (f.texels.size() > ((size_t)1 << 31))
+    return fail_invalid("image textures exceed 2^31 texels");
+
   // materials with their texture folded in
   for (int i = 0; i < d->n_materials; i++) {
     const rt_material &m = d->materials[i];
@@ -331,6 +348,13 @@ inline int flatten(const rt_scene_desc *d, Flat &f) {
         m0.y = ibits(RT_DTEX_NOISE);
         m0.z = (float)t.scale;
         m0.w = ibits(t.perlin);
+      } else if (t.type == RT_TEX_IMAGE) {
+        if (t.perlin < 0 || t.perlin >= d->n_images)
+          return fail_invalid("image texture index");
+        m0.y = ibits(RT_DTEX_IMAGE);
+        m0.z = ibits(d->images[t.perlin].width);
+        m0.w = ibits(d->images[t.perlin].height);
+        a = make_float4(ibits((int)image_offset[t.perlin]), 0.f, 0.f, 0.f);
       } else {
         return fail_invalid("unknown texture type");
       }

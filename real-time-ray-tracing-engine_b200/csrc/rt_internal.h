@@ -68,6 +68,7 @@ struct rt_scene {
   float4 *nodes = nullptr, *prims = nullptr, *bprims = nullptr, *mats = nullptr, *lights = nullptr,
          *perlin_grad = nullptr;
   unsigned char *perlin_perm = nullptr;
+  uint32_t *texels = nullptr;
   PrimExact *ex_prims = nullptr, *ex_bprims = nullptr;
   XformOpExact *ex_ops = nullptr;
   int *ex_chain_first = nullptr, *ex_chain_count = nullptr;

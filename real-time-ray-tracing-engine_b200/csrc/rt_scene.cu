@@ -56,6 +56,7 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
   // everything that does not depend on leaf order
   if ((st = upload(&sc->bprims, f.bprims)) || (st = upload(&sc->mats, f.mats)) || (st = upload(&sc->lights, f.lights)) ||
       (st = upload(&sc->perlin_grad, f.perlin_grad)) || (st = upload(&sc->perlin_perm, f.perlin_perm)) ||
+      (st = upload(&sc->texels, f.texels)) ||
       (st = upload(&sc->ex_bprims, f.ex_bprims)) || (st = upload(&sc->ex_ops, f.ops)) ||
       (st = upload(&sc->ex_chain_first, f.chain_first)) || (st = upload(&sc->ex_chain_count, f.chain_count)))
     return st;
@@ -195,6 +196,7 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
   sc->d.lights = sc->lights;
   sc->d.perlin_grad = sc->perlin_grad;
   sc->d.perlin_perm = sc->perlin_perm;
+  sc->d.texels = sc->texels;
   sc->d.n_prims = n;
   sc->d.n_lights = desc->n_lights;
   sc->d.n_media = desc->n_media;
@@ -225,6 +227,7 @@ void rt_scene_release(rt_scene *sc) {
   cudaFree(sc->lights);
   cudaFree(sc->perlin_grad);
   cudaFree(sc->perlin_perm);
+  cudaFree(sc->texels);
   cudaFree(sc->ex_prims);
   cudaFree(sc->ex_bprims);
   cudaFree(sc->ex_ops);

@@ -65,6 +65,25 @@ int SceneBuilder::noise(double scale, int perlin_index) {
   return int(textures.size()) - 1;
 }
 
+int SceneBuilder::image(int width, int height, const std::vector<uint8_t> &rgb) {
+  rt_image im{};
+  im.width = width;
+  im.height = height;
+  images.push_back(im);
+  image_data.push_back(rgb);
+  image_data.back().resize(size_t(width > 0 ? width : 0) * size_t(height > 0 ? height : 0) * 3);
+  return int(images.size()) - 1;
+}
+
+int SceneBuilder::image_texture(int image_index) {
+  rt_texture t{};
+  t.type = RT_TEX_IMAGE;
+  t.even = t.odd = -1;
+  t.perlin = image_index; // rt_texture: the table index field doubles as the image index
+  textures.push_back(t);
+  return int(textures.size()) - 1;
+}
+
 static int push_material(std::vector<rt_material> &v, int type, int tex, Vec albedo, double fuzz, double ior) {
   rt_material m{};
   m.type = type;
@@ -239,6 +258,10 @@ const rt_scene_desc *SceneBuilder::finalize() {
   m_desc.textures = textures.data();
   m_desc.perlins = perlins.data();
   m_desc.lights = lights.data();
+  for (size_t i = 0; i < images.size(); i++)
+    images[i].rgb = image_data[i].data();
+  m_desc.n_images = int(images.size());
+  m_desc.images = images.data();
   return &m_desc;
 }
 

@@ -74,6 +74,9 @@ public:
   int checker(double scale, Vec even, Vec odd);
   int perlin(Rng &rng); // a fresh Perlin table (utils/math/PerlinNoise.hpp:19-26)
   int noise(double scale, int perlin_index);
+  // image textures (not in the reference; include/rt_b200.h rt_image): rgb = width * height * 3 bytes
+  int image(int width, int height, const std::vector<uint8_t> &rgb);
+  int image_texture(int image_index);
   // materials -> index
   int lambertian(Vec albedo) { return lambertian_tex(solid(albedo)); }
   int lambertian_tex(int texture);
@@ -104,6 +107,8 @@ public:
   std::vector<rt_texture> textures;
   std::vector<rt_perlin> perlins;
   std::vector<rt_light> lights;
+  std::vector<rt_image> images;                 // rgb pointers are refreshed by finalize()
+  std::vector<std::vector<uint8_t>> image_data; // owned texel bytes, one vector per image
   int n_objects = 0;
 
   const rt_scene_desc *finalize();

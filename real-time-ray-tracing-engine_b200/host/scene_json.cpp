@@ -7,7 +7,9 @@
 //     "perlins":  [{"type":"PerlinNoise","rand_vec":[[x,y,z] x256],"perm_x":[..],"perm_y":[..],"perm_z":[..]}],
 //     "textures": [{"type":"SolidColorTexture","albedo":{..}},
 //                  {"type":"CheckerTexture","scale":..,"even_texture":<index>,"odd_texture":<index>},
-//                  {"type":"NoiseTexture","scale":..,"perlin":<index>}],
+//                  {"type":"NoiseTexture","scale":..,"perlin":<index>},
+//                  {"type":"ImageTexture","image":<index>}],           (not in the reference: rt_image)
+//     "images":   [{"type":"Image","file":"<name>.ppm"}],              (binary or ASCII PPM beside the JSON)
 //     "materials":[{"type":"LambertianMaterial","texture":<index>}, {"type":"MetalMaterial","albedo":{..},"fuzz":..},
 //                  {"type":"DielectricMaterial","refraction_index":..}, {"type":"DiffuseLightMaterial","texture":<index>},
 //                  {"type":"IsotropicMaterial","texture":<index>}],
@@ -279,7 +281,59 @@ struct Loader {
   }
 };
 
-void load_scene(const Json &root, SceneBuilder &s) {
+// PPM reader for image textures: binary P6 or ASCII P3, maxval 255.
+bool read_ppm(const std::string &path, int &w, int &h, std::vector<uint8_t> &rgb) {
+  std::ifstream in(path, std::ios::binary);
+  if (!in)
+    return false;
+  std::string magic;
+  in >> magic;
+  auto next_int = [&]() {
+    for (;;) {
+      in >> std::ws;
+      if (in.peek() == '#') {
+        std::string comment;
+        std::getline(in, comment);
+      } else {
+        break;
+      }
+    }
+    int v = -1;
+    in >> v;
+    return v;
+  };
+  w = next_int();
+  h = next_int();
+  int maxval = next_int();
+  if ((magic != "P6" && magic != "P3") || w <= 0 || h <= 0 || maxval != 255)
+    return false;
+  rgb.resize(size_t(w) * size_t(h) * 3);
+  if (magic == "P6") {
+    in.get(); // the single whitespace after maxval
+    in.read(reinterpret_cast<char *>(rgb.data()), std::streamsize(rgb.size()));
+    return size_t(in.gcount()) == rgb.size();
+  }
+  for (size_t k = 0; k < rgb.size(); k++) {
+    int v = -1;
+    in >> v;
+    if (v < 0 || v > 255)
+      return false;
+    rgb[k] = uint8_t(v);
+  }
+  return true;
+}
+
+void load_scene(const Json &root, SceneBuilder &s, const std::string &base_dir) {
+  if (const Json *arr = root.find("images"))
+    for (const Json &im : arr->array) {
+      int w = 0, h = 0;
+      std::vector<uint8_t> rgb;
+      std::string file = im.at("file").str();
+      std::string path = (!file.empty() && file[0] == '/') ? file : base_dir + file;
+      if (!read_ppm(path, w, h, rgb))
+        throw std::runtime_error("cannot read image texture " + path + " (binary or ASCII PPM, maxval 255)");
+      s.image(w, h, rgb);
+    }
   const Json &cam = root.at("camera");
   s.camera = rt_camera_config{};
   s.camera.aspect_ratio = cam.at("aspect_ratio").num();
@@ -334,6 +388,9 @@ void load_scene(const Json &root, SceneBuilder &s) {
         r.type = RT_TEX_NOISE;
         r.scale = t.at("scale").num();
         r.perlin = t.at("perlin").integer();
+      } else if (type == "ImageTexture") {
+        r.type = RT_TEX_IMAGE;
+        r.perlin = t.at("image").integer();
       } else {
         throw std::runtime_error("unknown texture type \"" + type + "\"");
       }
@@ -391,9 +448,21 @@ std::string vec_json(const double *p) {
   return "{\"type\":\"Vec3\",\"x\":" + num(p[0]) + ",\"y\":" + num(p[1]) + ",\"z\":" + num(p[2]) + "}";
 }
 
-void save_scene(const SceneBuilder &s, std::ostream &out) {
+void save_scene(const SceneBuilder &s, std::ostream &out, const std::string &json_path) {
+  // image textures are written beside the JSON as binary PPM files and referenced by file name
+  out << "{\n\"images\":[";
+  for (size_t i = 0; i < s.images.size(); i++) {
+    std::string file = json_path + ".image" + std::to_string(i) + ".ppm";
+    std::ofstream img(file, std::ios::binary);
+    img << "P6\n" << s.images[i].width << " " << s.images[i].height << "\n255\n";
+    img.write(reinterpret_cast<const char *>(s.image_data[i].data()), std::streamsize(s.image_data[i].size()));
+    size_t slash = file.find_last_of('/');
+    out << (i ? "," : "") << "{\"type\":\"Image\",\"width\":" << s.images[i].width << ",\"height\":" << s.images[i].height
+        << ",\"file\":\"" << (slash == std::string::npos ? file : file.substr(slash + 1)) << "\"}";
+  }
+  out << "],\n";
   const rt_camera_config &c = s.camera;
-  out << "{\n\"camera\":{\"type\":\"CameraConfig\",\"aspect_ratio\":" << num(c.aspect_ratio) << ",\"vfov\":" << num(c.vfov)
+  out << "\"camera\":{\"type\":\"CameraConfig\",\"aspect_ratio\":" << num(c.aspect_ratio) << ",\"vfov\":" << num(c.vfov)
       << ",\"defocus_angle\":" << num(c.defocus_angle) << ",\"focus_dist\":" << num(c.focus_dist)
       << ",\"lookfrom\":" << vec_json(c.lookfrom) << ",\"lookat\":" << vec_json(c.lookat) << ",\"vup\":" << vec_json(c.vup)
       << ",\"background\":" << vec_json(c.background) << "},\n";
@@ -423,6 +492,8 @@ void save_scene(const SceneBuilder &s, std::ostream &out) {
     else if (t.type == RT_TEX_CHECKER)
       out << "{\"type\":\"CheckerTexture\",\"scale\":" << num(t.scale) << ",\"even_texture\":" << t.even
           << ",\"odd_texture\":" << t.odd << "}";
+    else if (t.type == RT_TEX_IMAGE)
+      out << "{\"type\":\"ImageTexture\",\"image\":" << t.perlin << "}";
     else
       out << "{\"type\":\"NoiseTexture\",\"scale\":" << num(t.scale) << ",\"perlin\":" << t.perlin << "}";
   }
@@ -543,7 +614,9 @@ rth_scene *rth_scene_load_json(const char *path) {
   rth_scene *s = new rth_scene();
   try {
     rth::Json root = rth::Parser(text).parse();
-    rth::load_scene(root, s->builder);
+    std::string p(path);
+    size_t slash = p.find_last_of('/');
+    rth::load_scene(root, s->builder, slash == std::string::npos ? std::string() : p.substr(0, slash + 1));
   } catch (const std::exception &e) {
     rth::set_error(std::string(path) + ": " + e.what());
     delete s;
@@ -559,7 +632,7 @@ int rth_scene_save_json(const rth_scene *scene, const char *path) {
     return 1;
   }
   const_cast<rth_scene *>(scene)->builder.finalize();
-  rth::save_scene(scene->builder, out);
+  rth::save_scene(scene->builder, out, path);
   return out.good() ? 0 : 1;
 }
 

@@ -137,6 +137,53 @@ void final_scene(SceneBuilder &s, Rng &rng, int boxes_per_side, int n_cluster) {
   set_camera(s, 16.0 / 9.0, Vec(0, 0, 0), 40, Vec(478, 278, -600), Vec(278, 278, 0), 0, 10);
 }
 
+// Image-texture scene ("The Next Week" earth()): a globe and a framed picture on a quad, both textured with
+// one procedurally drawn map (the image has no network to fetch earthmap.jpg from): oceans, continents from
+// a few overlapping discs in longitude / latitude, polar caps and a 15-degree graticule.  The reference has
+// no image texture; this scene exists for the north star's image-texture requirement.
+void earth_scene(SceneBuilder &s) {
+  const int W = 512, H = 256;
+  std::vector<uint8_t> rgb(size_t(W) * H * 3);
+  const double blobs[][3] = {{-100, 45, 32}, {-60, -15, 24}, {20, 5, 28}, {25, 50, 22}, {90, 45, 38},
+                             {135, -25, 16}, {-45, 72, 12}, {105, 15, 14}}; // lon, lat, radius (degrees)
+  for (int j = 0; j < H; j++)
+    for (int i = 0; i < W; i++) {
+      double lon = (i + 0.5) / W * 360.0 - 180.0, lat = 90.0 - (j + 0.5) / H * 180.0;
+      bool land = false;
+      for (const auto &b : blobs) {
+        double dl = std::fabs(lon - b[0]);
+        dl = dl > 180 ? 360 - dl : dl;
+        double dx = dl * std::cos(lat * 3.14159265358979323846 / 180.0), dy = lat - b[1];
+        land = land || dx * dx + dy * dy < b[2] * b[2];
+      }
+      uint8_t r = 20, g = 60, bl = 150; // ocean
+      if (land) {
+        r = uint8_t(60 + std::fabs(lat) * 0.8);
+        g = uint8_t(140 - std::fabs(lat) * 0.6);
+        bl = 50;
+      }
+      if (std::fabs(lat) > 75) {
+        r = g = bl = 235;
+      }
+      if (std::fmod(lon + 180.0, 15.0) < 0.5 || std::fmod(lat + 90.0, 15.0) < 0.5) {
+        r = uint8_t(r / 2);
+        g = uint8_t(g / 2);
+        bl = uint8_t(bl / 2);
+      }
+      uint8_t *px = &rgb[(size_t(j) * W + i) * 3];
+      px[0] = r;
+      px[1] = g;
+      px[2] = bl;
+    }
+  int map = s.image_texture(s.image(W, H, rgb));
+  s.sphere(Vec(0, 0, 0), 2, s.lambertian_tex(map));
+  s.quad(Vec(-6, -2.5, -4), Vec(5, 0, 0), Vec(0, 2.5, 0), s.lambertian_tex(map));
+  s.sphere(Vec(0, -1002, 0), 1000, s.lambertian(Vec(0.5, 0.5, 0.5)));
+  s.quad(Vec(3, 1, -3), Vec(2, 0, 0), Vec(0, 0, 2), s.diffuse_light(Vec(4, 4, 4)));
+  s.light_quad(Vec(3, 1, -3), Vec(2, 0, 0), Vec(0, 0, 2));
+  set_camera(s, 16.0 / 9.0, Vec(0.70, 0.80, 1.00), 30, Vec(0, 1, 12), Vec(0, 0, 0), 0, 10);
+}
+
 } // namespace
 
 bool build_builtin(SceneBuilder &s, const std::string &name, uint64_t seed, int p0, int p1) {
@@ -151,6 +198,8 @@ bool build_builtin(SceneBuilder &s, const std::string &name, uint64_t seed, int 
     cornell_smoke_scene(s);
   else if (name == "final")
     final_scene(s, rng, p0 > 0 ? p0 : 20, p1 >= 0 ? p1 : 1000);
+  else if (name == "earth")
+    earth_scene(s);
   else
     return false;
   s.finalize();

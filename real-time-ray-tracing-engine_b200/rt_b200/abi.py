@@ -13,7 +13,7 @@ HOST_LIB_PATH = os.path.join(PKG_DIR, "host", "librt_host.so")
 
 RT_OK, RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_NO_DEVICE, RT_ERR_UNSUPPORTED = range(5)
 RT_MAT_LAMBERTIAN, RT_MAT_METAL, RT_MAT_DIELECTRIC, RT_MAT_DIFFUSE_LIGHT, RT_MAT_ISOTROPIC = range(5)
-RT_TEX_SOLID, RT_TEX_CHECKER, RT_TEX_NOISE = range(3)
+RT_TEX_SOLID, RT_TEX_CHECKER, RT_TEX_NOISE, RT_TEX_IMAGE = range(4)
 RT_XF_TRANSLATE, RT_XF_ROTATE_Y = range(2)
 RT_SHAPE_SPHERE, RT_SHAPE_QUAD = range(2)
 RT_PRIM_BOUNDARY = 1
@@ -67,6 +67,10 @@ class rt_light(C.Structure):
                 ("radius", C.c_double)]
 
 
+class rt_image(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("rgb", C.POINTER(C.c_uint8))]
+
+
 class rt_scene_desc(C.Structure):
     _fields_ = [("n_spheres", C.c_int32), ("n_quads", C.c_int32), ("n_xform_ops", C.c_int32),
                 ("n_xforms", C.c_int32), ("n_media", C.c_int32), ("n_materials", C.c_int32),
@@ -76,7 +80,8 @@ class rt_scene_desc(C.Structure):
                 ("xform_ops", C.POINTER(rt_xform_op)), ("xforms", C.POINTER(rt_xform)),
                 ("media", C.POINTER(rt_medium)), ("materials", C.POINTER(rt_material)),
                 ("textures", C.POINTER(rt_texture)), ("perlins", C.POINTER(rt_perlin)),
-                ("lights", C.POINTER(rt_light))]
+                ("lights", C.POINTER(rt_light)),
+                ("n_images", C.c_int32), ("pad_", C.c_int32), ("images", C.POINTER(rt_image))]
 
 
 class rt_camera_config(C.Structure):

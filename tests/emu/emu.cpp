@@ -135,6 +135,8 @@ EmuScene *emu_scene_create(const rt_scene_desc *desc) {
   s->d.lights = f.lights.empty() ? &zero4 : f.lights.data();
   s->d.perlin_grad = f.perlin_grad.empty() ? &zero4 : f.perlin_grad.data();
   s->d.perlin_perm = f.perlin_perm.empty() ? &zero1 : f.perlin_perm.data();
+  static const uint32_t zero_texel = 0;
+  s->d.texels = f.texels.empty() ? &zero_texel : f.texels.data();
   s->d.n_prims = (int)f.boxes.size();
   s->d.n_lights = desc->n_lights;
   s->d.n_media = desc->n_media;

@@ -370,3 +370,27 @@ def test_scatter_gathered_rgb8_kernel(ctx):
                                                              out.data_ptr()), "rt_film_scatter_gathered_rgb8")
     ctx.synchronize()
     assert torch.equal(out, full)
+
+
+def test_image_texture_scene(ctx, oracle, host_scenes):
+    """Image textures (north-star surface the reference lacks) through the CUDA path: closest hits bit-exact,
+    render follows the oracle's paths (a texel boundary may flip in FP32), static == sum of frames."""
+    hs = host_scenes("earth", 0, -1)
+    cfg = hs.camera_config(128, 4, 6)
+    osc = oracle.ora_scene_create(hs.desc)
+    img, rays, cnt = oracle_segments(oracle, osc, cfg, ol.ORA_RNG_PHILOX, ol.ORA_SAMPLER_POLAR, 9, 1)
+    want = (abi.rt_hit * len(rays))()
+    oracle.ora_trace(osc, rays, len(rays), 1, ol.ORA_RNG_PHILOX, 9, want)
+    scene = engine.Scene(ctx, hs.desc)
+    a, b = ol.hits_to_numpy(want), ol.hits_to_numpy(scene.trace(rays, abi.RT_TRACE_EXACT_F64, 9))
+    assert np.array_equal(a["prim"], b["prim"]) and np.array_equal(a["t"], b["t"])
+    cam = engine.camera_from_config(cfg)
+    film = engine.Film(ctx, cam.image_width, cam.image_height)
+    engine.render_static(scene, cam, film, 2, 6, 9)
+    got = film.read_rgb(0.25).astype(np.float64)
+    follows = np.abs(got - img).max(axis=1) < 4e-3
+    assert follows.mean() > 0.95, follows.mean()
+    assert abs(got.mean() - img.mean()) < 0.01 * img.mean()
+    film.close()
+    scene.close()
+    oracle.ora_scene_destroy(osc)

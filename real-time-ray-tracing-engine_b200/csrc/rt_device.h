@@ -387,7 +387,8 @@ RT_HD void leaf_test(const DScene &sc, int prim, const Ray &ray, float tmin, Hit
 // The stack holds (child ref, entry distance); `stack` is caller-provided storage of RT_STACK entries
 // (shared-memory short stack in the kernels, spilling to local memory beyond RT_STACK_SMEM).
 // ---------------------------------------------------------------------------------------------------
-#define RT_STACK 48
+#define RT_STACK 64 // > 3 pushes per level of a 63-bit Morton tree collapsed to 4-wide nodes; only the first
+                    // RT_STACK_SMEM entries are ever touched on typical scenes
 
 struct StackEntry {
   int ref;

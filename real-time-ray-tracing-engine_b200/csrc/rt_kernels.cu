@@ -5,9 +5,11 @@
 //   k_generate    camera rays for all paths of the pass             -> ray queue 0
 //   k_extend      BVH4 traversal + sphere / quad / medium tests     -> hit per queue slot
 //   k_shade       emit / scatter / light sampling, Philox draws     -> compacted ray queue of the next bounce
+//   k_tail        after the first bounces: the thin rest of the path population, traced and shaded to
+//                 completion in one persistent launch
 //   k_accumulate  per-pixel sum of the pass's samples, in order     -> film
 // Queue lengths stay on the device (counts[bounce]); every kernel is a persistent grid sized in
-// multiples of the SM count that strides over the queue, so the host never synchronises between
+// multiples of the SM count that pulls work from the queue, so the host never synchronises between
 // bounces.  Compaction uses one ballot + one atomic per warp.
 #include "rt_internal.h"
 
@@ -72,7 +74,6 @@ __device__ __forceinline__ void path_to_key(const PassParams &pp, int path, int 
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(RT_BLOCK)
     k_generate(const __grid_constant__ PassParams pp, float4 *__restrict__ ray_a, float4 *__restrict__ ray_b,
-               float2 *__restrict__ hit, float4 *__restrict__ throughput, float4 *__restrict__ radiance,
                unsigned int *__restrict__ counts) {
   int stride = gridDim.x * blockDim.x;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < pp.n_paths; p += stride) {
@@ -715,8 +716,7 @@ void launch_collapse(cudaStream_t s, BinTree t, const BuildBox *leaf_boxes, floa
 void launch_generate(const rt_context *ctx, const PassParams &pp, WaveBuffers &w) {
   LaunchShape sh = rt_persistent_shape(ctx, RT_BLOCK, 16);
   int need = ceil_div(pp.n_paths, RT_BLOCK);
-  k_generate<<<need < sh.blocks ? need : sh.blocks, RT_BLOCK, 0, ctx->stream>>>(pp, w.ray_a[0], w.ray_b[0], w.hit[0],
-                                                                                 w.throughput, w.radiance, w.counts);
+  k_generate<<<need < sh.blocks ? need : sh.blocks, RT_BLOCK, 0, ctx->stream>>>(pp, w.ray_a[0], w.ray_b[0], w.counts);
 }
 
 void launch_extend(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int bounce) {

@@ -63,6 +63,10 @@ typedef struct rth_cli_options {
   uint64_t seed;      /* --seed, default 1234 */
   int gpus;           /* --gpus, default 1 */
   int frames;         /* --frames: dynamic mode without a window renders this many frames, default 0 = sqrt_spp^2 */
+  char keys[256];     /* --keys: scripted key states for the headless dynamic camera, one character per frame:
+                         w/s/a/d move lookfrom and lookat by 10 units along +z/-z/-x/+x and restart the
+                         accumulation, '+'/'-' change samples per pixel (DynamicCamera::handle_events,
+                         core/camera/DynamicCamera.cpp:204-278), any other character = no key */
 } rth_cli_options;
 
 /* Returns 0 on success, non-zero on a malformed command line (message in rth_last_error). */

@@ -33,7 +33,10 @@ const char *rth_cli_help(void) {
          "  --seed <int>               Seed of the scene generator and of the render (default: 1234)\n"
          "  --gpus <int>               GPUs to partition the image over (default: 1)\n"
          "  --frames <int>             Dynamic camera without a window: progressive frames to render\n"
-         "                             (default: one per stratum)\n\n"
+         "                             (default: one per stratum)\n"
+         "  --keys <string>            Dynamic camera without a window: scripted key states, one character per\n"
+         "                             frame (w/s/a/d move the camera by 10 units and restart the accumulation,\n"
+         "                             +/- change the samples per pixel, anything else: no key)\n\n"
          "Examples:\n"
          "  raytracer --camera static --output render.ppm --scene spheres --width 400\n"
          "  raytracer --camera dynamic --scene spheres --width 1920 --samples 16 --depth 8\n";
@@ -111,6 +114,8 @@ int rth_cli_parse(int argc, char **argv, rth_cli_options *out) {
       need_int(i, "--gpus", out->gpus);
     } else if (arg == "--frames") {
       need_int(i, "--frames", out->frames);
+    } else if (arg == "--keys") {
+      need_str(i, "--keys", out->keys, sizeof out->keys);
     } else {
       errors += "Unknown option: " + arg + "\n";
     }

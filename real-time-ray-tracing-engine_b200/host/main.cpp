@@ -60,7 +60,7 @@ int main(int argc, char **argv) {
   rt_camera cam;
   CHECK(rt_camera_init(&cfg, &cam));
   const int W = cam.image_width, H = cam.image_height;
-  const int sqrt_spp = int(std::sqrt(double(opt.samples))); // Camera.cpp:209
+  int sqrt_spp = int(std::sqrt(double(opt.samples))); // Camera.cpp:209
   const int n_gpus = opt.gpus;
   if (rt_device_count() < n_gpus) {
     std::fprintf(stderr, "[ERROR] %d CUDA device(s) requested, %d available; there is no CPU fallback\n", n_gpus,
@@ -117,9 +117,27 @@ int main(int argc, char **argv) {
     std::fprintf(stderr, "[INFO] wrote %s\n", path.c_str());
   } else {
     int frames = opt.frames > 0 ? opt.frames : sqrt_spp * sqrt_spp;
-    int taken = 0;
+    int taken = 0, samples = opt.samples, moves = 0;
+    const size_t n_keys = std::strlen(opt.keys);
     for (int f = 0; f < frames; f++) {
       double f0 = now_ms();
+      // scripted key state of this frame: DynamicCamera::handle_events (DynamicCamera.cpp:204-278)
+      char key = size_t(f) < n_keys ? opt.keys[f] : '.';
+      double dx = key == 'd' ? 10.0 : (key == 'a' ? -10.0 : 0.0), dz = key == 'w' ? 10.0 : (key == 's' ? -10.0 : 0.0);
+      if (key == '+')
+        samples++;
+      if (key == '-' && samples > 1)
+        samples--;
+      sqrt_spp = std::max(1, int(std::sqrt(double(samples))));
+      if (dx != 0.0 || dz != 0.0) { // camera moved: restart the accumulation and recompute the camera
+        cfg.lookfrom[0] += dx, cfg.lookat[0] += dx;
+        cfg.lookfrom[2] += dz, cfg.lookat[2] += dz;
+        CHECK(rt_camera_init(&cfg, &cam));
+        for (int g = 0; g < n_gpus; g++)
+          CHECK(rt_film_clear(film[g]));
+        taken = 0;
+        moves++;
+      }
       int s = taken % (sqrt_spp * sqrt_spp);
       for (int g = 0; g < n_gpus; g++)
         CHECK(rt_render_accumulate(scene[g], &cam, film[g], s % sqrt_spp, s / sqrt_spp, sqrt_spp, opt.depth,
@@ -139,8 +157,8 @@ int main(int argc, char **argv) {
     mkdir("output", 0755);
     std::string path = std::string("output/") + opt.output;
     rth_write_ppm_p3(path.c_str(), W, H, rgb8.data());
-    std::fprintf(stderr, "[INFO] %d progressive frames in %.1f ms; last frame written to %s\n", frames, now_ms() - t0,
-                 path.c_str());
+    std::fprintf(stderr, "[INFO] %d progressive frames in %.1f ms (%d camera move(s), %d sample(s) in the last "
+                         "accumulation); last frame written to %s\n", frames, now_ms() - t0, moves, taken, path.c_str());
   }
   for (int g = 0; g < n_gpus; g++) {
     rt_film_destroy(film[g]);

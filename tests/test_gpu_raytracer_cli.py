@@ -71,3 +71,28 @@ def test_cli_errors(tmp_path):
     too_many = lib.rt_device_count() + 1
     r = run(["--scene", "cornell", "--width", "32", "--samples", "1", "--gpus", str(too_many)], tmp_path)
     assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+def test_scripted_camera_move_restarts_the_accumulation(tmp_path):
+    """DynamicCamera::handle_events (DynamicCamera.cpp:204-278): a movement key shifts lookfrom / lookat by 10
+    units, clears the accumulation and re-initialises the camera.  Frames 0-2 accumulate, frame 3 has 'd' down
+    (+10 in x), so the last image is the average of frames 3-5 seen from the moved camera."""
+    r = run(["--camera", "dynamic", "--scene", "cornell", "--width", "64", "--samples", "9", "--depth", "5", "--frames", "6",
+             "--keys", "...d", "--output", "moved.ppm"], tmp_path)
+    assert r.returncode == 0, r.stderr
+    assert "1 camera move(s), 3 sample(s)" in r.stderr
+    ctx = engine.Context(0)
+    hs = host.HostScene.builtin("cornell", 1234)
+    cfg = hs.camera_config(64, 9, 5)
+    cfg.lookfrom[0] += 10.0
+    cfg.lookat[0] += 10.0
+    cam = engine.camera_from_config(cfg)
+    scene = engine.Scene(ctx, hs.desc)
+    film = engine.Film(ctx, cam.image_width, cam.image_height)
+    for s in range(3):
+        engine.render_accumulate(scene, cam, film, s % 3, s // 3, 3, 5, 1234)
+    want = film.resolve_rgb8(1.0 / 3).reshape(cam.image_height, cam.image_width, 3)
+    assert np.array_equal(read_ppm(tmp_path / "output" / "moved.ppm"), want)
+    film.close()
+    scene.close()
+    ctx.close()

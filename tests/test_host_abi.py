@@ -123,7 +123,7 @@ class rth_cli_options(C.Structure):
     _fields_ = [("width", C.c_int), ("samples", C.c_int), ("depth", C.c_int), ("camera_dynamic", C.c_int),
                 ("use_parallelism", C.c_int), ("use_bvh", C.c_int), ("use_gpu", C.c_int), ("debug", C.c_int),
                 ("help", C.c_int), ("output", C.c_char * 256), ("scene", C.c_char * 256), ("seed", C.c_uint64),
-                ("gpus", C.c_int), ("frames", C.c_int)]
+                ("gpus", C.c_int), ("frames", C.c_int), ("keys", C.c_char * 256)]
 
 
 def parse_cli(args):
@@ -141,10 +141,10 @@ def test_cli_defaults_and_flags_match_the_reference():
     assert rc == 0 and (o.width, o.samples, o.depth) == (600, 100, 50)
     assert o.camera_dynamic == 0 and o.output == b"image.ppm" and not (o.use_parallelism or o.use_bvh or o.use_gpu or o.debug)
     rc, o = parse_cli(["--camera", "dynamic", "-p", "-b", "-g", "-d", "--width", "1920", "--samples", "16", "--depth", "8",
-                       "--output", "x.ppm", "--scene", "spheres", "--seed", "7", "--gpus", "2"])
+                       "--output", "x.ppm", "--scene", "spheres", "--seed", "7", "--gpus", "2", "--keys", "..w.a"])
     assert rc == 0 and o.camera_dynamic == 1 and (o.width, o.samples, o.depth) == (1920, 16, 8)
     assert o.use_parallelism and o.use_bvh and o.use_gpu and o.debug and o.output == b"x.ppm"
-    assert o.scene == b"spheres" and o.seed == 7 and o.gpus == 2
+    assert o.scene == b"spheres" and o.seed == 7 and o.gpus == 2 and o.keys == b"..w.a"
     # the reference's error cases (CLI.cpp:13-92)
     for bad in (["--camera", "orbit"], ["--camera"], ["--width"], ["--width", "abc"], ["--bogus"], ["--samples", "0"]):
         rc, _ = parse_cli(bad)

@@ -357,6 +357,10 @@ int rt_film_scatter_gathered_rgb8(rt_context *ctx, int width, int height, int n_
  * NVLink peer copies.  films[r] must be rank r of n_ranks.  host_rgb (width*height*3 floats) gets
  * scale * sum. */
 int rt_film_gather_p2p(rt_film **films, int n_ranks, double scale, float *host_rgb);
+/* The same for a displayed frame: every film's tiles are tone-mapped on their own device (to_byte), the RGB8
+ * tiles travel over NVLink, host_rgb8 (width*height*3 bytes) gets the frame - byte-identical to
+ * rt_film_resolve_rgb8 on one GPU. */
+int rt_film_gather_p2p_rgb8(rt_film **films, int n_ranks, double scale, uint8_t *host_rgb8);
 
 /* ----------------------------------------------------------------------------------------------
  * Counters (tracing / profiling aid)

@@ -587,11 +587,14 @@ int rt_film_scatter_gathered_rgb8(rt_context *ctx, int width, int height, int n_
   return scatter_gathered(ctx, width, height, n_ranks, tile_rows, device_gathered, device_full_image, 3);
 }
 
-// Single-process multi-GPU gather: every rank's compact film is copied over NVLink (peer copy) into
-// one rank-major buffer on rank 0's device and scattered into the full image there.
-int rt_film_gather_p2p(rt_film **films, int n_ranks, double scale, float *host_rgb) {
-  if (!films || n_ranks < 1 || !host_rgb)
-    return invalid("rt_film_gather_p2p: bad argument");
+// Single-process multi-GPU gather: every rank's tiles are copied over NVLink (peer copies) into one rank-major
+// buffer on rank 0's device and scattered into the full image there.  as_rgb8: every rank tone-maps its own
+// tiles first (to_byte, FP64 - the bytes are identical to a single-GPU resolve) and 3 bytes per pixel travel;
+// otherwise the float4 sums travel and rank 0 scales them.
+static int gather_p2p(rt_film **films, int n_ranks, double scale, float *host_rgb, uint8_t *host_rgb8) {
+  const bool as_rgb8 = host_rgb8 != nullptr;
+  if (!films || n_ranks < 1 || n_ranks > 64 || (!host_rgb && !host_rgb8))
+    return invalid("rt_film_gather_p2p: bad argument (1..64 ranks)");
   for (int r = 0; r < n_ranks; r++) {
     if (!films[r] || films[r]->map.rank != r || films[r]->map.n_ranks != n_ranks ||
         films[r]->map.width != films[0]->map.width || films[r]->map.height != films[0]->map.height ||
@@ -601,41 +604,90 @@ int rt_film_gather_p2p(rt_film **films, int n_ranks, double scale, float *host_r
   rt_context *ctx0 = films[0]->ctx;
   const int W = films[0]->map.width, H = films[0]->map.height;
   const int64_t total = (int64_t)W * H;
-  for (int r = 0; r < n_ranks; r++) {
-    RT_CUDA(cudaSetDevice(films[r]->ctx->device));
-    RT_CUDA(cudaStreamSynchronize(films[r]->ctx->stream));
-  }
-  RT_CUDA(cudaSetDevice(ctx0->device));
-  float4 *gathered = nullptr, *full = nullptr;
-  RT_CUDA(cudaMalloc((void **)&gathered, (size_t)total * sizeof(float4)));
-  cudaError_t e = cudaMalloc((void **)&full, (size_t)total * sizeof(float4));
-  if (e != cudaSuccess) {
+  const size_t px = as_rgb8 ? 3 : sizeof(float4);
+  std::vector<void *> staged(n_ranks, nullptr); // per-rank RGB8 tiles (as_rgb8 only)
+  unsigned char *gathered = nullptr, *full = nullptr;
+  int st = RT_OK;
+  cudaError_t e = cudaSuccess;
+  auto cleanup = [&]() {
+    for (int r = 0; r < n_ranks; r++)
+      if (staged[r]) {
+        cudaSetDevice(films[r]->ctx->device);
+        cudaFree(staged[r]);
+      }
+    cudaSetDevice(ctx0->device);
     cudaFree(gathered);
+    cudaFree(full);
+  };
+  for (int r = 0; r < n_ranks && st == RT_OK; r++) {
+    RT_CUDA(cudaSetDevice(films[r]->ctx->device));
+    if (as_rgb8 && films[r]->n_owned > 0) {
+      e = cudaMalloc(&staged[r], (size_t)films[r]->n_owned * 3);
+      if (e != cudaSuccess)
+        st = rt_cuda_fail(e, "cudaMalloc (rgb8 tiles)");
+      else
+        st = rt_film_resolve_rgb8_device(films[r], scale, staged[r]);
+    }
+    if (st == RT_OK && (e = cudaStreamSynchronize(films[r]->ctx->stream)) != cudaSuccess)
+      st = rt_cuda_fail(e, "cudaStreamSynchronize");
+    if (r > 0) { // direct NVLink copies into rank 0 (an error here only means it was enabled before)
+      cudaSetDevice(ctx0->device);
+      if (cudaDeviceEnablePeerAccess(films[r]->ctx->device, 0) != cudaSuccess)
+        cudaGetLastError();
+    }
+  }
+  if (st != RT_OK) {
+    cleanup();
+    return st;
+  }
+  cudaSetDevice(ctx0->device);
+  if ((e = cudaMalloc((void **)&gathered, (size_t)total * px)) != cudaSuccess ||
+      (e = cudaMalloc((void **)&full, (size_t)total * px)) != cudaSuccess) {
+    cleanup();
     return rt_cuda_fail(e, "cudaMalloc (gather)");
   }
   int64_t offset = 0;
   for (int r = 0; r < n_ranks && e == cudaSuccess; r++) {
-    size_t bytes = (size_t)films[r]->n_owned * sizeof(float4);
+    size_t bytes = (size_t)films[r]->n_owned * px;
+    const void *src = as_rgb8 ? staged[r] : (const void *)films[r]->accum;
     if (bytes)
-      e = cudaMemcpyPeerAsync(gathered + offset, ctx0->device, films[r]->accum, films[r]->ctx->device, bytes,
-                              ctx0->stream);
+      e = cudaMemcpyPeerAsync(gathered + (size_t)offset * px, ctx0->device, src, films[r]->ctx->device, bytes, ctx0->stream);
     offset += films[r]->n_owned;
   }
-  int st = RT_OK;
-  if (e == cudaSuccess) {
-    launch_scatter_gathered(ctx0->stream, W, H, n_ranks, films[0]->map.tile_rows, gathered, full, 16);
-    rt_film tmp;
-    tmp.ctx = ctx0;
-    tmp.accum = full;
-    tmp.n_owned = total;
-    st = rt_film_read_rgb(&tmp, scale, host_rgb);
-  } else {
+  if (e != cudaSuccess) {
     st = rt_cuda_fail(e, "cudaMemcpyPeerAsync");
+  } else {
+    launch_scatter_gathered(ctx0->stream, W, H, n_ranks, films[0]->map.tile_rows, gathered, full, (int)px);
+    ctx0->counters.kernel_launches += 1;
+    if (as_rgb8) {
+      e = cudaMemcpyAsync(host_rgb8, full, (size_t)total * 3, cudaMemcpyDeviceToHost, ctx0->stream);
+      if (e == cudaSuccess)
+        e = cudaStreamSynchronize(ctx0->stream);
+      if (e != cudaSuccess)
+        st = rt_cuda_fail(e, "rt_film_gather_p2p_rgb8");
+    } else {
+      rt_film whole;
+      whole.ctx = ctx0;
+      whole.accum = (float4 *)full;
+      whole.n_owned = total;
+      st = rt_film_read_rgb(&whole, scale, host_rgb);
+    }
   }
   cudaStreamSynchronize(ctx0->stream);
-  cudaFree(gathered);
-  cudaFree(full);
+  cleanup();
   return st;
+}
+
+int rt_film_gather_p2p(rt_film **films, int n_ranks, double scale, float *host_rgb) {
+  if (!host_rgb)
+    return invalid("rt_film_gather_p2p: null output");
+  return gather_p2p(films, n_ranks, scale, host_rgb, nullptr);
+}
+
+int rt_film_gather_p2p_rgb8(rt_film **films, int n_ranks, double scale, uint8_t *host_rgb8) {
+  if (!host_rgb8)
+    return invalid("rt_film_gather_p2p_rgb8: null output");
+  return gather_p2p(films, n_ranks, scale, nullptr, host_rgb8);
 }
 
 int rt_get_counters(rt_context *ctx, rt_counters *out) {

@@ -83,16 +83,7 @@ int main(int argc, char **argv) {
                opt.scene, (long long)info.n_prims, (long long)info.n_nodes, info.build_ms, W, H, sqrt_spp * sqrt_spp,
                opt.depth, n_gpus);
 
-  std::vector<float> rgb((size_t)W * H * 3);
   std::vector<uint8_t> rgb8((size_t)W * H * 3);
-  auto to_bytes = [&](void) {
-    for (size_t k = 0; k < rgb.size(); k++) { // to_byte (utils/ColorUtility.hpp:18-26)
-      double v = rgb[k];
-      double x = v > 0 ? std::sqrt(v) : 0;
-      x = x < 0.0 ? 0.0 : (x > 0.999 ? 0.999 : x);
-      rgb8[k] = (uint8_t)(256 * x);
-    }
-  };
 
   double t0 = now_ms();
   if (!opt.camera_dynamic) {
@@ -101,8 +92,7 @@ int main(int argc, char **argv) {
     if (n_gpus == 1) {
       CHECK(rt_film_resolve_rgb8(film[0], 1.0 / opt.samples, rgb8.data())); // pixel_samples_scale = 1/spp
     } else {
-      CHECK(rt_film_gather_p2p(film.data(), n_gpus, 1.0 / opt.samples, rgb.data()));
-      to_bytes();
+      CHECK(rt_film_gather_p2p_rgb8(film.data(), n_gpus, 1.0 / opt.samples, rgb8.data()));
     }
     double t1 = now_ms();
     long long paths = (long long)W * H * sqrt_spp * sqrt_spp;
@@ -147,8 +137,7 @@ int main(int argc, char **argv) {
       if (n_gpus == 1) {
         CHECK(rt_film_resolve_rgb8(film[0], scale, rgb8.data()));
       } else {
-        CHECK(rt_film_gather_p2p(film.data(), n_gpus, scale, rgb.data()));
-        to_bytes();
+        CHECK(rt_film_gather_p2p_rgb8(film.data(), n_gpus, scale, rgb8.data()));
       }
       double f1 = now_ms();
       if (f < 5 || f == frames - 1)

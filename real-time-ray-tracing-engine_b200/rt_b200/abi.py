@@ -154,6 +154,7 @@ RT_B200_SYMBOLS = {
     "rt_film_scatter_gathered_rgb8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                                 C.c_void_p]),
     "rt_film_gather_p2p": (C.c_int, [P(C.c_void_p), C.c_int, C.c_double, P(C.c_float)]),
+    "rt_film_gather_p2p_rgb8": (C.c_int, [P(C.c_void_p), C.c_int, C.c_double, P(C.c_uint8)]),
     "rt_get_counters": (C.c_int, [C.c_void_p, P(rt_counters)]),
     "rt_reset_counters": (C.c_int, [C.c_void_p]),
     "rt_context_set_stage_timing": (C.c_int, [C.c_void_p, C.c_int]),

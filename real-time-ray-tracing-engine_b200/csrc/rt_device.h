@@ -145,9 +145,12 @@ RT_HD Uniform4 philox_uniform4(uint64_t seed, uint32_t pixel, uint32_t sample, u
 // ---------------------------------------------------------------------------------------------------
 // BVH4 node: 8 x float4 = 128 B (one L1/L2 line), SoA over the four children.
 //   [0] lo.x  [1] hi.x  [2] lo.y  [3] hi.y  [4] lo.z  [5] hi.z  [6] child refs (int bits)  [7] spare
-// child ref >= 0: node index;  < 0 and != RT_EMPTY: leaf, primitive index = ~ref;  RT_EMPTY: unused slot.
+// child ref >= 0: node index;  < 0: leaf, primitive index = ~ref;  RT_EMPTY: unused slot (box inverted).
+// RT_EMPTY is the bit pattern of +inf: read as a float, a child ref is a tiny positive denormal (node), a
+// NaN or negative number (leaf) or +inf (empty), so max(entry distance, ref-as-float) leaves valid
+// children alone and makes an empty slot unreachable for any ray, NaN rays included, at no extra cost.
 #define RT_NODE_F4 8
-#define RT_EMPTY ((int)0x80000000)
+#define RT_EMPTY ((int)0x7f800000)
 
 // Primitive record: 4 x float4 = 64 B, in BVH leaf (Morton) order, world space (instances baked).
 //   sphere: [0] c0.xyz, radius       [1] center_dir.xyz, -          [2] -                [3] -, typemat, id, object
@@ -426,8 +429,8 @@ RT_HD float fma_sub(float a, float b, float c) { // a * b - c in one rounding
 #endif
 }
 
-// Visits inner node `node`: tests its four child boxes, pushes the hit children far-to-near and
-// returns the nearest one in `next` (false when no child is hit).
+// Visits inner node `node`: tests its four child boxes, returns the nearest hit child in `next` (false
+// when no child is hit) and pushes the other hit children.
 template <class Stack>
 RT_HD bool node_visit(const DScene &sc, int node, const RayTrav &rt, float tmin, float tmax, Stack &stack, int &sp,
                       int &next) {
@@ -444,14 +447,14 @@ RT_HD bool node_visit(const DScene &sc, int node, const RayTrav &rt, float tmin,
 #pragma unroll
   for (int c = 0; c < 4; c++) {
     float tnear = fmaxf(fmaxf(fma_sub(nx[c], rt.inv.x, rt.oi.x), fma_sub(ny[c], rt.inv.y, rt.oi.y)),
-                        fmaxf(fma_sub(nz[c], rt.inv.z, rt.oi.z), tmin));
+                        fmaxf(fma_sub(nz[c], rt.inv.z, rt.oi.z), fmaxf(tmin, i2f(cref[c]))));
     float tfar = fminf(fminf(fma_sub(fx[c], rt.inv.x, rt.oi.x), fma_sub(fy[c], rt.inv.y, rt.oi.y)),
                        fma_sub(fz[c], rt.inv.z, rt.oi.z));
     tfar = fminf(tfar * 1.0000004f + rt.slack, tmax_wide);
-    bool ok = (tnear <= tfar) && (cref[c] != RT_EMPTY);
-    tn[c] = ok ? tnear : RT_INF_F;
+    tn[c] = tnear <= tfar ? tnear : RT_INF_F;
   }
-  // sort the four children by entry distance (ascending), 5-comparator network
+  // three comparators bring the nearest child to slot 0; the others are pushed as they lie (sorting them
+  // too costs more instructions per visit than the better pop order saves: measured)
 #define RT_CSWAP(a, b)                                                                                       \
   if (tn[b] < tn[a]) {                                                                                       \
     float tt = tn[a];                                                                                        \
@@ -464,17 +467,26 @@ RT_HD bool node_visit(const DScene &sc, int node, const RayTrav &rt, float tmin,
   RT_CSWAP(0, 1)
   RT_CSWAP(2, 3)
   RT_CSWAP(0, 2)
-  RT_CSWAP(1, 3)
-  RT_CSWAP(1, 2)
 #undef RT_CSWAP
+  if (Stack::has_fast_push && sp + 3 <= Stack::fast_depth) {
+    // the usual case: all three slots are in the fast part of the stack, so the pushes are three
+    // predicated stores instead of three divergent branches
 #pragma unroll
-  for (int c = 3; c >= 1; c--)
-    if (tn[c] < RT_INF_F) {
-      if (sp < RT_STACK) {
-        stack.set(sp, cref[c], tn[c]);
-        sp++;
-      }
+    for (int c = 3; c >= 1; c--) {
+      bool p = tn[c] < RT_INF_F;
+      stack.set_fast_if(sp, cref[c], tn[c], p);
+      sp += p ? 1 : 0;
     }
+  } else {
+#pragma unroll
+    for (int c = 3; c >= 1; c--)
+      if (tn[c] < RT_INF_F) {
+        if (sp < RT_STACK) {
+          stack.set(sp, cref[c], tn[c]);
+          sp++;
+        }
+      }
+  }
   next = cref[0];
   return tn[0] < RT_INF_F;
 }
@@ -512,7 +524,13 @@ RT_HD void traverse(const DScene &sc, const Ray &ray, float tmin, Hit &hit, int 
 // The inexact FP32 slab test above may only ever ENTER more boxes than the exact one, so a simple
 // array stack is enough for host-side use.
 struct LocalStack {
+  static constexpr bool has_fast_push = false;
+  static constexpr int fast_depth = 0;
   StackEntry e[RT_STACK];
+  RT_HD void set_fast_if(int i, int ref, float t, bool p) {
+    if (p)
+      set(i, ref, t);
+  }
   RT_HD void set(int i, int ref, float t) {
     e[i].ref = ref;
     e[i].t = t;

@@ -32,10 +32,65 @@ LaunchShape rt_persistent_shape(const rt_context *ctx, int threads, int blocks_p
 // Short traversal stack: the first RT_STACK_SMEM entries of every thread live in shared memory
 // (column-interleaved: no bank conflicts), deeper entries spill to local memory.
 // ---------------------------------------------------------------------------------------------------
+#ifndef RT_LEAN
+#define RT_LEAN 1
+#endif
+#if RT_LEAN
+// One (reference, entry distance) pair per 8-byte word.  Every thread keeps the shared-window address of
+// its own column in a register (laundered through an empty asm so that it is not recomputed from the CTA's
+// window base at every use): a push or pop is one multiply-add and one 64-bit shared-memory access.
+__shared__ int2 rt_stack_smem[RT_STACK_SMEM * RT_BLOCK];
 struct SmemStack {
+  static constexpr bool has_fast_push = true;
+  static constexpr int fast_depth = RT_STACK_SMEM;
+  unsigned base;
+  StackEntry spill[RT_STACK - RT_STACK_SMEM];
+  __device__ __forceinline__ void init() {
+    base = (unsigned)__cvta_generic_to_shared(&rt_stack_smem[threadIdx.x]);
+    asm volatile("" : "+r"(base));
+  }
+  __device__ __forceinline__ void set_fast_if(int i, int ref, float t, bool p) { // i < RT_STACK_SMEM
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p st.shared.v2.b32 [%0], {%1, %2};\n\t}"
+                 :
+                 : "r"(base + (unsigned)i * (RT_BLOCK * 8u)), "r"(ref), "r"(__float_as_int(t)), "r"((int)p)
+                 : "memory");
+  }
+  __device__ __forceinline__ void set(int i, int ref, float t) {
+    if (i < RT_STACK_SMEM) {
+      set_fast_if(i, ref, t, true);
+    } else {
+      spill[i - RT_STACK_SMEM].ref = ref;
+      spill[i - RT_STACK_SMEM].t = t;
+    }
+  }
+  __device__ __forceinline__ void get(int i, int &ref, float &t) const {
+    if (i < RT_STACK_SMEM) {
+      int tb;
+      asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];"
+                   : "=r"(ref), "=r"(tb)
+                   : "r"(base + (unsigned)i * (RT_BLOCK * 8u))
+                   : "memory");
+      t = __int_as_float(tb);
+    } else {
+      ref = spill[i - RT_STACK_SMEM].ref;
+      t = spill[i - RT_STACK_SMEM].t;
+    }
+  }
+};
+#define RT_DECLARE_STACK(stack)                                                                              \
+  SmemStack stack;                                                                                           \
+  stack.init()
+#else
+struct SmemStack {
+  static constexpr bool has_fast_push = false;
+  static constexpr int fast_depth = 0;
   int *s_ref;
   float *s_t;
   StackEntry spill[RT_STACK - RT_STACK_SMEM];
+  __device__ __forceinline__ void set_fast_if(int i, int ref, float t, bool p) {
+    if (p)
+      set(i, ref, t);
+  }
   __device__ __forceinline__ void set(int i, int ref, float t) {
     if (i < RT_STACK_SMEM) {
       s_ref[i * RT_BLOCK] = ref;
@@ -55,6 +110,13 @@ struct SmemStack {
     }
   }
 };
+#define RT_DECLARE_STACK(stack)                                                                              \
+  __shared__ int s_ref[RT_STACK_SMEM * RT_BLOCK];                                                            \
+  __shared__ float s_t[RT_STACK_SMEM * RT_BLOCK];                                                            \
+  SmemStack stack;                                                                                           \
+  stack.s_ref = s_ref + threadIdx.x;                                                                         \
+  stack.s_t = s_t + threadIdx.x
+#endif
 
 __device__ __forceinline__ void path_to_key(const PassParams &pp, int path, int bounce, RayKey &key, int &owned_pixel) {
   int k = path % pp.n_owned;
@@ -107,7 +169,7 @@ __global__ void __launch_bounds__(RT_BLOCK)
 #define RT_REFILL 16 // measured: 16 beats 22 and 28 by 1-2 %
 #endif
 #ifndef RT_TAIL_BLOCKS
-#define RT_TAIL_BLOCKS 4 // resident blocks per SM of k_tail (register budget = 65536 / (128 * RT_TAIL_BLOCKS))
+#define RT_TAIL_BLOCKS 5 // resident blocks per SM of k_tail (register budget = 65536 / (128 * RT_TAIL_BLOCKS))
 #endif
 #define RT_DONE 0x7fffffff
 
@@ -116,11 +178,7 @@ __global__ void __launch_bounds__(RT_BLOCK, 8)
              const float4 *__restrict__ ray_a, const float4 *__restrict__ ray_b, float2 *__restrict__ hit,
              const unsigned int *__restrict__ counts, unsigned int *__restrict__ cursor, int bounce, int has_media,
              unsigned long long *stats) {
-  __shared__ int s_ref[RT_STACK_SMEM * RT_BLOCK];
-  __shared__ float s_t[RT_STACK_SMEM * RT_BLOCK];
-  SmemStack stack;
-  stack.s_ref = s_ref + threadIdx.x;
-  stack.s_t = s_t + threadIdx.x;
+  RT_DECLARE_STACK(stack);
   const unsigned int n = counts[bounce];
   if (blockIdx.x == 0 && threadIdx.x == 0)
     atomicAdd(&stats[0], (unsigned long long)n);
@@ -212,11 +270,7 @@ __global__ void __launch_bounds__(RT_BLOCK)
     k_extend_simple(const __grid_constant__ DScene sc, const __grid_constant__ PassParams pp,
                     const float4 *__restrict__ ray_a, const float4 *__restrict__ ray_b, float2 *__restrict__ hit,
                     const unsigned int *__restrict__ counts, int bounce, int has_media, unsigned long long *stats) {
-  __shared__ int s_ref[RT_STACK_SMEM * RT_BLOCK];
-  __shared__ float s_t[RT_STACK_SMEM * RT_BLOCK];
-  SmemStack stack;
-  stack.s_ref = s_ref + threadIdx.x;
-  stack.s_t = s_t + threadIdx.x;
+  RT_DECLARE_STACK(stack);
   const int n = (int)counts[bounce];
   if (blockIdx.x == 0 && threadIdx.x == 0)
     atomicAdd(&stats[0], (unsigned long long)n);
@@ -318,11 +372,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_TAIL_BLOCKS)
            float4 *__restrict__ next_b, float2 *__restrict__ next_hit, float4 *__restrict__ throughput,
            float4 *__restrict__ radiance, unsigned int *__restrict__ counts, unsigned int *__restrict__ cursor,
            int first_bounce, int end_bounce, int has_media, unsigned long long *stats) {
-  __shared__ int s_ref[RT_STACK_SMEM * RT_BLOCK];
-  __shared__ float s_t[RT_STACK_SMEM * RT_BLOCK];
-  SmemStack stack;
-  stack.s_ref = s_ref + threadIdx.x;
-  stack.s_t = s_t + threadIdx.x;
+  RT_DECLARE_STACK(stack);
   const unsigned int n = counts[first_bounce];
   const unsigned int lane = threadIdx.x & 31u;
   const unsigned int lt_mask = (1u << lane) - 1u;
@@ -514,11 +564,7 @@ __global__ void k_scatter_gathered(int width, int height, int n_ranks, int tile_
 __global__ void __launch_bounds__(RT_BLOCK)
     k_trace_fast(const __grid_constant__ DScene sc, const rt_ray *__restrict__ rays, long long n, uint64_t seed,
                  const int *__restrict__ leaf_object, const int *__restrict__ leaf_id, rt_hit *__restrict__ hits) {
-  __shared__ int s_ref[RT_STACK_SMEM * RT_BLOCK];
-  __shared__ float s_t[RT_STACK_SMEM * RT_BLOCK];
-  SmemStack stack;
-  stack.s_ref = s_ref + threadIdx.x;
-  stack.s_t = s_t + threadIdx.x;
+  RT_DECLARE_STACK(stack);
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride) {
     const rt_ray &in = rays[q];

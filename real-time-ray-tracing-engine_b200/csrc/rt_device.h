@@ -153,7 +153,8 @@ RT_HD Uniform4 philox_uniform4(uint64_t seed, uint32_t pixel, uint32_t sample, u
 #define RT_EMPTY ((int)0x7f800000)
 
 // Primitive record: 4 x float4 = 64 B, in BVH leaf (Morton) order, world space (instances baked).
-//   sphere: [0] c0.xyz, radius       [1] center_dir.xyz, -          [2] -                [3] -, typemat, id, object
+//   sphere: [0] c0.xyz, radius       [1] center_dir.xyz, colour.g   [2] material header  [3] colour.b, typemat, id, object
+//           [2] = copy of the material record's [0]; for metal / solid textures [2].w = colour.r as well
 //   quad:   [0] normal.xyz, D        [1] A.xyz, Q.x                 [2] B.xyz, Q.y       [3] Q.z, typemat, id, object
 //           alpha = A . (p - Q), beta = B . (p - Q)   with A = v x w, B = w x u  (Plane.cpp:93-94 rearranged)
 //   medium: [0] -1/density, first boundary record, n boundary records, medium index      [3] -, typemat, id, object
@@ -245,6 +246,26 @@ RT_HD Ray camera_ray(const DCamera &cam, int i, int j, int s_i, int s_j, float r
 RT_HD float4 ldg4(const float4 *p) {
 #if defined(__CUDA_ARCH__)
   return __ldg(p);
+#else
+  return *p;
+#endif
+}
+// Read-only loads the compiler may not move: issued where they are written, so that independent fetches of
+// a latency-bound kernel go out together instead of being sunk below the first branch that uses one of them.
+RT_HD float4 ldg4_now(const float4 *p) {
+#if defined(__CUDA_ARCH__)
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+#else
+  return *p;
+#endif
+}
+RT_HD float2 ldg2_now(const float2 *p) {
+#if defined(__CUDA_ARCH__)
+  float2 v;
+  asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
 #else
   return *p;
 #endif
@@ -731,12 +752,16 @@ RT_HD bool shade_segment(const DScene &sc, const Ray &ray, Hit hit, f3 throughpu
     return false;
   }
   const float4 *rec = sc.prims + (size_t)hit.prim * RT_PRIM_F4;
-  float4 r0 = ldg4(rec), r3 = ldg4(rec + 3);
+  float4 r0 = ldg4_now(rec), r1 = ldg4_now(rec + 1), r2 = ldg4_now(rec + 2), r3 = ldg4_now(rec + 3);
   uint32_t typemat = (uint32_t)f2i(r3.y);
   int type = typemat >> 28;
   const float4 *m = sc.mats + (size_t)(typemat & 0x0fffffffu) * RT_MAT_F4;
-  float4 m0 = ldg4(m);
+  // a sphere record carries its material header and, for metal / solid textures, the colour
+  // (rt_flatten.h): the hit is shaded after one dependent fetch instead of three
+  float4 m0 = type == RT_PT_SPHERE ? r2 : ldg4(m);
   int mtype = f2i(m0.x);
+  const bool inline_color = type == RT_PT_SPHERE && (mtype == 1 || f2i(m0.y) == RT_DTEX_SOLID);
+  const f3 color_a = inline_color ? F3(m0.w, r1.w, r3.x) : F3(0.f, 0.f, 0.f);
 
   // hit point, normal, front face (HitRecord::set_face_normal, HitRecord.hpp:36-39)
   f3 p = ray.o + hit.t * ray.d;
@@ -745,7 +770,6 @@ RT_HD bool shade_segment(const DScene &sc, const Ray &ray, Hit hit, f3 throughpu
   float tex_u = 0.f, tex_v = 0.f; // surface coordinates, only computed for image textures
   const bool wants_uv = f2i(m0.y) == RT_DTEX_IMAGE;
   if (type == RT_PT_SPHERE) {
-    float4 r1 = ldg4(rec + 1);
     f3 center = F3(r0) + ray.time * F3(r1);
     f3 outward = (1.0f / r0.w) * (p - center);
     outward = normalize(outward);
@@ -760,7 +784,6 @@ RT_HD bool shade_segment(const DScene &sc, const Ray &ray, Hit hit, f3 throughpu
     normal = front ? outward : -outward;
     out.next_skip_prim = hit.prim; // a ray leaving a flat primitive cannot hit it again
     if (wants_uv) {
-      float4 r1 = ldg4(rec + 1), r2 = ldg4(rec + 2);
       f3 hp = p - F3(r1.w, r2.w, r3.x);
       tex_u = dot(F3(r1), hp);
       tex_v = dot(F3(r2), hp);
@@ -772,7 +795,7 @@ RT_HD bool shade_segment(const DScene &sc, const Ray &ray, Hit hit, f3 throughpu
 
   if (mtype == 3) { // diffuse light: emits on the front face, never scatters (DiffuseLightMaterial.cpp:12-19)
     if (front)
-      out.radiance = throughput * material_texture(sc, m, m0, p, tex_u, tex_v);
+      out.radiance = throughput * (inline_color ? color_a : material_texture(sc, m, m0, p, tex_u, tex_v));
     return false;
   }
   if (last_bounce) // the scattered ray would be traced with depth 0 and contribute nothing
@@ -785,7 +808,7 @@ RT_HD bool shade_segment(const DScene &sc, const Ray &ray, Hit hit, f3 throughpu
   if (mtype == 1) { // metal (MetalMaterial.cpp:46-61)
     f3 reflected = ray.d - (2.f * dot(ray.d, normal)) * normal;
     out.next.d = normalize(reflected) + m0.z * unit_vector_polar(u.y, u.z);
-    out.throughput = throughput * F3(ldg4(m + 1));
+    out.throughput = throughput * (inline_color ? color_a : F3(ldg4(m + 1)));
     return true;
   }
   if (mtype == 2) { // dielectric (DielectricMaterial.cpp:62-84, Vec3Utility.hpp:76-89)
@@ -812,7 +835,7 @@ RT_HD bool shade_segment(const DScene &sc, const Ray &ray, Hit hit, f3 throughpu
 
   // lambertian (LambertianMaterial.cpp:15-59) / isotropic (IsotropicMaterial.cpp:12-31)
   bool lambert = mtype == 0;
-  f3 attenuation = material_texture(sc, m, m0, p, tex_u, tex_v);
+  f3 attenuation = inline_color ? color_a : material_texture(sc, m, m0, p, tex_u, tex_v);
   Onb uvw;
   if (lambert)
     uvw = onb_make(normal);

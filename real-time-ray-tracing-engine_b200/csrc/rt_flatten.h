@@ -366,6 +366,23 @@ inline int flatten(const rt_scene_desc *d, Flat &f) {
     f.mats.push_back(b);
   }
 
+  // spheres carry a copy of their material: the header in [2] and, when one colour is all the material
+  // needs (metal, or a solid texture), that colour in [2].w, [1].w, [3].x - shading a sphere hit then takes
+  // one dependent fetch (the primitive record) instead of three (record -> header -> colour)
+  for (size_t r = 0; r + RT_PRIM_F4 <= f.prims.size(); r += RT_PRIM_F4) {
+    uint32_t typemat = (uint32_t)f2i(f.prims[r + 3].y);
+    if ((typemat >> 28) != RT_PT_SPHERE || d->n_materials == 0)
+      continue;
+    size_t m = (size_t)(typemat & 0x0fffffffu) * RT_MAT_F4;
+    float4 m0 = f.mats[m], a = f.mats[m + 1];
+    if (f2i(m0.x) == RT_MAT_METAL || f2i(m0.y) == RT_DTEX_SOLID) {
+      m0.w = a.x;
+      f.prims[r + 1].w = a.y;
+      f.prims[r + 3].x = a.z;
+    }
+    f.prims[r + 2] = m0;
+  }
+
   for (int i = 0; i < d->n_perlins; i++) {
     const rt_perlin &p = d->perlins[i];
     for (int k = 0; k < RT_PERLIN_POINTS; k++)

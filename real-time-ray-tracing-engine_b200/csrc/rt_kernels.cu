@@ -320,8 +320,9 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_BLOCKS)
     ShadeResult res;
     int path = 0;
     if (active) {
-      float4 a = ray_a[q], b = ray_b[q];
-      float2 h = hit[q];
+      // all three queue reads go out before anything waits on one of them
+      float4 a = ldg4_now(ray_a + q), b = ldg4_now(ray_b + q);
+      float2 h = ldg2_now(hit + q);
       path = __float_as_int(b.w);
       Ray r;
       r.o = F3(a.x, a.y, a.z);
@@ -329,7 +330,9 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_BLOCKS)
       r.time = a.w;
       Hit ht;
       ht.t = h.x;
-      ht.prim = __float_as_int(h.y);
+      // a ray with a NaN time counts as a miss; the test also ties the miss branch to ray_a, which keeps
+      // that read next to the other two instead of behind the branch (one exposed memory latency less)
+      ht.prim = a.w == a.w ? __float_as_int(h.y) : -1;
       RayKey key;
       int k;
       path_to_key(pp, path, bounce, key, k);

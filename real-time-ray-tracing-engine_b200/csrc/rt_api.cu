@@ -123,6 +123,7 @@ int render_pass(rt_scene *scene, const rt_camera *camera, rt_film *film, int fir
   pp.recip_sqrt_spp = (float)(1.0 / sqrt_spp);
   pp.max_depth = max_depth;
   pp.seed = seed;
+  pp.film_direct = n_samples == 1 ? film->accum : nullptr;
   if (pp.n_paths == 0)
     return RT_OK;
   int st = ensure_wave(ctx, (size_t)pp.n_paths, 2 * ((size_t)max_depth + 2)); // queue lengths + fetch cursors
@@ -157,11 +158,11 @@ int render_pass(rt_scene *scene, const rt_camera *camera, rt_film *film, int fir
     launch_tail(ctx, sc, pp, w, first, std::min(max_depth, first + ctx->tail_span), buffer);
     tail_launches++;
   }
-  {
+  if (!pp.film_direct) {
     StageSpan span(ctx, RT_STAGE_ACCUMULATE);
     launch_accumulate(ctx, pp, w, film->accum);
   }
-  ctx->counters.kernel_launches += 2 + 2 * (uint64_t)wave_bounces + (uint64_t)tail_launches;
+  ctx->counters.kernel_launches += (pp.film_direct ? 1 : 2) + 2 * (uint64_t)wave_bounces + (uint64_t)tail_launches;
   ctx->counters.paths += (uint64_t)pp.n_paths;
   RT_CUDA(cudaGetLastError());
   return RT_OK;

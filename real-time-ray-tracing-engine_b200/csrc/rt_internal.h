@@ -24,6 +24,7 @@ struct PassParams {
   float recip_sqrt_spp;
   int max_depth;
   uint64_t seed;
+  float4 *film_direct; // one-sample passes: the film, written by the kernel that ends a path; else null
 };
 
 // Per-context wavefront storage (sized for the largest pass so far).

@@ -118,6 +118,21 @@ struct SmemStack {
   stack.s_t = s_t + threadIdx.x
 #endif
 
+// A path ends exactly once.  In a one-sample pass it is the only path of its pixel, so its contribution goes
+// straight into the film (bit-identical to k_accumulate's film + radiance); multi-sample passes park it per
+// path and k_accumulate sums each pixel's samples in order.
+__device__ __forceinline__ void path_ends(const PassParams &pp, float4 *__restrict__ radiance, int path, f3 rad) {
+  if (pp.film_direct) {
+    float4 f = pp.film_direct[path];
+    f.x += rad.x;
+    f.y += rad.y;
+    f.z += rad.z;
+    pp.film_direct[path] = f;
+  } else {
+    radiance[path] = make_float4(rad.x, rad.y, rad.z, 0.f);
+  }
+}
+
 __device__ __forceinline__ void path_to_key(const PassParams &pp, int path, int bounce, RayKey &key, int &owned_pixel) {
   int k = path % pp.n_owned;
   int s_local = path / pp.n_owned;
@@ -339,7 +354,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_BLOCKS)
       float4 tp = bounce == 0 ? make_float4(1.f, 1.f, 1.f, 0.f) : throughput[path];
       cont = shade_segment(sc, r, ht, F3(tp.x, tp.y, tp.z), key, last_bounce, res);
       if (!cont)
-        radiance[path] = make_float4(res.radiance.x, res.radiance.y, res.radiance.z, 0.f);
+        path_ends(pp, radiance, path, res.radiance);
     }
     unsigned int mask = __ballot_sync(0xffffffffu, cont);
     if (mask) {
@@ -485,7 +500,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_TAIL_BLOCKS)
         bounce++;
         segments++;
       } else {
-        radiance[path] = make_float4(res.radiance.x, res.radiance.y, res.radiance.z, 0.f);
+        path_ends(pp, radiance, path, res.radiance);
         best.t = -1.0f;
       }
     }

@@ -429,7 +429,7 @@ struct StackEntry {
 struct RayTrav {
   f3 inv, oi;
   float slack;
-  int nx, ny, nz; // row of the near plane: x 0/1, y 2/3, z 4/5
+  unsigned nx, ny, nz; // row of the near plane: x 0/1, y 2/3, z 4/5
 };
 RT_HD bool sign_bit(float f) { return f2i(f) < 0; }
 RT_HD RayTrav make_trav(f3 o, f3 d) {
@@ -456,9 +456,11 @@ template <class Stack>
 RT_HD bool node_visit(const DScene &sc, int node, const RayTrav &rt, float tmin, float tmax, Stack &stack, int &sp,
                       int &next) {
   RT_STAT_NODE();
-  const float4 *n = sc.nodes + (size_t)node * RT_NODE_F4;
-  float4 nrx = ldg4(n + rt.nx), frx = ldg4(n + (rt.nx ^ 1)), nry = ldg4(n + rt.ny), fry = ldg4(n + (rt.ny ^ 1)),
-         nrz = ldg4(n + rt.nz), frz = ldg4(n + (rt.nz ^ 1)), cr = ldg4(n + 6);
+  // rows are addressed with one 32-bit index each (node * 8 + row): a single wide multiply-add per load
+  const unsigned n = (unsigned)node * RT_NODE_F4;
+  float4 nrx = ldg4(sc.nodes + (n + rt.nx)), frx = ldg4(sc.nodes + (n + (rt.nx ^ 1u))),
+         nry = ldg4(sc.nodes + (n + rt.ny)), fry = ldg4(sc.nodes + (n + (rt.ny ^ 1u))),
+         nrz = ldg4(sc.nodes + (n + rt.nz)), frz = ldg4(sc.nodes + (n + (rt.nz ^ 1u))), cr = ldg4(sc.nodes + (n + 6u));
   float tn[4];
   int cref[4] = {f2i(cr.x), f2i(cr.y), f2i(cr.z), f2i(cr.w)};
   const float nx[4] = {nrx.x, nrx.y, nrx.z, nrx.w}, fx[4] = {frx.x, frx.y, frx.z, frx.w};

@@ -186,6 +186,9 @@ __global__ void __launch_bounds__(RT_BLOCK)
 #ifndef RT_TAIL_BLOCKS
 #define RT_TAIL_BLOCKS 5 // resident blocks per SM of k_tail (register budget = 65536 / (128 * RT_TAIL_BLOCKS))
 #endif
+#ifndef RT_TAIL_REFILL
+#define RT_TAIL_REFILL 8 // k_tail leaves the traversal loop to shade / refill below this many busy lanes
+#endif
 #define RT_DONE 0x7fffffff
 
 __global__ void __launch_bounds__(RT_BLOCK, 8)
@@ -460,7 +463,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_TAIL_BLOCKS)
         } while (ref < 0);
       }
       unsigned int busy = __ballot_sync(0xffffffffu, ref != RT_DONE);
-      if (__popc(busy) < RT_REFILL)
+      if (__popc(busy) < RT_TAIL_REFILL)
         break;
     }
 

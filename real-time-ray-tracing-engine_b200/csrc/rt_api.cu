@@ -124,6 +124,10 @@ int render_pass(rt_scene *scene, const rt_camera *camera, rt_film *film, int fir
   pp.max_depth = max_depth;
   pp.seed = seed;
   pp.film_direct = n_samples == 1 ? film->accum : nullptr;
+  pp.div_owned = fastdiv_make((uint32_t)std::max(pp.n_owned, 1));
+  pp.div_width = fastdiv_make((uint32_t)std::max(pp.map.width, 1));
+  pp.div_tile_rows = fastdiv_make((uint32_t)std::max(pp.map.tile_rows, 1));
+  pp.div_sqrt_spp = fastdiv_make((uint32_t)std::max(sqrt_spp, 1));
   if (pp.n_paths == 0)
     return RT_OK;
   int st = ensure_wave(ctx, (size_t)pp.n_paths, 2 * ((size_t)max_depth + 2)); // queue lengths + fetch cursors

@@ -89,11 +89,68 @@ RT_HD f3 operator*(f3 a, float t) { return F3(t * a.x, t * a.y, t * a.z); }
 RT_HD float dot(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 RT_HD f3 cross(f3 a, f3 b) { return F3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 RT_HD float length(f3 a) { return sqrtf(dot(a, a)); }
-RT_HD f3 normalize(f3 a) { // Vec3::normalize (Vec3.hpp:141-149)
-  float len = length(a);
-  if (len > 1e-8f)
-    return (1.0f / len) * a;
+// Single-instruction reciprocal / square root / reciprocal square root (<= 2 ulp) for the shading code, where
+// IEEE rounding buys nothing (the FP32 result is a Monte-Carlo sample); ray-box and ray-primitive tests
+// keep the correctly rounded operations.
+RT_HD float fast_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return 1.0f / x;
+#endif
+}
+RT_HD float fast_sqrt(float x) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return sqrtf(x);
+#endif
+}
+RT_HD float fast_rsqrt(float x) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
+RT_HD f3 normalize(f3 a) { // Vec3::normalize (Vec3.hpp:141-149): |a| <= 1e-8 -> (1, 0, 0)
+  float len2 = dot(a, a);
+  if (len2 > 1e-16f)
+    return fast_rsqrt(len2) * a;
   return F3(1.f, 0.f, 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Division by a launch-invariant integer (Granlund & Montgomery round-up method): x / d for x < 2^31 as
+// (mulhi(x, mul) + x) >> shift.  Path and pixel indexing divides by the film width, the tile height and
+// the owned-pixel count for every path at every bounce; a hardware-less 32-bit division is ~20
+// instructions, this is 3.
+// ---------------------------------------------------------------------------------------------------
+struct FastDiv {
+  uint32_t mul, shift, d;
+};
+inline FastDiv fastdiv_make(uint32_t d) { // d >= 1
+  FastDiv f;
+  uint32_t l = 0;
+  while (l < 32 && ((uint64_t)1 << l) < d)
+    l++;
+  f.mul = (uint32_t)((((uint64_t)1 << 32) * (((uint64_t)1 << l) - d)) / d + 1);
+  f.shift = l;
+  f.d = d;
+  return f;
+}
+RT_HD uint32_t fastdiv(const FastDiv &f, uint32_t x) { // x < 2^31
+#if defined(__CUDA_ARCH__)
+  return (__umulhi(x, f.mul) + x) >> f.shift;
+#else
+  return (uint32_t)((((uint64_t)x * f.mul) >> 32) + x) >> f.shift;
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -619,7 +676,7 @@ RT_HD f3 material_texture(const DScene &sc, const float4 *m, float4 m0, f3 p, fl
   if (tex == RT_DTEX_SOLID)
     return F3(ldg4(m + 1));
   if (tex == RT_DTEX_CHECKER) {
-    float inv_scale = 1.0f / m0.z;
+    float inv_scale = fast_rcp(m0.z);
     int xi = (int)floorf(inv_scale * p.x), yi = (int)floorf(inv_scale * p.y), zi = (int)floorf(inv_scale * p.z);
     bool even = ((xi + yi + zi) % 2) == 0;
     return F3(ldg4(m + (even ? 1 : 2)));
@@ -666,7 +723,7 @@ RT_HD void sincos_2pi(float u, float &sn, float &cs) {
 // cuda_vec3_random_unit_vector (Vec3Utility.cuh:65-70)
 RT_HD f3 unit_vector_polar(float u1, float u2) {
   float z = -1.0f + 2.0f * u1;
-  float r = sqrtf(fmaxf(0.f, 1.0f - z * z));
+  float r = fast_sqrt(fmaxf(0.f, 1.0f - z * z));
   float sn, cs;
   sincos_2pi(u2, sn, cs);
   return F3(r * cs, r * sn, z);
@@ -675,8 +732,8 @@ RT_HD f3 unit_vector_polar(float u1, float u2) {
 RT_HD f3 cosine_direction(float r1, float r2) {
   float sn, cs;
   sincos_2pi(r1, sn, cs);
-  float s = sqrtf(r2);
-  return F3(cs * s, sn * s, sqrtf(1.f - r2));
+  float s = fast_sqrt(r2);
+  return F3(cs * s, sn * s, fast_sqrt(1.f - r2));
 }
 
 // Lights: HittablePDF over the light list (PDF.hpp:82-113, HittableList.cpp:44-63).
@@ -694,10 +751,10 @@ RT_HD f3 light_random(const float4 *l, f3 origin, float r1, float r2) {
   float distance_squared = dot(direction, direction);
   Onb uvw = onb_make(direction);
   float radius = l1.x;
-  float z = 1.f + r2 * (sqrtf(fmaxf(0.f, 1.f - radius * radius / distance_squared)) - 1.f);
+  float z = 1.f + r2 * (fast_sqrt(fmaxf(0.f, 1.f - radius * radius * fast_rcp(distance_squared))) - 1.f);
   float sn, cs;
   sincos_2pi(r1, sn, cs);
-  float s = sqrtf(fmaxf(0.f, 1.f - z * z));
+  float s = fast_sqrt(fmaxf(0.f, 1.f - z * z));
   return onb_transform(uvw, F3(cs * s, sn * s, z));
 }
 
@@ -718,8 +775,8 @@ RT_HD float light_pdf_value(const float4 *l, f3 origin, f3 dir) {
       return 0.f;
     float dd = dot(dir, dir);
     float distance_squared = t * t * dd;
-    float cosine = fabsf(dot(dir, F3(l3)) / sqrtf(dd));
-    return distance_squared / (cosine * l1.w);
+    float cosine = fabsf(dot(dir, F3(l3)) * fast_rsqrt(dd));
+    return distance_squared * fast_rcp(cosine * l1.w);
   }
   // Sphere::pdf_value (Sphere.cpp:145-159)
   float4 s0 = make_float4(l0.x, l0.y, l0.z, l1.x);
@@ -727,9 +784,9 @@ RT_HD float light_pdf_value(const float4 *l, f3 origin, f3 dir) {
   if (!sphere_hit(s0, s1, r, RT_T_MIN, RT_INF_F, t))
     return 0.f;
   f3 oc = F3(l0) - origin;
-  float cos_theta_max = sqrtf(fmaxf(0.f, 1.f - l1.x * l1.x / dot(oc, oc)));
+  float cos_theta_max = fast_sqrt(fmaxf(0.f, 1.f - l1.x * l1.x * fast_rcp(dot(oc, oc))));
   float solid_angle = 2.f * RT_PI_F * (1.f - cos_theta_max);
-  return 1.f / solid_angle;
+  return fast_rcp(solid_angle);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -773,8 +830,7 @@ RT_HD bool shade_segment(const DScene &sc, const Ray &ray, Hit hit, f3 throughpu
   const bool wants_uv = f2i(m0.y) == RT_DTEX_IMAGE;
   if (type == RT_PT_SPHERE) {
     f3 center = F3(r0) + ray.time * F3(r1);
-    f3 outward = (1.0f / r0.w) * (p - center);
-    outward = normalize(outward);
+    f3 outward = normalize(p - center); // (p - center) / radius (Sphere.cpp:123), renormalised
     p = center + r0.w * outward; // keep the point on the surface (FP32 drift on large spheres)
     front = dot(ray.d, outward) < 0.f;
     normal = front ? outward : -outward;
@@ -814,12 +870,12 @@ RT_HD bool shade_segment(const DScene &sc, const Ray &ray, Hit hit, f3 throughpu
     return true;
   }
   if (mtype == 2) { // dielectric (DielectricMaterial.cpp:62-84, Vec3Utility.hpp:76-89)
-    float ri = front ? (1.0f / m0.z) : m0.z;
+    float ri = front ? fast_rcp(m0.z) : m0.z;
     f3 unit_direction = normalize(ray.d);
     float cos_theta = fminf(dot(-unit_direction, normal), 1.0f);
-    float sin_theta = sqrtf(fmaxf(0.f, 1.0f - cos_theta * cos_theta));
+    float sin_theta = fast_sqrt(fmaxf(0.f, 1.0f - cos_theta * cos_theta));
     bool cannot_refract = ri * sin_theta > 1.0f;
-    float r0s = (1.f - ri) / (1.f + ri);
+    float r0s = (1.f - ri) * fast_rcp(1.f + ri);
     r0s = r0s * r0s;
     float c1 = 1.f - cos_theta;
     float reflectance = r0s + (1.f - r0s) * (c1 * c1 * c1 * c1 * c1);
@@ -827,7 +883,7 @@ RT_HD bool shade_segment(const DScene &sc, const Ray &ray, Hit hit, f3 throughpu
       out.next.d = unit_direction - (2.f * dot(unit_direction, normal)) * normal;
     } else {
       f3 perp = ri * (unit_direction + cos_theta * normal);
-      f3 parallel = (-sqrtf(fabsf(1.0f - dot(perp, perp)))) * normal;
+      f3 parallel = (-fast_sqrt(fabsf(1.0f - dot(perp, perp)))) * normal;
       out.next.d = perp + parallel;
     }
     out.throughput = throughput;
@@ -871,7 +927,7 @@ RT_HD bool shade_segment(const DScene &sc, const Ray &ray, Hit hit, f3 throughpu
   if (!(pdf_value > 1e-8f) || !(scattering_pdf > 0.f)) // zero weight: nothing further can contribute
     return false;
   out.next.d = dir;
-  out.throughput = throughput * ((scattering_pdf / pdf_value) * attenuation);
+  out.throughput = throughput * ((scattering_pdf * fast_rcp(pdf_value)) * attenuation);
   return true;
 }
 

@@ -25,6 +25,7 @@ struct PassParams {
   int max_depth;
   uint64_t seed;
   float4 *film_direct; // one-sample passes: the film, written by the kernel that ends a path; else null
+  FastDiv div_owned, div_width, div_tile_rows, div_sqrt_spp; // invariant divisors of the path -> pixel mapping
 };
 
 // Per-context wavefront storage (sized for the largest pass so far).

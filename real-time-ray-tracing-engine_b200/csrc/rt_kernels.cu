@@ -133,17 +133,25 @@ __device__ __forceinline__ void path_ends(const PassParams &pp, float4 *__restri
   }
 }
 
-__device__ __forceinline__ void path_to_key(const PassParams &pp, int path, int bounce, RayKey &key, int &owned_pixel) {
-  int k = path % pp.n_owned;
-  int s_local = path / pp.n_owned;
-  int local_row = k / pp.map.width;
-  int col = k - local_row * pp.map.width;
-  int row = owned_row_to_global(pp.map, local_row);
+__device__ __forceinline__ void path_to_key(const PassParams &pp, int path, int bounce, RayKey &key, int &owned_pixel,
+                                            int &row, int &col) {
+  uint32_t s_local = fastdiv(pp.div_owned, (uint32_t)path);
+  uint32_t k = (uint32_t)path - s_local * (uint32_t)pp.n_owned;
+  uint32_t local_row = fastdiv(pp.div_width, k);
+  col = (int)(k - local_row * (uint32_t)pp.map.width);
+  // owned_row_to_global (rt_device.h): tile t of this rank is global tile t * n_ranks + rank
+  uint32_t tile_local = fastdiv(pp.div_tile_rows, local_row);
+  uint32_t in_tile = local_row - tile_local * (uint32_t)pp.map.tile_rows;
+  row = (int)((tile_local * (uint32_t)pp.map.n_ranks + (uint32_t)pp.map.rank) * (uint32_t)pp.map.tile_rows + in_tile);
   key.seed = pp.seed;
   key.pixel = (uint32_t)row * (uint32_t)pp.map.width + (uint32_t)col;
-  key.sample = (uint32_t)(pp.first_sample + s_local);
+  key.sample = (uint32_t)pp.first_sample + s_local;
   key.bounce = (uint32_t)bounce;
-  owned_pixel = k;
+  owned_pixel = (int)k;
+}
+__device__ __forceinline__ void path_to_key(const PassParams &pp, int path, int bounce, RayKey &key, int &owned_pixel) {
+  int row, col;
+  path_to_key(pp, path, bounce, key, owned_pixel, row, col);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -155,11 +163,9 @@ __global__ void __launch_bounds__(RT_BLOCK)
   int stride = gridDim.x * blockDim.x;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < pp.n_paths; p += stride) {
     RayKey key;
-    int k;
-    path_to_key(pp, p, 0, key, k);
-    int row = (int)(key.pixel / (uint32_t)pp.map.width), col = (int)(key.pixel % (uint32_t)pp.map.width);
-    int s = (int)key.sample;
-    int s_i = s % pp.sqrt_spp, s_j = s / pp.sqrt_spp;
+    int k, row, col;
+    path_to_key(pp, p, 0, key, k, row, col);
+    int s_j = (int)fastdiv(pp.div_sqrt_spp, key.sample), s_i = (int)key.sample - s_j * pp.sqrt_spp;
     Uniform4 u0 = philox_uniform4(pp.seed, key.pixel, key.sample, 0, RT_STREAM_CAMERA, 0);
     Uniform4 u1 = philox_uniform4(pp.seed, key.pixel, key.sample, 0, RT_STREAM_CAMERA, 1);
     Ray r = camera_ray(pp.cam, col, row, s_i, s_j, pp.recip_sqrt_spp, u0, u1);

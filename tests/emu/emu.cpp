@@ -316,4 +316,7 @@ void emu_render(EmuScene *s, const rt_camera *camera, int first_sample, int n_sa
     *segments = segs;
 }
 
+// x / d through the device code's FastDiv
+uint32_t emu_fastdiv(uint32_t d, uint32_t x) { return fastdiv(fastdiv_make(d), x); }
+
 } // extern "C"

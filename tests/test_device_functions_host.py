@@ -144,3 +144,18 @@ def test_image_texture_scene(oracle, emu, host_scenes, tmp_path):
     assert ol.desc_bytes(db)[5:7] == ol.desc_bytes(d)[5:7]  # materials, textures
     emu.emu_scene_destroy(es)
     oracle.ora_scene_destroy(osc)
+
+
+def test_fast_division_by_invariant_integers(emu):
+    """FastDiv (rt_device.h) maps path ids to pixels in every kernel: exact for every divisor and x < 2^31."""
+    emu.emu_fastdiv.restype = C.c_uint32
+    emu.emu_fastdiv.argtypes = [C.c_uint32, C.c_uint32]
+    rng = np.random.default_rng(7)
+    divisors = [1, 2, 3, 5, 7, 8, 10, 64, 225, 400, 1080, 1920, 3840, 2073600, 8294400, 2**30, 2**31 - 1]
+    divisors += [int(d) for d in rng.integers(1, 2**31, 200)]
+    for d in divisors:
+        xs = [0, 1, d - 1, d, d + 1, 2 * d - 1, 2 * d, 2**31 - 1] + [int(x) for x in rng.integers(0, 2**31, 50)]
+        xs += [q * d + r for q in (3, 1000, (2**31 - 1) // d) for r in (-1, 0, 1)]
+        for x in xs:
+            if 0 <= x < 2**31:
+                assert emu.emu_fastdiv(d, x) == x // d, (d, x)

@@ -328,17 +328,27 @@ __global__ void __launch_bounds__(RT_BLOCK)
 #ifndef RT_SHADE_BLOCKS
 #define RT_SHADE_BLOCKS 8 // resident blocks per SM (64 registers): k_shade is latency bound, occupancy wins over a few spills
 #endif
-__global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_BLOCKS)
+#ifndef RT_SHADE_THREADS
+#define RT_SHADE_THREADS 256
+#endif
+#define RT_SHADE_WARPS (RT_SHADE_THREADS / 32)
+// Queue compaction: every warp counts its continuing paths with a ballot, the block adds the counts up in
+// shared memory and reserves the slots of all its warps with ONE atomicAdd on the next queue's length.  All
+// atomics of a launch hit the same address and the L2 serialises them (~0.85 clocks each): one per warp
+// (65 k per launch at 1080p) kept every warp waiting on that queue; one per block is 8 times fewer.
+__global__ void __launch_bounds__(RT_SHADE_THREADS, RT_SHADE_BLOCKS * RT_BLOCK / RT_SHADE_THREADS)
     k_shade(const __grid_constant__ DScene sc, const __grid_constant__ PassParams pp, const float4 *__restrict__ ray_a,
             const float4 *__restrict__ ray_b, const float2 *__restrict__ hit, float4 *__restrict__ next_a,
             float4 *__restrict__ next_b, float2 *__restrict__ next_hit, float4 *__restrict__ throughput,
             float4 *__restrict__ radiance, unsigned int *__restrict__ counts, int bounce) {
+  __shared__ unsigned int s_count[RT_SHADE_WARPS], s_first[RT_SHADE_WARPS];
   const int n = (int)counts[bounce];
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool last_bounce = bounce + 1 >= pp.max_depth;
-  int stride = gridDim.x * blockDim.x;
-  for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < n; base += stride) {
-    int q = base + lane;
+  const int stride = gridDim.x * blockDim.x;
+  // the same trip count for every warp of the block: the loop body has block-wide barriers
+  for (int block_base = blockIdx.x * blockDim.x; block_base < n; block_base += stride) {
+    int q = block_base + (int)threadIdx.x;
     bool active = q < n;
     bool cont = false;
     ShadeResult res;
@@ -364,20 +374,36 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_BLOCKS)
       cont = shade_segment(sc, r, ht, F3(tp.x, tp.y, tp.z), key, last_bounce, res);
       if (!cont)
         path_ends(pp, radiance, path, res.radiance);
+      else
+        throughput[path] = make_float4(res.throughput.x, res.throughput.y, res.throughput.z, 0.f);
     }
     unsigned int mask = __ballot_sync(0xffffffffu, cont);
-    if (mask) {
-      unsigned int pos = 0;
-      if (lane == __ffs(mask) - 1)
-        pos = atomicAdd(&counts[bounce + 1], (unsigned int)__popc(mask));
-      pos = __shfl_sync(0xffffffffu, pos, __ffs(mask) - 1);
-      if (cont) {
-        unsigned int slot = pos + (unsigned int)__popc(mask & ((1u << lane) - 1u));
-        next_a[slot] = make_float4(res.next.o.x, res.next.o.y, res.next.o.z, res.next.time);
-        next_b[slot] = make_float4(res.next.d.x, res.next.d.y, res.next.d.z, __int_as_float(path));
-        next_hit[slot] = make_float2(0.f, __int_as_float(res.next_skip_prim));
-        throughput[path] = make_float4(res.throughput.x, res.throughput.y, res.throughput.z, 0.f);
+    if (lane == 0)
+      s_count[warp] = (unsigned int)__popc(mask);
+    __syncthreads();
+    if (warp == 0) { // exclusive prefix over the warps' counts + the block's reservation
+      unsigned int c = lane < RT_SHADE_WARPS ? s_count[lane] : 0u;
+      unsigned int incl = c;
+#pragma unroll
+      for (int o = 1; o < RT_SHADE_WARPS; o <<= 1) {
+        unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o)
+          incl += t;
       }
+      unsigned int total = __shfl_sync(0xffffffffu, incl, RT_SHADE_WARPS - 1);
+      unsigned int first = 0;
+      if (lane == 0 && total)
+        first = atomicAdd(&counts[bounce + 1], total);
+      first = __shfl_sync(0xffffffffu, first, 0);
+      if (lane < RT_SHADE_WARPS)
+        s_first[lane] = first + incl - c;
+    }
+    __syncthreads();
+    if (cont) {
+      unsigned int slot = s_first[warp] + (unsigned int)__popc(mask & ((1u << lane) - 1u));
+      next_a[slot] = make_float4(res.next.o.x, res.next.o.y, res.next.o.z, res.next.time);
+      next_b[slot] = make_float4(res.next.d.x, res.next.d.y, res.next.d.z, __int_as_float(path));
+      next_hit[slot] = make_float2(0.f, __int_as_float(res.next_skip_prim));
     }
   }
 }
@@ -812,12 +838,12 @@ void launch_extend(const rt_context *ctx, const DScene &sc, const PassParams &pp
 }
 
 void launch_shade(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int bounce) {
-  LaunchShape sh = rt_persistent_shape(ctx, RT_BLOCK, 8);
-  int need = ceil_div(pp.n_paths, RT_BLOCK);
+  LaunchShape sh = rt_persistent_shape(ctx, RT_SHADE_THREADS, RT_SHADE_BLOCKS * RT_BLOCK / RT_SHADE_THREADS);
+  int need = ceil_div(pp.n_paths, RT_SHADE_THREADS);
   int b = bounce & 1, nb = b ^ 1;
-  k_shade<<<need < sh.blocks ? need : sh.blocks, RT_BLOCK, 0, ctx->stream>>>(sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b],
-                                                                             w.ray_a[nb], w.ray_b[nb], w.hit[nb],
-                                                                             w.throughput, w.radiance, w.counts, bounce);
+  k_shade<<<need < sh.blocks ? need : sh.blocks, RT_SHADE_THREADS, 0, ctx->stream>>>(
+      sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b], w.ray_a[nb], w.ray_b[nb], w.hit[nb], w.throughput, w.radiance, w.counts,
+      bounce);
 }
 
 void launch_tail(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int first_bounce,

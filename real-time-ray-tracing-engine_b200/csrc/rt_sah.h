@@ -1,0 +1,175 @@
+// rt_sah.h — host-side binary SAH build for small scenes (the same cost model as the reference's builder,
+// optimization/BVHNode.cpp:168-320: surface-area heuristic over candidate planes on the centroid bounds, median
+// fallback), written as an iterative binned sweep.  Produces the BinTree arrays the device collapse stage
+// (rt_bvh.h, k_collapse) turns into 4-wide nodes, so everything downstream of the binary tree is shared with the
+// GPU LBVH path.  Used below RT_SAH_MAX_PRIMS primitives, where a host build costs less than a millisecond
+// and the better tree saves ~20 % of the node visits of every ray; larger scenes keep the device LBVH.
+#pragma once
+
+#include "rt_bvh.h"
+
+#include <algorithm>
+#include <cstdint>
+#include <vector>
+
+#include <cstdlib>
+#include <cstring>
+
+#define RT_SAH_MIN_PRIMS 64 // below this the tree is two levels either way (measured: no gain, Cornell + smoke loses)
+#define RT_SAH_MAX_PRIMS (1 << 16)
+
+namespace rtsah {
+
+// RT_BVH=lbvh / RT_BVH=sah force one builder (A/B runs and the tests of both paths).
+inline bool use_sah(int n) {
+  const char *e = std::getenv("RT_BVH");
+  if (e && !std::strcmp(e, "lbvh"))
+    return false;
+  if (e && !std::strcmp(e, "sah"))
+    return n >= 2;
+  return n >= RT_SAH_MIN_PRIMS && n <= RT_SAH_MAX_PRIMS;
+}
+
+struct HostTree {
+  std::vector<int> left, right, parent; // BinTree layout: parent has 2n-1 entries (internal, then leaves)
+  std::vector<BuildBox> box;            // per internal node
+  std::vector<uint32_t> order;          // leaf j holds primitive order[j]
+};
+
+inline BuildBox empty_box() {
+  BuildBox b;
+  for (int a = 0; a < 3; a++) {
+    b.lo[a] = RT_INF_F;
+    b.hi[a] = -RT_INF_F;
+  }
+  return b;
+}
+inline float safe_area(const BuildBox &b) { return b.hi[0] < b.lo[0] ? 0.f : box_area(b); }
+
+// boxes: one per primitive (n >= 2).  Leaves hold exactly one primitive.
+inline void build(const BuildBox *boxes, int n, HostTree &t) {
+  const int n_internal = n - 1;
+  t.left.assign(n_internal, 0);
+  t.right.assign(n_internal, 0);
+  t.parent.assign(2 * (size_t)n - 1, -1);
+  t.box.assign(n_internal, empty_box());
+  t.order.resize(n);
+  for (int i = 0; i < n; i++)
+    t.order[i] = (uint32_t)i;
+  std::vector<float> cen((size_t)n * 3);
+  for (int i = 0; i < n; i++)
+    for (int a = 0; a < 3; a++)
+      cen[(size_t)i * 3 + a] = 0.5f * (boxes[i].lo[a] + boxes[i].hi[a]);
+
+  struct Task {
+    int first, count, node; // range of `order`, internal node index to fill
+  };
+  std::vector<Task> stack;
+  int next_node = 1;
+  stack.push_back({0, n, 0});
+  constexpr int kBins = 32;
+  while (!stack.empty()) {
+    Task task = stack.back();
+    stack.pop_back();
+    uint32_t *idx = t.order.data() + task.first;
+    BuildBox bounds = empty_box(), cbounds = empty_box();
+    for (int k = 0; k < task.count; k++) {
+      bounds = box_union(bounds, boxes[idx[k]]);
+      for (int a = 0; a < 3; a++) {
+        float c = cen[(size_t)idx[k] * 3 + a];
+        cbounds.lo[a] = fminf(cbounds.lo[a], c);
+        cbounds.hi[a] = fmaxf(cbounds.hi[a], c);
+      }
+    }
+    t.box[task.node] = bounds;
+
+    int mid = -1;
+    if (task.count == 2) {
+      mid = 1;
+    } else {
+      // binned SAH over the three axes of the centroid bounds
+      float best_cost = RT_INF_F;
+      int best_axis = -1, best_bin = -1;
+      for (int a = 0; a < 3; a++) {
+        float ext = cbounds.hi[a] - cbounds.lo[a];
+        if (!(ext > 0.f))
+          continue;
+        float scale = (float)kBins / ext;
+        BuildBox bin_box[kBins];
+        int bin_count[kBins];
+        for (int b = 0; b < kBins; b++) {
+          bin_box[b] = empty_box();
+          bin_count[b] = 0;
+        }
+        for (int k = 0; k < task.count; k++) {
+          int b = (int)((cen[(size_t)idx[k] * 3 + a] - cbounds.lo[a]) * scale);
+          b = b < 0 ? 0 : (b > kBins - 1 ? kBins - 1 : b);
+          bin_box[b] = box_union(bin_box[b], boxes[idx[k]]);
+          bin_count[b]++;
+        }
+        float right_area[kBins];
+        int right_count[kBins];
+        BuildBox acc = empty_box();
+        int cnt = 0;
+        for (int b = kBins - 1; b >= 1; b--) {
+          acc = box_union(acc, bin_box[b]);
+          cnt += bin_count[b];
+          right_area[b] = safe_area(acc);
+          right_count[b] = cnt;
+        }
+        acc = empty_box();
+        cnt = 0;
+        for (int b = 0; b < kBins - 1; b++) { // split between bin b and b + 1
+          acc = box_union(acc, bin_box[b]);
+          cnt += bin_count[b];
+          if (cnt == 0 || right_count[b + 1] == 0)
+            continue;
+          float cost = safe_area(acc) * (float)cnt + right_area[b + 1] * (float)right_count[b + 1];
+          if (cost < best_cost) {
+            best_cost = cost;
+            best_axis = a;
+            best_bin = b;
+          }
+        }
+      }
+      if (best_axis >= 0) {
+        float ext = cbounds.hi[best_axis] - cbounds.lo[best_axis];
+        float scale = (float)kBins / ext;
+        float lo = cbounds.lo[best_axis];
+        uint32_t *m = std::partition(idx, idx + task.count, [&](uint32_t p) {
+          int b = (int)((cen[(size_t)p * 3 + best_axis] - lo) * scale);
+          b = b < 0 ? 0 : (b > kBins - 1 ? kBins - 1 : b);
+          return b <= best_bin;
+        });
+        mid = (int)(m - idx);
+      }
+      if (mid <= 0 || mid >= task.count) { // all centroids coincide (or numerical trouble): split in the middle
+        mid = task.count / 2;
+        int axis = 0;
+        for (int a = 1; a < 3; a++)
+          if (cbounds.hi[a] - cbounds.lo[a] > cbounds.hi[axis] - cbounds.lo[axis])
+            axis = a;
+        std::nth_element(idx, idx + mid, idx + task.count, [&](uint32_t p, uint32_t q) {
+          return cen[(size_t)p * 3 + axis] < cen[(size_t)q * 3 + axis];
+        });
+      }
+    }
+    // children: a single primitive becomes leaf ~position, otherwise a new internal node
+    int child[2];
+    int first[2] = {task.first, task.first + mid}, count[2] = {mid, task.count - mid};
+    for (int c = 0; c < 2; c++) {
+      if (count[c] == 1) {
+        child[c] = ~first[c];
+        t.parent[(size_t)n_internal + first[c]] = task.node;
+      } else {
+        child[c] = next_node++;
+        t.parent[child[c]] = task.node;
+        stack.push_back({first[c], count[c], child[c]});
+      }
+    }
+    t.left[task.node] = child[0];
+    t.right[task.node] = child[1];
+  }
+}
+
+} // namespace rtsah

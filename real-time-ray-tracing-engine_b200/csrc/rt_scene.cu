@@ -13,6 +13,9 @@
 #include <limits>
 
 #include "rt_flatten.h"
+#include "rt_sah.h"
+
+#include <chrono>
 
 using namespace rtflat;
 
@@ -142,16 +145,35 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
     RT_CUDA(cudaMemcpyAsync(d_bounds, bounds, sizeof bounds, cudaMemcpyHostToDevice, s));
     RT_CUDA(cudaMemsetAsync(t.visits, 0, sizeof(unsigned int) * (n - 1), s));
 
+    const bool sah = rtsah::use_sah(n);
+    double host_build_ms = 0.0;
+    if (sah) {
+      // small scene: binary SAH tree on the host (rt_sah.h); primitive order, children and boxes are
+      // uploaded in the layout the device hierarchy + refit stages would have produced
+      auto t0 = std::chrono::steady_clock::now();
+      rtsah::HostTree ht;
+      rtsah::build(boxes.data(), n, ht);
+      host_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      RT_CUDA(cudaMemcpyAsync(d_index_sorted, ht.order.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, s));
+      RT_CUDA(cudaMemcpyAsync(t.left, ht.left.data(), sizeof(int) * (n - 1), cudaMemcpyHostToDevice, s));
+      RT_CUDA(cudaMemcpyAsync(t.right, ht.right.data(), sizeof(int) * (n - 1), cudaMemcpyHostToDevice, s));
+      RT_CUDA(cudaMemcpyAsync(t.box, ht.box.data(), sizeof(BuildBox) * (n - 1), cudaMemcpyHostToDevice, s));
+      RT_CUDA(cudaStreamSynchronize(s)); // ht goes out of scope
+    }
     RT_CUDA(cudaEventRecord(ev0, s));
-    launch_morton(s, d_boxes, n, d_bounds, d_bounds + 3, d_codes, d_index);
-    if ((st = sort_pairs(s, d_codes, d_codes_sorted, d_index, d_index_sorted, n)))
-      return st;
+    if (!sah) {
+      launch_morton(s, d_boxes, n, d_bounds, d_bounds + 3, d_codes, d_index);
+      if ((st = sort_pairs(s, d_codes, d_codes_sorted, d_index, d_index_sorted, n)))
+        return st;
+    }
     launch_gather_boxes(s, d_boxes, d_index_sorted, d_sorted_boxes, n);
     launch_gather_records(s, d_prims_in, d_index_sorted, sc->prims, n, RT_PRIM_F4 * (int)sizeof(float4));
     static_assert(sizeof(PrimExact) % 16 == 0, "PrimExact must be a multiple of 16 bytes");
     launch_gather_records(s, d_ex_in, d_index_sorted, sc->ex_prims, n, (int)sizeof(PrimExact));
-    launch_hierarchy(s, d_codes_sorted, t);
-    launch_refit(s, t, d_sorted_boxes);
+    if (!sah) {
+      launch_hierarchy(s, d_codes_sorted, t);
+      launch_refit(s, t, d_sorted_boxes);
+    }
 
     // collapse, level by level; the root binary node 0 becomes wide node 0
     CollapseItem root{0, 0};
@@ -173,7 +195,7 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
     RT_CUDA(cudaEventSynchronize(ev1));
     float ms = 0.f;
     RT_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
-    sc->info.build_ms = ms;
+    sc->info.build_ms = ms + host_build_ms;
     RT_CUDA(cudaMemcpy(order.data(), d_index_sorted, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
     RT_CUDA(cudaGetLastError());
   }

@@ -8,6 +8,7 @@ static uint64_t g_stat_nodes = 0, g_stat_leaves = 0;
 #define RT_STAT_NODE() (++g_stat_nodes)
 #define RT_STAT_LEAF() (++g_stat_leaves)
 #include "../../real-time-ray-tracing-engine_b200/csrc/rt_flatten.h"
+#include "../../real-time-ray-tracing-engine_b200/csrc/rt_sah.h"
 
 #include <algorithm>
 #include <cstdio>
@@ -60,30 +61,43 @@ static void build_bvh(EmuScene &s) {
       double ext = centroids.hi[a] - centroids.lo[a];
       bounds[3 + a] = ext > 0 ? (float)(1.0 / ext) : 0.f;
     }
-    std::vector<uint64_t> codes(n), sorted_codes(n);
-    for (int i = 0; i < n; i++)
-      codes[i] = morton_body(boxes[i], bounds, bounds + 3);
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return codes[a] < codes[b]; });
     std::vector<BuildBox> sorted_boxes(n);
-    for (int j = 0; j < n; j++) {
-      sorted_codes[j] = codes[order[j]];
-      sorted_boxes[j] = boxes[order[j]];
-    }
     std::vector<int> left(n - 1), right(n - 1), parent(2 * n - 1, -2);
     std::vector<BuildBox> box(n - 1);
     std::vector<unsigned int> visits(n - 1, 0);
-    BinTree t{left.data(), right.data(), parent.data(), box.data(), visits.data(), n};
-    for (int i = 0; i < n - 1; i++)
-      hierarchy_body(sorted_codes.data(), t, i);
-    for (int j = 0; j < n; j++) { // k_refit
-      int node = parent[(n - 1) + j];
-      while (node >= 0) {
-        if (visits[node]++ == 0)
-          break;
-        box[node] = box_union(child_box(t, sorted_boxes.data(), left[node]), child_box(t, sorted_boxes.data(), right[node]));
-        node = parent[node];
+    if (rtsah::use_sah(n)) { // small scenes: host SAH tree (rt_sah.h), as rt_scene.cu does
+      rtsah::HostTree ht;
+      rtsah::build(boxes.data(), n, ht);
+      order = ht.order;
+      left = ht.left;
+      right = ht.right;
+      parent = ht.parent;
+      box = ht.box;
+      for (int j = 0; j < n; j++)
+        sorted_boxes[j] = boxes[order[j]];
+    } else {
+      std::vector<uint64_t> codes(n), sorted_codes(n);
+      for (int i = 0; i < n; i++)
+        codes[i] = morton_body(boxes[i], bounds, bounds + 3);
+      std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return codes[a] < codes[b]; });
+      for (int j = 0; j < n; j++) {
+        sorted_codes[j] = codes[order[j]];
+        sorted_boxes[j] = boxes[order[j]];
+      }
+      BinTree t{left.data(), right.data(), parent.data(), box.data(), visits.data(), n};
+      for (int i = 0; i < n - 1; i++)
+        hierarchy_body(sorted_codes.data(), t, i);
+      for (int j = 0; j < n; j++) { // k_refit
+        int node = parent[(n - 1) + j];
+        while (node >= 0) {
+          if (visits[node]++ == 0)
+            break;
+          box[node] = box_union(child_box(t, sorted_boxes.data(), left[node]), child_box(t, sorted_boxes.data(), right[node]));
+          node = parent[node];
+        }
       }
     }
+    BinTree t{left.data(), right.data(), parent.data(), box.data(), visits.data(), n};
     std::vector<CollapseItem> items{{0, 0}}, next;
     int wide_count = 1;
     while (!items.empty()) { // k_collapse, one level per iteration

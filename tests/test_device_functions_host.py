@@ -159,3 +159,34 @@ def test_fast_division_by_invariant_integers(emu):
         for x in xs:
             if 0 <= x < 2**31:
                 assert emu.emu_fastdiv(d, x) == x // d, (d, x)
+
+
+@pytest.mark.parametrize("name,p0", [("spheres", 11), ("final", 5), ("cornell", 0)])
+def test_both_bvh_builders_answer_alike(oracle, emu, host_scenes, monkeypatch, name, p0):
+    """Host SAH tree (rt_sah.h, small scenes) and the LBVH (rt_bvh.h): both consistent, and the FP64 traversal
+    finds the same hits in either; the SAH tree must not need more node visits than the LBVH on the bigger scenes."""
+    emu.emu_stats.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int]
+    hs = host_scenes(name, p0, 60 if name == "final" else -1)
+    cfg = hs.camera_config(64, 1, 8)
+    osc = oracle.ora_scene_create(hs.desc)
+    _, rays, _ = oracle_segments(oracle, osc, cfg, ol.ORA_RNG_PHILOX, ol.ORA_SAMPLER_POLAR, 7, 1)
+    n = len(rays)
+    hits, visits = {}, {}
+    for mode in ("lbvh", "sah"):
+        monkeypatch.setenv("RT_BVH", mode)
+        es = emu.emu_scene_create(hs.desc)
+        assert es and emu.emu_scene_check_bvh(es) == 0
+        out = (abi.rt_hit * n)()
+        a, b = C.c_uint64(), C.c_uint64()
+        emu.emu_stats(C.byref(a), C.byref(b), 1)
+        emu.emu_trace(es, rays, n, abi.RT_TRACE_FAST_F32, 7, out)
+        emu.emu_stats(C.byref(a), C.byref(b), 1)
+        visits[mode] = a.value
+        emu.emu_trace(es, rays, n, abi.RT_TRACE_EXACT_F64, 7, out)
+        hits[mode] = ol.hits_to_numpy(out)
+        emu.emu_scene_destroy(es)
+    for k in ("t", "prim", "object", "front_face"):
+        assert np.array_equal(hits["lbvh"][k], hits["sah"][k]), k
+    if name != "cornell":  # 13 primitives: either tree is two levels
+        assert visits["sah"] < visits["lbvh"], visits
+    oracle.ora_scene_destroy(osc)

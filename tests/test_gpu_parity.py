@@ -26,14 +26,16 @@ def n_surface_prims(desc):
     return desc.contents.n_spheres + desc.contents.n_quads
 
 
+@pytest.mark.parametrize("bvh", ["sah", "lbvh"])
 @pytest.mark.parametrize("name", ["spheres", "spheres_textured", "cornell", "final"])
-def test_exact_trace_equals_the_reference(ctx, scene_index, host_scenes, name):
+def test_exact_trace_equals_the_reference(ctx, scene_index, host_scenes, name, bvh, monkeypatch):
     """Rays and answers both come from the unmodified reference (golden fixtures): primary rays of one
     stratum and every segment of a small render.  FP64 parity mode must reproduce t, object and front face
-    bit for bit."""
+    bit for bit - over the host SAH tree (small scenes' default) and over the device LBVH."""
     g = load_golden(name)
     meta = scene_index[name]
     hs = host_scenes(meta["builtin"], meta["p0"], meta["p1"], meta["seed"])
+    monkeypatch.setenv("RT_BVH", bvh)  # read by rt_scene_create
     scene = engine.Scene(ctx, hs.desc)
     sets = [("primary_rays", "primary_hits_bvh0")]
     if "segment_rays" in g.files:

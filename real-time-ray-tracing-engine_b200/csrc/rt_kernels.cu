@@ -123,11 +123,20 @@ struct SmemStack {
 // path and k_accumulate sums each pixel's samples in order.
 __device__ __forceinline__ void path_ends(const PassParams &pp, float4 *__restrict__ radiance, int path, f3 rad) {
   if (pp.film_direct) {
+#if RT_FILM_RED
+    // no other path of this pass touches the pixel: three reductions give the same sums as load-add-store
+    // without waiting for the load (subnormal sums would be flushed; radiance never gets there)
+    float *f = reinterpret_cast<float *>(pp.film_direct + path);
+    atomicAdd(f + 0, rad.x);
+    atomicAdd(f + 1, rad.y);
+    atomicAdd(f + 2, rad.z);
+#else
     float4 f = pp.film_direct[path];
     f.x += rad.x;
     f.y += rad.y;
     f.z += rad.z;
     pp.film_direct[path] = f;
+#endif
   } else {
     radiance[path] = make_float4(rad.x, rad.y, rad.z, 0.f);
   }
@@ -191,6 +200,9 @@ __global__ void __launch_bounds__(RT_BLOCK)
 #endif
 #ifndef RT_TAIL_BLOCKS
 #define RT_TAIL_BLOCKS 5 // resident blocks per SM of k_tail (register budget = 65536 / (128 * RT_TAIL_BLOCKS))
+#endif
+#ifndef RT_FILM_RED
+#define RT_FILM_RED 1
 #endif
 #ifndef RT_TAIL_REFILL
 #define RT_TAIL_REFILL 8 // k_tail leaves the traversal loop to shade / refill below this many busy lanes

@@ -13,6 +13,7 @@
  *   rth_cli_parse         <- parse_cli / CLIOptions (input/CLI.cpp:4-92, input/CLI.hpp:8-51)
  *   rth_write_ppm_p3      <- the PPM P3 writer in StaticCamera::render_cpu (StaticCamera.cpp:57,94-99,
  *                            utils/ColorUtility.hpp:30-37)
+ *   rth_presenter_*       <- the SDL3 window of DynamicCamera (core/camera/DynamicCamera.cpp:62-91,196-306)
  */
 #ifndef RT_HOST_H
 #define RT_HOST_H
@@ -67,11 +68,31 @@ typedef struct rth_cli_options {
                          w/s/a/d move lookfrom and lookat by 10 units along +z/-z/-x/+x and restart the
                          accumulation, '+'/'-' change samples per pixel (DynamicCamera::handle_events,
                          core/camera/DynamicCamera.cpp:204-278), any other character = no key */
+  int headless;       /* --headless: the dynamic camera never opens a window (default: a window when SDL3 can be loaded
+                         and --frames is not given) */
+  int adaptive;       /* --adaptive: headless frames adapt the samples per frame to the frame rate as the window does */
 } rth_cli_options;
 
 /* Returns 0 on success, non-zero on a malformed command line (message in rth_last_error). */
 int rth_cli_parse(int argc, char **argv, rth_cli_options *out);
 const char *rth_cli_help(void);
+
+/* Progressive window of the dynamic camera (DynamicCamera.cpp:62-91 window + streaming RGB24 texture, :204-278 key
+ * handling, :196-200 present).  SDL3 is opened with dlopen at run time (RT_SDL3_LIB overrides the library name):
+ * rth_presenter_open returns NULL and sets rth_last_error when it is not installed. */
+typedef struct rth_presenter rth_presenter;
+typedef struct rth_input {
+  int quit;      /* ESC pressed or window closed */
+  int spp_delta; /* '=' presses minus '-' presses since the last poll */
+  int move_x;    /* D held (+1) / A held (-1) */
+  int move_z;    /* W held (+1) / S held (-1) */
+  int moved;     /* any movement key held: the accumulation restarts (even if the moves cancel) */
+} rth_input;
+rth_presenter *rth_presenter_open(int width, int height, const char *title);
+int rth_presenter_poll(rth_presenter *presenter, rth_input *out);
+/* Uploads one row-major RGB8 frame and shows it; status_line (may be NULL) goes to the window title. */
+int rth_presenter_present(rth_presenter *presenter, const uint8_t *rgb8, const char *status_line);
+void rth_presenter_close(rth_presenter *presenter);
 
 /* "P3\nW H\n255\n" followed by one "r g b\n" line per pixel. */
 int rth_write_ppm_p3(const char *path, int width, int height, const uint8_t *rgb8);

@@ -1,5 +1,5 @@
 // Command line of the `raytracer` program: the reference's flags with the reference's defaults
-// (input/CLI.cpp:4-126, input/CLI.hpp:8-27) plus --scene / --seed / --gpus / --frames.
+// (input/CLI.cpp:4-126, input/CLI.hpp:8-27) plus --scene / --seed / --gpus / --frames / --keys / --headless / --adaptive.
 #include "../../include/rt_host.h"
 
 #include <cstdio>
@@ -34,6 +34,10 @@ const char *rth_cli_help(void) {
          "  --gpus <int>               GPUs to partition the image over (default: 1)\n"
          "  --frames <int>             Dynamic camera without a window: progressive frames to render\n"
          "                             (default: one per stratum)\n"
+         "  --headless                 Dynamic camera: never open a window (default: an SDL3 window when SDL3 is\n"
+         "                             installed and --frames is not given)\n"
+         "  --adaptive                 Headless frames adapt the samples per frame to the frame rate as the\n"
+         "                             window does (> 30 FPS: twice as many, < 15 FPS: half, 1..64)\n"
          "  --keys <string>            Dynamic camera without a window: scripted key states, one character per\n"
          "                             frame (w/s/a/d move the camera by 10 units and restart the accumulation,\n"
          "                             +/- change the samples per pixel, anything else: no key)\n\n"
@@ -116,6 +120,10 @@ int rth_cli_parse(int argc, char **argv, rth_cli_options *out) {
       need_int(i, "--frames", out->frames);
     } else if (arg == "--keys") {
       need_str(i, "--keys", out->keys, sizeof out->keys);
+    } else if (arg == "--headless") {
+      out->headless = 1;
+    } else if (arg == "--adaptive") {
+      out->adaptive = 1;
     } else {
       errors += "Unknown option: " + arg + "\n";
     }

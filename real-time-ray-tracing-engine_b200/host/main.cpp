@@ -1,14 +1,16 @@
 // raytracer — the host program: the reference's CLI (src/main.cpp:133-173) in front of the B200
 // backend.  Static camera: renders the image and writes output/<file> as ASCII PPM
 // (StaticCamera::render, core/camera/StaticCamera.cpp:25-57,94-99).  Dynamic camera: the reference
-// opens an SDL3 window and adds one stratum per frame (DynamicCamera.cpp:103-194); SDL3 is not
-// available in this build, so the dynamic camera runs headless: it renders the progressive frames,
-// resolves each to RGB8 exactly as update_texture does (:280-306), reports per-frame times and writes the
+// opens an SDL3 window and adds one stratum per frame (DynamicCamera.cpp:103-194).  Here the window is opened
+// when libSDL3 can be loaded at run time (host/presenter.cpp, dlopen) and --frames is not given; otherwise the
+// dynamic camera runs headless: it renders the progressive frames, resolves each to RGB8 exactly as
+// update_texture does (:280-306), takes its key states from --keys, reports per-frame times and writes the
 // last frame.  Images are partitioned over --gpus devices by interleaved scanline tiles and gathered over
 // NVLink peer copies.  There is no CPU rendering path: without a CUDA device the program fails.
 #include "../../include/rt_b200.h"
 #include "../../include/rt_host.h"
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -106,48 +108,103 @@ int main(int argc, char **argv) {
     }
     std::fprintf(stderr, "[INFO] wrote %s\n", path.c_str());
   } else {
-    int frames = opt.frames > 0 ? opt.frames : sqrt_spp * sqrt_spp;
-    int taken = 0, samples = opt.samples, moves = 0;
+    // Dynamic camera (DynamicCamera.cpp:103-200).  One displayed frame = handle input, add strata to the
+    // accumulation unless it has converged, resolve to RGB8, present.  With a window the key states come from
+    // SDL3 and the loop runs until ESC; headless they come from --keys and the loop runs --frames frames.
+    rth_presenter *window = nullptr;
+    if (!opt.headless && opt.frames <= 0) {
+      window = rth_presenter_open(W, H, "Dynamic Camera");
+      if (!window)
+        std::fprintf(stderr, "[WARN] %s; rendering headless\n", rth_last_error());
+    }
+    const bool adaptive = window != nullptr || opt.adaptive;
+    int frames = window ? -1 : (opt.frames > 0 ? opt.frames : sqrt_spp * sqrt_spp);
+    int taken = 0, samples = opt.samples, moves = 0, shown = 0;
+    // Adaptive quality: the reference doubles / halves its tile size (16..64 px) once a second when the frame
+    // rate is above 30 / below 15 FPS (DynamicCamera.cpp:180-193).  A frame is one wavefront pass here, so the
+    // knob is the number of strata added per displayed frame (1..64) with the same thresholds.
+    int strata_per_frame = 1, fps_frames = 0;
+    double fps = 0.0, fps_t0 = now_ms();
     const size_t n_keys = std::strlen(opt.keys);
-    for (int f = 0; f < frames; f++) {
+    for (int f = 0; frames < 0 || f < frames; f++) {
       double f0 = now_ms();
-      // scripted key state of this frame: DynamicCamera::handle_events (DynamicCamera.cpp:204-278)
-      char key = size_t(f) < n_keys ? opt.keys[f] : '.';
-      double dx = key == 'd' ? 10.0 : (key == 'a' ? -10.0 : 0.0), dz = key == 'w' ? 10.0 : (key == 's' ? -10.0 : 0.0);
-      if (key == '+')
-        samples++;
-      if (key == '-' && samples > 1)
-        samples--;
+      rth_input in{};
+      if (window) {
+        rth_presenter_poll(window, &in);
+        if (in.quit)
+          break;
+      } else { // scripted key state of this frame
+        char key = size_t(f) < n_keys ? opt.keys[f] : '.';
+        in.move_x = key == 'd' ? 1 : (key == 'a' ? -1 : 0);
+        in.move_z = key == 'w' ? 1 : (key == 's' ? -1 : 0);
+        in.moved = in.move_x != 0 || in.move_z != 0;
+        in.spp_delta = key == '+' ? 1 : (key == '-' ? -1 : 0);
+      }
+      // DynamicCamera::handle_events (:204-278)
+      samples = std::max(1, samples + in.spp_delta);
       sqrt_spp = std::max(1, int(std::sqrt(double(samples))));
-      if (dx != 0.0 || dz != 0.0) { // camera moved: restart the accumulation and recompute the camera
-        cfg.lookfrom[0] += dx, cfg.lookat[0] += dx;
-        cfg.lookfrom[2] += dz, cfg.lookat[2] += dz;
+      const int total_strata = sqrt_spp * sqrt_spp;
+      if (in.moved) { // camera moved: restart the accumulation and recompute the camera
+        const double step = 10.0;
+        cfg.lookfrom[0] += step * in.move_x, cfg.lookat[0] += step * in.move_x;
+        cfg.lookfrom[2] += step * in.move_z, cfg.lookat[2] += step * in.move_z;
         CHECK(rt_camera_init(&cfg, &cam));
         for (int g = 0; g < n_gpus; g++)
           CHECK(rt_film_clear(film[g]));
         taken = 0;
         moves++;
       }
-      int s = taken % (sqrt_spp * sqrt_spp);
-      for (int g = 0; g < n_gpus; g++)
-        CHECK(rt_render_accumulate(scene[g], &cam, film[g], s % sqrt_spp, s / sqrt_spp, sqrt_spp, opt.depth,
-                                   opt.seed + (uint64_t)(taken / (sqrt_spp * sqrt_spp))));
-      taken++;
+      // the window stops sampling at convergence (:115); headless frames keep refining with a new seed per round
+      const bool converged = window != nullptr && taken >= total_strata;
+      if (!converged) {
+        int s = taken % total_strata;
+        int n = adaptive ? std::min(strata_per_frame, total_strata - s) : 1;
+        uint64_t seed = opt.seed + (uint64_t)(taken / total_strata);
+        for (int g = 0; g < n_gpus; g++) {
+          if (n == 1)
+            CHECK(rt_render_accumulate(scene[g], &cam, film[g], s % sqrt_spp, s / sqrt_spp, sqrt_spp, opt.depth, seed));
+          else
+            CHECK(rt_render_strata(scene[g], &cam, film[g], s, n, sqrt_spp, opt.depth, seed));
+        }
+        taken += n;
+      }
       double scale = 1.0 / std::max(1, taken); // DynamicCamera.cpp:285
       if (n_gpus == 1) {
         CHECK(rt_film_resolve_rgb8(film[0], scale, rgb8.data()));
       } else {
         CHECK(rt_film_gather_p2p_rgb8(film.data(), n_gpus, scale, rgb8.data()));
       }
+      shown++;
+      fps_frames++;
       double f1 = now_ms();
-      if (f < 5 || f == frames - 1)
+      if (f1 - fps_t0 >= 1000.0) { // once a second (:180-193)
+        fps = 1000.0 * fps_frames / (f1 - fps_t0);
+        fps_frames = 0;
+        fps_t0 = f1;
+        if (adaptive && !converged && fps > 30.0 && strata_per_frame < 64)
+          strata_per_frame *= 2;
+        else if (adaptive && !converged && fps < 15.0 && strata_per_frame > 1)
+          strata_per_frame /= 2;
+      }
+      if (window) {
+        char line[160]; // draw_fps (:308-348) as the window title
+        std::snprintf(line, sizeof line, "Dynamic Camera - %.1f fps, %d/%d samples%s", fps, std::min(taken, total_strata),
+                      total_strata, converged ? " - converged" : "");
+        if (rth_presenter_present(window, rgb8.data(), line) != 0) {
+          std::fprintf(stderr, "[ERROR] %s\n", rth_last_error());
+          break;
+        }
+      } else if (f < 5 || f == frames - 1) {
         std::fprintf(stderr, "[INFO] frame %d: %.3f ms (%.1f FPS)\n", f, f1 - f0, 1000.0 / (f1 - f0));
+      }
     }
+    if (window)
+      rth_presenter_close(window);
     mkdir("output", 0755);
     std::string path = std::string("output/") + opt.output;
     rth_write_ppm_p3(path.c_str(), W, H, rgb8.data());
     std::fprintf(stderr, "[INFO] %d progressive frames in %.1f ms (%d camera move(s), %d sample(s) in the last "
-                         "accumulation); last frame written to %s\n", frames, now_ms() - t0, moves, taken, path.c_str());
+                         "accumulation); last frame written to %s\n", shown, now_ms() - t0, moves, taken, path.c_str());
   }
   for (int g = 0; g < n_gpus; g++) {
     rt_film_destroy(film[g]);

@@ -113,3 +113,30 @@ def test_multi_gpu_flag_gives_the_same_bytes(tmp_path):
     d = run(["--camera", "dynamic", "--gpus", str(n), "--output", "dyn.ppm"] + args, tmp_path)
     assert d.returncode == 0, d.stderr
     assert np.array_equal(read_ppm(tmp_path / "output" / "dyn.ppm"), read_ppm(tmp_path / "output" / "one.ppm"))
+
+
+def test_window_mode_shows_the_frames_the_headless_mode_writes(tmp_path):
+    """Dynamic camera with a window (a test double of libSDL3, tests/emu/fake_sdl3.c): keys come from SDL, every
+    frame goes through SDL_UpdateTexture, ESC ends the loop.  Same key script headless -> same last frame."""
+    fake = os.path.join(REPO, "tests", "emu", "libfake_sdl3.so")
+    subprocess.check_call(["make", "-s", "-C", os.path.join(REPO, "tests", "emu"), "libfake_sdl3.so"])
+    env = dict(os.environ, RT_SDL3_LIB=fake, FAKE_SDL_LOG=str(tmp_path / "sdl.log"), FAKE_SDL_FRAME=str(tmp_path / "frame.bin"),
+               FAKE_SDL_KEYS="..d..e")
+    args = ["--camera", "dynamic", "--scene", "cornell", "--width", "64", "--samples", "16", "--depth", "5"]
+    w = subprocess.run([EXE] + args + ["--output", "win.ppm"], cwd=tmp_path, capture_output=True, text=True, timeout=300, env=env)
+    assert w.returncode == 0, w.stderr
+    assert "5 progressive frames" in w.stderr and "1 camera move(s), 3 sample(s)" in w.stderr
+    h = run(args + ["--frames", "5", "--keys", "..d..", "--output", "headless.ppm"], tmp_path)
+    assert h.returncode == 0, h.stderr
+    want = read_ppm(tmp_path / "output" / "headless.ppm")
+    assert np.array_equal(read_ppm(tmp_path / "output" / "win.ppm"), want)
+    shown = np.fromfile(tmp_path / "frame.bin", dtype=np.uint8).reshape(want.shape)
+    assert np.array_equal(shown, want)  # what SDL_UpdateTexture received last
+    calls = (tmp_path / "sdl.log").read_text().splitlines()
+    assert sum(c.startswith("SDL_UpdateTexture") for c in calls) == 5 and calls[-1] == "SDL_Quit"
+    assert any("3/16 samples" in c for c in calls if c.startswith("SDL_SetWindowTitle"))
+    # without SDL3 the same command falls back to the headless loop and says so
+    env2 = dict(os.environ, RT_SDL3_LIB=str(tmp_path / "missing.so"))
+    f = subprocess.run([EXE] + ["--camera", "dynamic", "--scene", "cornell", "--width", "32", "--samples", "4", "--depth", "3"],
+                       cwd=tmp_path, capture_output=True, text=True, timeout=300, env=env2)
+    assert f.returncode == 0 and "rendering headless" in f.stderr and "4 progressive frames" in f.stderr

@@ -123,7 +123,7 @@ class rth_cli_options(C.Structure):
     _fields_ = [("width", C.c_int), ("samples", C.c_int), ("depth", C.c_int), ("camera_dynamic", C.c_int),
                 ("use_parallelism", C.c_int), ("use_bvh", C.c_int), ("use_gpu", C.c_int), ("debug", C.c_int),
                 ("help", C.c_int), ("output", C.c_char * 256), ("scene", C.c_char * 256), ("seed", C.c_uint64),
-                ("gpus", C.c_int), ("frames", C.c_int), ("keys", C.c_char * 256)]
+                ("gpus", C.c_int), ("frames", C.c_int), ("keys", C.c_char * 256), ("headless", C.c_int), ("adaptive", C.c_int)]
 
 
 def parse_cli(args):

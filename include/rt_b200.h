@@ -267,6 +267,14 @@ typedef struct rt_scene_info {
 } rt_scene_info;
 int rt_scene_get_info(rt_scene *scene, rt_scene_info *out);
 
+/* Animated scenes (absent from the reference, whose only motion is the per-ray shutter blend of a sphere's two
+ * centres, Sphere.cpp:101-104): replaces spheres [first_sphere, first_sphere + n_spheres) of the description the
+ * scene was created from - centres, radius, material, instance chain - and refits the BVH bottom-up.  The tree
+ * keeps its topology: exact for any motion, but its quality degrades as objects travel far from where they were
+ * built; rt_scene_create rebuilds (<= 2 ms for 10^6 primitives).  Boundary spheres of media cannot be updated
+ * (RT_ERR_UNSUPPORTED).  Ordered after earlier work on the context's stream; returns when the update is done. */
+int rt_scene_update_spheres(rt_scene *scene, int first_sphere, int n_spheres, const rt_sphere *spheres);
+
 /* ----------------------------------------------------------------------------------------------
  * Closest-hit parity hook
  * -------------------------------------------------------------------------------------------- */

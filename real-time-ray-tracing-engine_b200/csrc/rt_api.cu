@@ -340,6 +340,13 @@ void rt_scene_destroy(rt_scene *scene) {
   delete scene;
 }
 
+int rt_scene_update_spheres(rt_scene *scene, int first_sphere, int n_spheres, const rt_sphere *spheres) {
+  if (!scene)
+    return invalid("rt_scene_update_spheres: null scene");
+  RT_CUDA(cudaSetDevice(scene->ctx->device));
+  return rt_scene_update_spheres_impl(scene, first_sphere, n_spheres, spheres);
+}
+
 int rt_scene_get_info(rt_scene *scene, rt_scene_info *out) {
   if (!scene || !out)
     return invalid("rt_scene_get_info: null argument");

@@ -134,6 +134,7 @@ RT_HD BuildBox child_box(const BinTree &t, const BuildBox *leaf_boxes, int ref) 
 // Collapse work item: binary node `bin` becomes wide node `wide`.
 struct CollapseItem {
   int bin, wide;
+  int up; // parent wide node * 4 + slot in it, -1 for the root: stored in the node's spare row for refits
 };
 
 // Returns the number of internal children; their work items are written to next[*] by the caller
@@ -164,7 +165,7 @@ RT_HD int collapse_gather(const BinTree &t, const BuildBox *leaf_boxes, int bin,
 }
 
 RT_HD void collapse_write(const BinTree &t, const BuildBox *leaf_boxes, float4 *nodes, int wide, const int child[4],
-                          int n_child, const int wide_ref[4]) {
+                          int n_child, const int wide_ref[4], int up) {
   float lo[3][4], hi[3][4];
   int ref[4];
   for (int k = 0; k < 4; k++) {
@@ -191,5 +192,47 @@ RT_HD void collapse_write(const BinTree &t, const BuildBox *leaf_boxes, float4 *
   n[4] = make_float4(lo[2][0], lo[2][1], lo[2][2], lo[2][3]);
   n[5] = make_float4(hi[2][0], hi[2][1], hi[2][2], hi[2][3]);
   n[6] = make_float4(i2f(ref[0]), i2f(ref[1]), i2f(ref[2]), i2f(ref[3]));
-  n[7] = make_float4(0.f, 0.f, 0.f, 0.f);
+  n[7] = make_float4(i2f(up), 0.f, 0.f, 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Refit of the finished BVH4 (animated scenes, rt_scene_update_spheres): every node stores its children's
+// boxes, so a node's own box is the union of its used slots and lives in its parent's slot; row 7 of a node
+// holds `parent * 4 + slot` (-1 at the root).  Leaves climb, the last child to arrive at a node moves on.
+// ---------------------------------------------------------------------------------------------------
+RT_HD void node_set_slot_box(float4 *nodes, int node, int slot, const BuildBox &b) {
+  float *n = reinterpret_cast<float *>(nodes + (size_t)node * RT_NODE_F4);
+  for (int a = 0; a < 3; a++) {
+    n[(2 * a) * 4 + slot] = b.lo[a];
+    n[(2 * a + 1) * 4 + slot] = b.hi[a];
+  }
+}
+RT_HD int node_child_count(const float4 *nodes, int node) {
+  const float4 cr = nodes[(size_t)node * RT_NODE_F4 + 6];
+  return (f2i(cr.x) != RT_EMPTY) + (f2i(cr.y) != RT_EMPTY) + (f2i(cr.z) != RT_EMPTY) + (f2i(cr.w) != RT_EMPTY);
+}
+// rows[0..5] = the node's six box rows as the caller read them (the device reads them past L1)
+RT_HD BuildBox node_bounds(const float4 rows[6], const float4 cr) {
+  const int ref[4] = {f2i(cr.x), f2i(cr.y), f2i(cr.z), f2i(cr.w)};
+  BuildBox b;
+  for (int a = 0; a < 3; a++) {
+    const float lo[4] = {rows[2 * a].x, rows[2 * a].y, rows[2 * a].z, rows[2 * a].w};
+    const float hi[4] = {rows[2 * a + 1].x, rows[2 * a + 1].y, rows[2 * a + 1].z, rows[2 * a + 1].w};
+    b.lo[a] = RT_INF_F;
+    b.hi[a] = -RT_INF_F;
+    for (int k = 0; k < 4; k++)
+      if (ref[k] != RT_EMPTY) {
+        b.lo[a] = fminf(b.lo[a], lo[k]);
+        b.hi[a] = fmaxf(b.hi[a], hi[k]);
+      }
+  }
+  return b;
+}
+// leaf -> (node * 4 + slot) of the slot that references it; thread `node` fills the entries of its leaf children
+RT_HD void leaf_links_body(const float4 *nodes, int node, int *leaf_up) {
+  const float4 cr = nodes[(size_t)node * RT_NODE_F4 + 6];
+  const int ref[4] = {f2i(cr.x), f2i(cr.y), f2i(cr.z), f2i(cr.w)};
+  for (int k = 0; k < 4; k++)
+    if (ref[k] < 0)
+      leaf_up[~ref[k]] = node * 4 + k;
 }

@@ -131,6 +131,23 @@ struct Flat {
   std::vector<BoxD> boxes;
 };
 
+// Spheres carry a copy of their material: the header in [2] and, when one colour is all the material needs
+// (metal, or a solid texture), that colour in [2].w, [1].w, [3].x - shading a sphere hit then takes one dependent
+// fetch (the primitive record) instead of three (record -> header -> colour).  `rec` = the 4 float4 of a record.
+inline void embed_sphere_material(float4 *rec, const std::vector<float4> &mats) {
+  uint32_t typemat = (uint32_t)f2i(rec[3].y);
+  size_t m = (size_t)(typemat & 0x0fffffffu) * RT_MAT_F4;
+  if ((typemat >> 28) != RT_PT_SPHERE || m + 1 >= mats.size())
+    return;
+  float4 m0 = mats[m], a = mats[m + 1];
+  if (f2i(m0.x) == RT_MAT_METAL || f2i(m0.y) == RT_DTEX_SOLID) {
+    m0.w = a.x;
+    rec[1].w = a.y;
+    rec[3].x = a.z;
+  }
+  rec[2] = m0;
+}
+
 inline void push_sphere(const Baker &bk, const rt_sphere &s, int id, int material, std::vector<float4> &fast,
                  std::vector<PrimExact> &exact, BoxD &box) {
   D3 c0 = bk.point(s.xform, d3(s.center0));
@@ -366,22 +383,8 @@ inline int flatten(const rt_scene_desc *d, Flat &f) {
     f.mats.push_back(b);
   }
 
-  // spheres carry a copy of their material: the header in [2] and, when one colour is all the material
-  // needs (metal, or a solid texture), that colour in [2].w, [1].w, [3].x - shading a sphere hit then takes
-  // one dependent fetch (the primitive record) instead of three (record -> header -> colour)
-  for (size_t r = 0; r + RT_PRIM_F4 <= f.prims.size(); r += RT_PRIM_F4) {
-    uint32_t typemat = (uint32_t)f2i(f.prims[r + 3].y);
-    if ((typemat >> 28) != RT_PT_SPHERE || d->n_materials == 0)
-      continue;
-    size_t m = (size_t)(typemat & 0x0fffffffu) * RT_MAT_F4;
-    float4 m0 = f.mats[m], a = f.mats[m + 1];
-    if (f2i(m0.x) == RT_MAT_METAL || f2i(m0.y) == RT_DTEX_SOLID) {
-      m0.w = a.x;
-      f.prims[r + 1].w = a.y;
-      f.prims[r + 3].x = a.z;
-    }
-    f.prims[r + 2] = m0;
-  }
+  for (size_t r = 0; r + RT_PRIM_F4 <= f.prims.size(); r += RT_PRIM_F4)
+    embed_sphere_material(&f.prims[r], f.mats);
 
   for (int i = 0; i < d->n_perlins; i++) {
     const rt_perlin &p = d->perlins[i];

@@ -77,6 +77,15 @@ struct rt_scene {
   int *leaf_object = nullptr, *leaf_id = nullptr; // per leaf-order primitive: object / unified id
   rt_scene_info info{};
   int n_leaf = 0;
+  // kept for rt_scene_update_spheres (animated scenes): the instance chains and materials the records are
+  // baked with, the current spheres, where each sphere's leaf is, and the refit links (made at the first update)
+  std::vector<rt_xform> h_xforms;
+  std::vector<rt_xform_op> h_xform_ops;
+  std::vector<rt_sphere> h_spheres;
+  std::vector<int> sphere_leaf; // -1: boundary sphere of a medium (not a leaf of its own)
+  std::vector<float4> h_mats;
+  int *leaf_up = nullptr;            // device: per leaf, parent node * 4 + slot
+  unsigned int *arrivals = nullptr;  // device: per node refit counter
 };
 
 struct rt_film {
@@ -101,6 +110,7 @@ int rt_cuda_fail(cudaError_t e, const char *what);
 // ---- scene construction (rt_scene.cu) ----
 int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *scene);
 void rt_scene_release(rt_scene *scene);
+int rt_scene_update_spheres_impl(rt_scene *scene, int first, int count, const rt_sphere *spheres);
 
 // ---- kernel launch wrappers (rt_kernels.cu); all asynchronous on `stream` ----
 struct LaunchShape {
@@ -125,6 +135,10 @@ void launch_extend(const rt_context *ctx, const DScene &sc, const PassParams &pp
 void launch_shade(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int bounce);
 void launch_tail(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int first_bounce,
                  int end_bounce, int buffer);
+void launch_leaf_links(cudaStream_t s, const float4 *nodes, int n_nodes, int *leaf_up);
+void launch_update_leaves(cudaStream_t s, const float4 *records, const PrimExact *exact, const BuildBox *boxes,
+                          const int *leaf, int count, const int *leaf_up, float4 *prims, PrimExact *ex_prims, float4 *nodes);
+void launch_refit_wide(cudaStream_t s, float4 *nodes, const int *leaf_up, unsigned int *arrivals, int n_leaf);
 void launch_accumulate(const rt_context *ctx, const PassParams &pp, WaveBuffers &w, float4 *film);
 void launch_resolve_rgb8(cudaStream_t s, const float4 *film, int64_t n, double scale, uint8_t *out);
 void launch_resolve_rgb(cudaStream_t s, const float4 *film, int64_t n, double scale, float *out);

@@ -764,10 +764,60 @@ __global__ void k_collapse(BinTree t, const BuildBox *__restrict__ leaf_boxes, f
         wide_ref[k] = first_wide + m;
         next[first_slot + m].bin = child[k];
         next[first_slot + m].wide = first_wide + m;
+        next[first_slot + m].up = it.wide * 4 + k;
         m++;
       }
   }
-  collapse_write(t, leaf_boxes, nodes, it.wide, child, n_child, wide_ref);
+  collapse_write(t, leaf_boxes, nodes, it.wide, child, n_child, wide_ref, it.up);
+}
+
+// ---- refit of the BVH4 after primitive updates (rt_scene_update_spheres) ----
+__global__ void k_leaf_links(const float4 *__restrict__ nodes, int n_nodes, int *__restrict__ leaf_up) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_nodes)
+    leaf_links_body(nodes, i, leaf_up);
+}
+
+// Scatters `count` updated records to their leaves and writes each new leaf box into its parent's slot.
+__global__ void k_update_leaves(const float4 *__restrict__ records, const PrimExact *__restrict__ exact,
+                                const BuildBox *__restrict__ boxes, const int *__restrict__ leaf, int count,
+                                const int *__restrict__ leaf_up, float4 *__restrict__ prims,
+                                PrimExact *__restrict__ ex_prims, float4 *__restrict__ nodes) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count)
+    return;
+  int j = leaf[i];
+  for (int k = 0; k < RT_PRIM_F4; k++)
+    prims[(size_t)j * RT_PRIM_F4 + k] = records[(size_t)i * RT_PRIM_F4 + k];
+  ex_prims[j] = exact[i];
+  int up = leaf_up[j];
+  node_set_slot_box(nodes, up >> 2, up & 3, boxes[i]);
+}
+
+// One thread per leaf climbs towards the root; at every node the last child to arrive recomputes the node's
+// box from its slots and stores it in the parent's slot (every node is completed exactly once).
+__global__ void k_refit_wide(float4 *nodes, const int *__restrict__ leaf_up, unsigned int *arrivals, int n_leaf) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_leaf)
+    return;
+  int node = leaf_up[j] >> 2;
+  for (;;) {
+    __threadfence(); // the slot this thread (or k_update_leaves) wrote is visible before the arrival is counted
+    const float4 *n = nodes + (size_t)node * RT_NODE_F4;
+    const float4 cr = __ldcg(n + 6);
+    const int n_children = (f2i(cr.x) != RT_EMPTY) + (f2i(cr.y) != RT_EMPTY) + (f2i(cr.z) != RT_EMPTY) + (f2i(cr.w) != RT_EMPTY);
+    if (atomicAdd(&arrivals[node], 1u) + 1u < (unsigned int)n_children)
+      return;
+    __threadfence();
+    int up = f2i(__ldcg(n + 7).x);
+    if (up < 0)
+      return;
+    float4 rows[6];
+    for (int r = 0; r < 6; r++)
+      rows[r] = __ldcg(n + r);
+    node_set_slot_box(nodes, up >> 2, up & 3, node_bounds(rows, cr));
+    node = up >> 2;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -778,6 +828,20 @@ static inline int ceil_div(long long a, int b) { return (int)((a + b - 1) / b); 
 void launch_morton(cudaStream_t s, const BuildBox *boxes, int n, const float *scene_lo, const float *scene_inv,
                    uint64_t *codes, uint32_t *index) {
   k_morton<<<ceil_div(n, 256), 256, 0, s>>>(boxes, n, scene_lo, scene_inv, codes, index);
+}
+
+void launch_leaf_links(cudaStream_t s, const float4 *nodes, int n_nodes, int *leaf_up) {
+  if (n_nodes > 0)
+    k_leaf_links<<<ceil_div(n_nodes, 256), 256, 0, s>>>(nodes, n_nodes, leaf_up);
+}
+void launch_update_leaves(cudaStream_t s, const float4 *records, const PrimExact *exact, const BuildBox *boxes,
+                          const int *leaf, int count, const int *leaf_up, float4 *prims, PrimExact *ex_prims, float4 *nodes) {
+  if (count > 0)
+    k_update_leaves<<<ceil_div(count, 128), 128, 0, s>>>(records, exact, boxes, leaf, count, leaf_up, prims, ex_prims, nodes);
+}
+void launch_refit_wide(cudaStream_t s, float4 *nodes, const int *leaf_up, unsigned int *arrivals, int n_leaf) {
+  if (n_leaf > 0)
+    k_refit_wide<<<ceil_div(n_leaf, 256), 256, 0, s>>>(nodes, leaf_up, arrivals, n_leaf);
 }
 
 int sort_pairs(cudaStream_t s, uint64_t *keys_in, uint64_t *keys_out, uint32_t *vals_in, uint32_t *vals_out, int n) {

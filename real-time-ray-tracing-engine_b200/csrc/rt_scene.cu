@@ -95,7 +95,7 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
       node[2 * a + 1] = make_float4(n ? boxes[0].hi[a] : -inf, -inf, -inf, -inf);
     }
     node[6] = make_float4(ibits(n ? ~0 : RT_EMPTY), ibits(RT_EMPTY), ibits(RT_EMPTY), ibits(RT_EMPTY));
-    node[7] = make_float4(0.f, 0.f, 0.f, 0.f);
+    node[7] = make_float4(ibits(-1), 0.f, 0.f, 0.f); // the root has no parent slot
     RT_CUDA(cudaMemcpy(sc->nodes, node.data(), sizeof(float4) * RT_NODE_F4, cudaMemcpyHostToDevice));
     if (n) {
       RT_CUDA(cudaMemcpy(sc->prims, f.prims.data(), sizeof(float4) * RT_PRIM_F4, cudaMemcpyHostToDevice));
@@ -176,7 +176,7 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
     }
 
     // collapse, level by level; the root binary node 0 becomes wide node 0
-    CollapseItem root{0, 0};
+    CollapseItem root{0, 0, -1};
     int counters[2] = {0, 1};
     RT_CUDA(cudaMemcpyAsync(d_items[0], &root, sizeof root, cudaMemcpyHostToDevice, s));
     RT_CUDA(cudaMemcpyAsync(d_counters, counters, sizeof counters, cudaMemcpyHostToDevice, s));
@@ -211,6 +211,22 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
   RT_CUDA(cudaMemcpy(sc->leaf_object, leaf_object.data(), sizeof(int) * leaf_object.size(), cudaMemcpyHostToDevice));
   RT_CUDA(cudaMemcpy(sc->leaf_id, leaf_id.data(), sizeof(int) * leaf_id.size(), cudaMemcpyHostToDevice));
 
+  // kept on the host for rt_scene_update_spheres
+  sc->h_xforms.assign(desc->xforms, desc->xforms + desc->n_xforms);
+  sc->h_xform_ops.assign(desc->xform_ops, desc->xform_ops + desc->n_xform_ops);
+  sc->h_spheres.assign(desc->spheres, desc->spheres + desc->n_spheres);
+  sc->h_mats = f.mats;
+  {
+    std::vector<int> leaf_of_record(std::max(n, 1), -1);
+    for (int j = 0; j < n; j++)
+      leaf_of_record[order[j]] = j;
+    sc->sphere_leaf.assign(desc->n_spheres, -1);
+    int record = 0; // surface spheres are the first records, in description order (rt_flatten.h)
+    for (int i = 0; i < desc->n_spheres; i++)
+      if (!(desc->spheres[i].flags & RT_PRIM_BOUNDARY))
+        sc->sphere_leaf[i] = leaf_of_record[record++];
+  }
+
   sc->d.nodes = sc->nodes;
   sc->d.prims = sc->prims;
   sc->d.bprims = sc->bprims;
@@ -241,7 +257,76 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
   return RT_OK;
 }
 
+// rt_scene_update_spheres: re-bakes the given spheres (instance chains, material copy, FP64 parity record, box),
+// scatters them to their leaves and refits the BVH4 bottom-up.  The tree keeps its topology.
+int rt_scene_update_spheres_impl(rt_scene *sc, int first, int count, const rt_sphere *spheres) {
+  const int n_spheres = (int)sc->h_spheres.size();
+  if (count == 0)
+    return RT_OK;
+  if (!spheres || first < 0 || count < 0 || first > n_spheres - count) {
+    rt_set_error("rt_scene_update_spheres: sphere range out of bounds");
+    return RT_ERR_INVALID;
+  }
+  rt_scene_desc d{};
+  d.xforms = sc->h_xforms.data();
+  d.n_xforms = (int)sc->h_xforms.size();
+  d.xform_ops = sc->h_xform_ops.data();
+  d.n_xform_ops = (int)sc->h_xform_ops.size();
+  Baker bk{&d};
+  const int n_materials = (int)(sc->h_mats.size() / RT_MAT_F4);
+  std::vector<float4> records;
+  std::vector<PrimExact> exact;
+  std::vector<BuildBox> boxes;
+  std::vector<int> leaves;
+  for (int k = 0; k < count; k++) {
+    const rt_sphere &s = spheres[k];
+    const int i = first + k;
+    if (sc->sphere_leaf[i] < 0 || (s.flags & RT_PRIM_BOUNDARY)) {
+      rt_set_error("rt_scene_update_spheres: boundary spheres of media cannot be updated");
+      return RT_ERR_UNSUPPORTED;
+    }
+    if (s.xform < -1 || s.xform >= d.n_xforms || s.material < 0 || s.material >= n_materials) {
+      rt_set_error("rt_scene_update_spheres: instance chain or material index out of range");
+      return RT_ERR_INVALID;
+    }
+    BoxD box;
+    push_sphere(bk, s, i, s.material, records, exact, box);
+    embed_sphere_material(&records[records.size() - RT_PRIM_F4], sc->h_mats);
+    boxes.push_back(to_build_box(box));
+    leaves.push_back(sc->sphere_leaf[i]);
+  }
+  cudaStream_t st = sc->ctx->stream;
+  const int n_nodes = (int)sc->info.n_nodes;
+  if (!sc->leaf_up) { // first update: where every leaf hangs, and the refit counters
+    RT_CUDA(cudaMalloc((void **)&sc->leaf_up, sizeof(int) * std::max(sc->n_leaf, 1)));
+    RT_CUDA(cudaMalloc((void **)&sc->arrivals, sizeof(unsigned int) * std::max(n_nodes, 1)));
+    launch_leaf_links(st, sc->nodes, n_nodes, sc->leaf_up);
+  }
+  Scratch scratch;
+  float4 *d_records = nullptr;
+  PrimExact *d_exact = nullptr;
+  BuildBox *d_boxes = nullptr;
+  int *d_leaves = nullptr;
+  RT_CUDA(scratch.alloc(&d_records, records.size()));
+  RT_CUDA(scratch.alloc(&d_exact, exact.size()));
+  RT_CUDA(scratch.alloc(&d_boxes, boxes.size()));
+  RT_CUDA(scratch.alloc(&d_leaves, leaves.size()));
+  RT_CUDA(cudaMemcpyAsync(d_records, records.data(), sizeof(float4) * records.size(), cudaMemcpyHostToDevice, st));
+  RT_CUDA(cudaMemcpyAsync(d_exact, exact.data(), sizeof(PrimExact) * exact.size(), cudaMemcpyHostToDevice, st));
+  RT_CUDA(cudaMemcpyAsync(d_boxes, boxes.data(), sizeof(BuildBox) * boxes.size(), cudaMemcpyHostToDevice, st));
+  RT_CUDA(cudaMemcpyAsync(d_leaves, leaves.data(), sizeof(int) * leaves.size(), cudaMemcpyHostToDevice, st));
+  RT_CUDA(cudaMemsetAsync(sc->arrivals, 0, sizeof(unsigned int) * std::max(n_nodes, 1), st));
+  launch_update_leaves(st, d_records, d_exact, d_boxes, d_leaves, count, sc->leaf_up, sc->prims, sc->ex_prims, sc->nodes);
+  launch_refit_wide(st, sc->nodes, sc->leaf_up, sc->arrivals, sc->n_leaf);
+  RT_CUDA(cudaStreamSynchronize(st)); // the staging buffers go out of scope
+  RT_CUDA(cudaGetLastError());
+  std::copy(spheres, spheres + count, sc->h_spheres.begin() + first);
+  return RT_OK;
+}
+
 void rt_scene_release(rt_scene *sc) {
+  cudaFree(sc->leaf_up);
+  cudaFree(sc->arrivals);
   cudaFree(sc->nodes);
   cudaFree(sc->prims);
   cudaFree(sc->bprims);

@@ -68,6 +68,11 @@ class Scene:
         abi.check(self.lib, self.lib.rt_scene_get_info(self._h, C.byref(i)), "rt_scene_get_info")
         return i
 
+    def update_spheres(self, first, spheres):
+        """Animated scenes: replace spheres [first, first + len(spheres)) and refit the BVH.
+        spheres: ctypes array of rt_sphere."""
+        abi.check(self.lib, self.lib.rt_scene_update_spheres(self._h, first, len(spheres), spheres), "rt_scene_update_spheres")
+
     def trace(self, rays, mode=abi.RT_TRACE_EXACT_F64, seed=0):
         """rays: ctypes array of rt_ray.  Returns a ctypes array of rt_hit."""
         n = len(rays)

@@ -27,6 +27,8 @@ struct EmuScene {
   DScene d{};
   ExactScene ex{};
   int n_wide = 0;
+  const rt_scene_desc *desc = nullptr; // caller-owned, alive as long as the scene (tests)
+  std::vector<int> sphere_leaf;
 };
 
 // The build stages of rt_scene.cu, one serial loop per kernel.
@@ -53,6 +55,7 @@ static void build_bvh(EmuScene &s) {
       s.nodes[2 * a + 1] = make_float4(n ? boxes[0].hi[a] : -inf, -inf, -inf, -inf);
     }
     s.nodes[6] = make_float4(ibits(n ? ~0 : RT_EMPTY), ibits(RT_EMPTY), ibits(RT_EMPTY), ibits(RT_EMPTY));
+    s.nodes[7] = make_float4(ibits(-1), 0.f, 0.f, 0.f);
     s.n_wide = 1;
   } else {
     float bounds[6];
@@ -98,7 +101,7 @@ static void build_bvh(EmuScene &s) {
       }
     }
     BinTree t{left.data(), right.data(), parent.data(), box.data(), visits.data(), n};
-    std::vector<CollapseItem> items{{0, 0}}, next;
+    std::vector<CollapseItem> items{{0, 0, -1}}, next;
     int wide_count = 1;
     while (!items.empty()) { // k_collapse, one level per iteration
       next.clear();
@@ -109,13 +112,23 @@ static void build_bvh(EmuScene &s) {
         for (int k = 0; k < n_child; k++)
           if (child[k] >= 0) {
             wide_ref[k] = wide_count++;
-            next.push_back({child[k], wide_ref[k]});
+            next.push_back({child[k], wide_ref[k], it.wide * 4 + k});
           }
-        collapse_write(t, sorted_boxes.data(), s.nodes.data(), it.wide, child, n_child, wide_ref);
+        collapse_write(t, sorted_boxes.data(), s.nodes.data(), it.wide, child, n_child, wide_ref, it.up);
       }
       items.swap(next);
     }
     s.n_wide = wide_count;
+  }
+  { // rt_scene.cu: where each surface sphere of the description ended up
+    std::vector<int> leaf_of_record(std::max(n, 1), -1);
+    for (int j = 0; j < n; j++)
+      leaf_of_record[order[j]] = j;
+    s.sphere_leaf.assign(s.desc->n_spheres, -1);
+    int record = 0;
+    for (int i = 0; i < s.desc->n_spheres; i++)
+      if (!(s.desc->spheres[i].flags & RT_PRIM_BOUNDARY))
+        s.sphere_leaf[i] = leaf_of_record[record++];
   }
   s.leaf_object.assign(std::max(n, 1), -1);
   s.leaf_id.assign(std::max(n, 1), -1);
@@ -138,6 +151,7 @@ EmuScene *emu_scene_create(const rt_scene_desc *desc) {
     delete s;
     return nullptr;
   }
+  s->desc = desc;
   build_bvh(*s);
   rtflat::Flat &f = s->flat;
   static const float4 zero4 = {0, 0, 0, 0};
@@ -164,6 +178,45 @@ EmuScene *emu_scene_create(const rt_scene_desc *desc) {
 }
 
 void emu_scene_destroy(EmuScene *s) { delete s; }
+
+// rt_scene_update_spheres_impl (rt_scene.cu) with k_leaf_links / k_update_leaves / k_refit_wide as serial loops.
+int emu_scene_update_spheres(EmuScene *s, int first, int count, const rt_sphere *spheres) {
+  using namespace rtflat;
+  Baker bk{s->desc};
+  const int n_leaf = s->d.n_prims;
+  std::vector<int> leaf_up(std::max(n_leaf, 1), -1);
+  for (int node = 0; node < s->n_wide; node++)
+    leaf_links_body(s->nodes.data(), node, leaf_up.data());
+  for (int k = 0; k < count; k++) {
+    int leaf = s->sphere_leaf[first + k];
+    if (leaf < 0)
+      return 1;
+    std::vector<float4> rec;
+    std::vector<PrimExact> ex;
+    BoxD box;
+    push_sphere(bk, spheres[k], first + k, spheres[k].material, rec, ex, box);
+    embed_sphere_material(rec.data(), s->flat.mats);
+    for (int q = 0; q < RT_PRIM_F4; q++)
+      s->prims[(size_t)leaf * RT_PRIM_F4 + q] = rec[q];
+    s->ex_prims[leaf] = ex[0];
+    node_set_slot_box(s->nodes.data(), leaf_up[leaf] >> 2, leaf_up[leaf] & 3, to_build_box(box));
+  }
+  std::vector<unsigned int> arrivals(std::max(s->n_wide, 1), 0);
+  for (int j = 0; j < n_leaf; j++) {
+    int node = leaf_up[j] >> 2;
+    for (;;) {
+      if (++arrivals[node] < (unsigned int)node_child_count(s->nodes.data(), node))
+        break;
+      const float4 *n = s->nodes.data() + (size_t)node * RT_NODE_F4;
+      int up = f2i(n[7].x);
+      if (up < 0)
+        break;
+      node_set_slot_box(s->nodes.data(), up >> 2, up & 3, node_bounds(n, n[6]));
+      node = up >> 2;
+    }
+  }
+  return 0;
+}
 void emu_stats(uint64_t *nodes, uint64_t *leaves, int reset) {
   *nodes = g_stat_nodes;
   *leaves = g_stat_leaves;

@@ -190,3 +190,68 @@ def test_both_bvh_builders_answer_alike(oracle, emu, host_scenes, monkeypatch, n
     if name != "cornell":  # 13 primitives: either tree is two levels
         assert visits["sah"] < visits["lbvh"], visits
     oracle.ora_scene_destroy(osc)
+
+
+def moved_spheres(desc, rng, count, first=3):
+    """A copy of desc's sphere array with `count` surface spheres from `first` on displaced / resized, the
+    changed slice, and a scene description that uses the copy."""
+    d = desc.contents
+    spheres = (abi.rt_sphere * d.n_spheres)()
+    C.memmove(spheres, d.spheres, C.sizeof(spheres))
+    for i in range(first, first + count):
+        s = spheres[i]
+        for a in range(3):
+            s.center0[a] += float(rng.uniform(-3.0, 3.0)) * (0.2 if a == 1 else 1.0)
+        s.center_dir[1] = float(rng.uniform(0.0, 0.5))
+        s.radius = float(rng.uniform(0.1, 0.45))
+    changed = (abi.rt_sphere * count)(*[spheres[i] for i in range(first, first + count)])
+    d2 = abi.rt_scene_desc()
+    C.memmove(C.byref(d2), C.byref(d), C.sizeof(d2))
+    d2.spheres = C.cast(spheres, C.POINTER(abi.rt_sphere))
+    return spheres, changed, d2
+
+
+def test_update_spheres_refits_the_tree(oracle, emu, host_scenes):
+    """rt_scene_update_spheres (rt_scene.cu, mirrored in the emu): moved / resized spheres are re-baked, the BVH4
+    is refitted bottom-up, and the updated scene answers exactly like a scene built from the new description."""
+    emu.emu_scene_update_spheres.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(abi.rt_sphere)]
+    hs = host_scenes("spheres", 11)
+    rng = np.random.default_rng(11)
+    first, count = 3, 120
+    keep, changed, d2 = moved_spheres(hs.desc, rng, count, first)
+    es = emu.emu_scene_create(hs.desc)
+    assert emu.emu_scene_update_spheres(es, first, count, changed) == 0
+    assert emu.emu_scene_check_bvh(es) == 0  # every child box still inside its parent's slot
+    fresh = emu.emu_scene_create(C.byref(d2))
+    cfg = hs.camera_config(96, 1, 8)
+    osc = oracle.ora_scene_create(C.byref(d2))
+    _, rays, _ = oracle_segments(oracle, osc, cfg, ol.ORA_RNG_PHILOX, ol.ORA_SAMPLER_POLAR, 5, 1)
+    n = len(rays)
+    want = (abi.rt_hit * n)()
+    oracle.ora_trace(osc, rays, n, 1, ol.ORA_RNG_PHILOX, 5, want)
+    a, b = (abi.rt_hit * n)(), (abi.rt_hit * n)()
+    emu.emu_trace(es, rays, n, abi.RT_TRACE_EXACT_F64, 5, a)
+    emu.emu_trace(fresh, rays, n, abi.RT_TRACE_EXACT_F64, 5, b)
+    w, ha, hb = ol.hits_to_numpy(want), ol.hits_to_numpy(a), ol.hits_to_numpy(b)
+    for k in ("t", "prim", "object", "front_face"):
+        assert np.array_equal(ha[k], hb[k]), k
+        assert np.array_equal(ha[k], w[k]), k
+    moved_hit = np.isin(w["prim"], np.arange(first, first + count)).sum()
+    assert moved_hit > 50  # the rays do see the moved spheres
+    # the FP32 traversal over the refitted tree finds them as well
+    c = (abi.rt_hit * n)()
+    emu.emu_trace(es, rays, n, abi.RT_TRACE_FAST_F32, 5, c)
+    assert (ol.hits_to_numpy(c)["prim"] != w["prim"]).mean() < 2e-3
+    # a boundary sphere of a medium has no leaf of its own
+    smoke = host_scenes("final", 5, 60)
+    d = smoke.desc.contents
+    boundary = [i for i in range(d.n_spheres) if d.spheres[i].flags & abi.RT_PRIM_BOUNDARY]
+    if boundary:
+        es2 = emu.emu_scene_create(smoke.desc)
+        one = (abi.rt_sphere * 1)(d.spheres[boundary[0]])
+        assert emu.emu_scene_update_spheres(es2, boundary[0], 1, one) != 0
+        emu.emu_scene_destroy(es2)
+    emu.emu_scene_destroy(es)
+    emu.emu_scene_destroy(fresh)
+    oracle.ora_scene_destroy(osc)
+    del keep

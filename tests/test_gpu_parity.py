@@ -396,3 +396,61 @@ def test_image_texture_scene(ctx, oracle, host_scenes):
     film.close()
     scene.close()
     oracle.ora_scene_destroy(osc)
+
+
+def test_update_spheres_refit(ctx, oracle, host_scenes):
+    """rt_scene_update_spheres: 200 spheres of the 485-sphere scene move / change size; the refitted scene must
+    answer the FP64 parity traversal exactly like a scene created from the new description (and like the oracle),
+    and render the same image up to FP32 traversal-order effects."""
+    from test_device_functions_host import moved_spheres
+
+    hs = host_scenes("spheres", 11)
+    rng = np.random.default_rng(23)
+    first, count = 3, 200
+    keep, changed, d2 = moved_spheres(hs.desc, rng, count, first)
+    scene = engine.Scene(ctx, hs.desc)
+    scene.update_spheres(first, changed)
+    fresh = engine.Scene(ctx, d2)
+    cfg = hs.camera_config(160, 1, 8)
+    cam = engine.camera_from_config(cfg)
+    osc = oracle.ora_scene_create(C.byref(d2))
+    _, rays, _ = oracle_segments(oracle, osc, cfg, ol.ORA_RNG_PHILOX, ol.ORA_SAMPLER_POLAR, 9, 1)
+    n = len(rays)
+    want = (abi.rt_hit * n)()
+    oracle.ora_trace(osc, rays, n, 1, ol.ORA_RNG_PHILOX, 9, want)
+    w = ol.hits_to_numpy(want)
+    a = ol.hits_to_numpy(scene.trace(rays, abi.RT_TRACE_EXACT_F64, 9))
+    b = ol.hits_to_numpy(fresh.trace(rays, abi.RT_TRACE_EXACT_F64, 9))
+    for k in ("t", "prim", "object", "front_face"):
+        assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(a[k], w[k]), k
+    assert np.isin(w["prim"], np.arange(first, first + count)).sum() > 100
+    fa, fb = engine.Film(ctx, cam.image_width, cam.image_height), engine.Film(ctx, cam.image_width, cam.image_height)
+    engine.render_static(scene, cam, fa, 2, 8, 77)
+    engine.render_static(fresh, cam, fb, 2, 8, 77)
+    ia, ib = fa.read_rgb(0.25).astype(np.float64), fb.read_rgb(0.25).astype(np.float64)
+    assert (np.abs(ia - ib).max(axis=1) < 1e-5).mean() > 0.995  # same paths; a grazing ray may flip in FP32
+    assert abs(ia.mean() - ib.mean()) < 2e-3 * ib.mean()
+    # a second update (back to the original spheres) restores the original answers
+    d = hs.desc.contents
+    original = (abi.rt_sphere * count)(*[d.spheres[i] for i in range(first, first + count)])
+    scene.update_spheres(first, original)
+    base = engine.Scene(ctx, hs.desc)
+    osc0 = oracle.ora_scene_create(hs.desc)
+    _, rays0, _ = oracle_segments(oracle, osc0, cfg, ol.ORA_RNG_PHILOX, ol.ORA_SAMPLER_POLAR, 9, 1)
+    a0 = ol.hits_to_numpy(scene.trace(rays0, abi.RT_TRACE_EXACT_F64, 9))
+    b0 = ol.hits_to_numpy(base.trace(rays0, abi.RT_TRACE_EXACT_F64, 9))
+    for k in ("t", "prim", "object", "front_face"):
+        assert np.array_equal(a0[k], b0[k]), k
+    # error behaviour
+    with pytest.raises(abi.RtError):
+        scene.update_spheres(d.n_spheres - 1, (abi.rt_sphere * 2)(d.spheres[0], d.spheres[1]))
+    bad = (abi.rt_sphere * 1)(d.spheres[5])
+    bad[0].material = d.n_materials
+    with pytest.raises(abi.RtError):
+        scene.update_spheres(5, bad)
+    for x in (fa, fb, scene, fresh, base):
+        x.close()
+    oracle.ora_scene_destroy(osc)
+    oracle.ora_scene_destroy(osc0)
+    del keep

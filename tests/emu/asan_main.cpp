@@ -20,6 +20,36 @@ int main() {
     uint64_t segs = 0;
     emu_render(es, &cam, 0, 4, 2, 12, 3, 0.25, out.data(), &segs);
     double m = 0; for (float v : out) m += v;
+    // garbage rays (NaN / infinite / zero components): the FP32 traversal must stay inside the arrays - an unused
+    // child slot is unreachable for any ray (RT_EMPTY is +inf as a float, rt_device.h)
+    {
+      const float nan = __builtin_nanf(""), inf = __builtin_huge_valf();
+      const float vals[] = {0.f, -0.f, 1.f, -1.f, nan, inf, -inf, 1e30f, 1e-30f};
+      std::vector<rt_ray> rays;
+      for (float a : vals)
+        for (float b : vals)
+          for (float c : vals) {
+            rt_ray r{};
+            r.origin[0] = b, r.origin[1] = 1.0, r.origin[2] = c;
+            r.direction[0] = a, r.direction[1] = c, r.direction[2] = b;
+            r.time = a == a ? 0.5 : a;
+            r.t_min = 0.001, r.t_max = inf;
+            rays.push_back(r);
+            r.origin[1] = a;
+            rays.push_back(r);
+          }
+      std::vector<rt_hit> hits(rays.size());
+      emu_trace(es, rays.data(), (int64_t)rays.size(), RT_TRACE_FAST_F32, 1, hits.data());
+      for (const rt_hit &h : hits)
+        if (h.prim < -1 || h.prim >= d->n_spheres + d->n_quads + d->n_media) { printf("%s: bad hit %d\n", names[k], h.prim); return 1; }
+    }
+    // animated scene: move the first surface spheres, refit, render again (rt_scene_update_spheres)
+    if (d->n_spheres > 4 && !(d->spheres[1].flags & RT_PRIM_BOUNDARY) && !(d->spheres[2].flags & RT_PRIM_BOUNDARY)) {
+      rt_sphere moved[2] = {d->spheres[1], d->spheres[2]};
+      moved[0].center0[0] += 1.5, moved[1].center0[2] -= 2.0, moved[1].radius *= 1.5;
+      if (emu_scene_update_spheres(es, 1, 2, moved) != 0 || emu_scene_check_bvh(es) != 0) { printf("%s: refit failed\n", names[k]); return 1; }
+      emu_render(es, &cam, 0, 1, 2, 6, 3, 1.0, out.data(), &segs);
+    }
     printf("%s: bvh check %d, segs %llu, mean %.4f\n", names[k], emu_scene_check_bvh(es), (unsigned long long)segs, m / out.size());
     emu_scene_destroy(es); rth_scene_free(hs);
   }

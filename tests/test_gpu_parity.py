@@ -454,3 +454,31 @@ def test_update_spheres_refit(ctx, oracle, host_scenes):
     oracle.ora_scene_destroy(osc)
     oracle.ora_scene_destroy(osc0)
     del keep
+
+
+def test_garbage_rays_do_not_leave_the_arrays(ctx, host_scenes):
+    """NaN / infinite / zero ray components through the FP32 traversal: no ray can enter an unused child slot
+    (RT_EMPTY is +inf read as a float), so the launch completes, every answer is a miss or a valid primitive, and
+    the context is still usable afterwards."""
+    hs = host_scenes("spheres", 11)
+    scene = engine.Scene(ctx, hs.desc)
+    vals = [0.0, -0.0, 1.0, -1.0, float("nan"), float("inf"), float("-inf"), 1e30, 1e-30]
+    combos = [(a, b, c) for a in vals for b in vals for c in vals]
+    rays = (abi.rt_ray * (2 * len(combos)))()
+    for i, (a, b, c) in enumerate(combos):
+        for k, oy in enumerate((1.0, a)):
+            r = rays[2 * i + k]
+            r.origin[:] = (b, oy, c)
+            r.direction[:] = (a, c, b)
+            r.time = 0.5 if a == a else a
+            r.t_min, r.t_max = 0.001, float("inf")
+    n_prims = scene.info().n_prims
+    for mode in (abi.RT_TRACE_FAST_F32, abi.RT_TRACE_EXACT_F64):
+        h = ol.hits_to_numpy(scene.trace(rays, mode, 3))
+        assert ((h["prim"] >= -1) & (h["prim"] < n_prims)).all()
+    good = (abi.rt_ray * 1)()
+    good[0].origin[:] = (13, 2, 3)
+    good[0].direction[:] = (-13, -2, -3)
+    good[0].t_min, good[0].t_max = 0.001, float("inf")
+    assert scene.trace(good, abi.RT_TRACE_FAST_F32, 3)[0].prim >= 0
+    scene.close()

@@ -332,6 +332,12 @@ def run_ours(args):
     achieved = seg_per_launch * BYTES_PER_SEGMENT / (extend_ms_per_launch * 1e-3) / 1e9 if extend_ms_per_launch > 0 else 0.0
     fp32_peak = 148 * 128 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
     flops = seg_per_launch * FLOPS_PER_SEGMENT / (extend_ms_per_launch * 1e-3) / 1e12 if extend_ms_per_launch > 0 else 0.0
+    cache = {}
+    try:  # L1- / L2-resident read bandwidth measured on this pool (tools/cache_peaks): the levels that serve the BVH
+        with open(os.path.join(REPO, "profiles", "cache_peaks.json")) as f:
+            cache = json.load(f)
+    except Exception:
+        pass
     traffic = None
     try:
         with open(os.path.join(REPO, "profiles", "extend_traffic.json")) as f:
@@ -371,6 +377,11 @@ def run_ours(args):
                          "note": "working set is L1/L2 resident (0.06 MB scene); the algorithmic bytes are node/primitive "
                                  "fetches + queue traffic, so this is an L1/L2 figure set against the HBM copy peak",
                          "fp32": {"achieved_tflops": flops, "peak_tflops": fp32_peak, "frac": flops / fp32_peak},
+                         "on_chip": ({"note": "the same algorithmic bytes against the measured L1- and L2-resident read "
+                                              "bandwidth (profiles/cache_peaks.json, tools/cache_peaks): the BVH is served by L1",
+                                      "l1_peak": cache["l1_read_gbs"], "l1_frac": achieved / cache["l1_read_gbs"],
+                                      "l2_peak": cache["l2_read_gbs"], "l2_frac": achieved / cache["l2_read_gbs"]}
+                                     if cache.get("l1_read_gbs") and cache.get("l2_read_gbs") else None),
                          "hbm_only": {"note": "bytes that must come from HBM per segment: the ray queue entry read (32 B) "
                                               "+ skip primitive read and hit written (16 B); the BVH stays in L1/L2",
                                       "bytes_per_segment": 48.0,

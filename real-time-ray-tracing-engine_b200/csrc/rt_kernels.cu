@@ -121,21 +121,22 @@ struct SmemStack {
 // A path ends exactly once.  In a one-sample pass it is the only path of its pixel, so its contribution goes
 // straight into the film (bit-identical to k_accumulate's film + radiance); multi-sample passes park it per
 // path and k_accumulate sums each pixel's samples in order.
-__device__ __forceinline__ void path_ends(const PassParams &pp, float4 *__restrict__ radiance, int path, f3 rad) {
+__device__ __forceinline__ void path_ends(const PassParams &pp, float4 *__restrict__ radiance, int path, int owned_pixel,
+                                          f3 rad) {
   if (pp.film_direct) {
 #if RT_FILM_RED
     // no other path of this pass touches the pixel: three reductions give the same sums as load-add-store
     // without waiting for the load (subnormal sums would be flushed; radiance never gets there)
-    float *f = reinterpret_cast<float *>(pp.film_direct + path);
+    float *f = reinterpret_cast<float *>(pp.film_direct + owned_pixel);
     atomicAdd(f + 0, rad.x);
     atomicAdd(f + 1, rad.y);
     atomicAdd(f + 2, rad.z);
 #else
-    float4 f = pp.film_direct[path];
+    float4 f = pp.film_direct[owned_pixel];
     f.x += rad.x;
     f.y += rad.y;
     f.z += rad.z;
-    pp.film_direct[path] = f;
+    pp.film_direct[owned_pixel] = f;
 #endif
   } else {
     radiance[path] = make_float4(rad.x, rad.y, rad.z, 0.f);
@@ -145,9 +146,21 @@ __device__ __forceinline__ void path_ends(const PassParams &pp, float4 *__restri
 __device__ __forceinline__ void path_to_key(const PassParams &pp, int path, int bounce, RayKey &key, int &owned_pixel,
                                             int &row, int &col) {
   uint32_t s_local = fastdiv(pp.div_owned, (uint32_t)path);
-  uint32_t k = (uint32_t)path - s_local * (uint32_t)pp.n_owned;
-  uint32_t local_row = fastdiv(pp.div_width, k);
-  col = (int)(k - local_row * (uint32_t)pp.map.width);
+  uint32_t k = (uint32_t)path - s_local * (uint32_t)pp.n_owned; // index within the sample
+  uint32_t local_row;
+  if (pp.tiled) {
+    // 32 consecutive paths = an 8 x 4 pixel block (a warp of camera rays is a compact bundle, and so are
+    // the hit points its scattered rays start from); the film stays row-major, only the path order changes
+    uint32_t block = k >> 5, lane = k & 31u;
+    uint32_t band = fastdiv(pp.div_blocks_x, block);
+    uint32_t bx = block - band * (uint32_t)pp.blocks_x;
+    local_row = band * 4u + (lane >> 3);
+    col = (int)(bx * 8u + (lane & 7u));
+    k = local_row * (uint32_t)pp.map.width + (uint32_t)col;
+  } else {
+    local_row = fastdiv(pp.div_width, k);
+    col = (int)(k - local_row * (uint32_t)pp.map.width);
+  }
   // owned_row_to_global (rt_device.h): tile t of this rank is global tile t * n_ranks + rank
   uint32_t tile_local = fastdiv(pp.div_tile_rows, local_row);
   uint32_t in_tile = local_row - tile_local * (uint32_t)pp.map.tile_rows;
@@ -385,7 +398,7 @@ __global__ void __launch_bounds__(RT_SHADE_THREADS, RT_SHADE_BLOCKS * RT_BLOCK /
       float4 tp = bounce == 0 ? make_float4(1.f, 1.f, 1.f, 0.f) : throughput[path];
       cont = shade_segment(sc, r, ht, F3(tp.x, tp.y, tp.z), key, last_bounce, res);
       if (!cont)
-        path_ends(pp, radiance, path, res.radiance);
+        path_ends(pp, radiance, path, k, res.radiance);
       else
         throughput[path] = make_float4(res.throughput.x, res.throughput.y, res.throughput.z, 0.f);
     }
@@ -547,7 +560,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_TAIL_BLOCKS)
         bounce++;
         segments++;
       } else {
-        path_ends(pp, radiance, path, res.radiance);
+        path_ends(pp, radiance, path, k, res.radiance);
         best.t = -1.0f;
       }
     }
@@ -562,12 +575,16 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_TAIL_BLOCKS)
 // ---------------------------------------------------------------------------------------------------
 // accumulate / resolve
 // ---------------------------------------------------------------------------------------------------
-__global__ void k_accumulate(const float4 *__restrict__ radiance, int n_owned, int n_samples, float4 *__restrict__ film) {
+__global__ void k_accumulate(const __grid_constant__ PassParams pp, const float4 *__restrict__ radiance,
+                             float4 *__restrict__ film) {
   int stride = gridDim.x * blockDim.x;
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_owned; k += stride) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < pp.n_owned; j += stride) {
+    RayKey key;
+    int k; // film index of the pixel whose paths are j, j + n_owned, ...
+    path_to_key(pp, j, 0, key, k);
     float4 acc = film[k];
-    for (int s = 0; s < n_samples; s++) {
-      float4 r = radiance[(size_t)s * n_owned + k];
+    for (int s = 0; s < pp.n_samples; s++) {
+      float4 r = radiance[(size_t)s * pp.n_owned + j];
       acc.x += r.x;
       acc.y += r.y;
       acc.z += r.z;
@@ -936,7 +953,7 @@ void launch_tail(const rt_context *ctx, const DScene &sc, const PassParams &pp, 
 void launch_accumulate(const rt_context *ctx, const PassParams &pp, WaveBuffers &w, float4 *film) {
   LaunchShape sh = rt_persistent_shape(ctx, 256, 8);
   int need = ceil_div(pp.n_owned, 256);
-  k_accumulate<<<need < sh.blocks ? need : sh.blocks, 256, 0, ctx->stream>>>(w.radiance, pp.n_owned, pp.n_samples, film);
+  k_accumulate<<<need < sh.blocks ? need : sh.blocks, 256, 0, ctx->stream>>>(pp, w.radiance, film);
 }
 
 void launch_resolve_rgb8(cudaStream_t s, const float4 *film, int64_t n, double scale, uint8_t *out) {

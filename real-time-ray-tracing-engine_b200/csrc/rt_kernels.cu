@@ -7,10 +7,12 @@
 //   k_shade       emit / scatter / light sampling, Philox draws     -> compacted ray queue of the next bounce
 //   k_tail        after the first bounces: the thin rest of the path population, traced and shaded to
 //                 completion in one persistent launch
-//   k_accumulate  per-pixel sum of the pass's samples, in order     -> film
+//   k_accumulate  multi-sample passes: per-pixel sum of the pass's samples, in order -> film (in one-sample
+//                 passes the kernel that ends a path adds its radiance to the film itself)
 // Queue lengths stay on the device (counts[bounce]); every kernel is a persistent grid sized in
 // multiples of the SM count that pulls work from the queue, so the host never synchronises between
-// bounces.  Compaction uses one ballot + one atomic per warp.
+// bounces.  Compaction uses one ballot per warp and one atomic per block.  Paths are numbered by 8 x 4 pixel
+// blocks, so a warp of camera rays is a compact bundle.
 #include "rt_internal.h"
 
 #include <cub/device/device_radix_sort.cuh>

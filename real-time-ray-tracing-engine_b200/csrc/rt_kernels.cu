@@ -34,10 +34,6 @@ LaunchShape rt_persistent_shape(const rt_context *ctx, int threads, int blocks_p
 // Short traversal stack: the first RT_STACK_SMEM entries of every thread live in shared memory
 // (column-interleaved: no bank conflicts), deeper entries spill to local memory.
 // ---------------------------------------------------------------------------------------------------
-#ifndef RT_LEAN
-#define RT_LEAN 1
-#endif
-#if RT_LEAN
 // One (reference, entry distance) pair per 8-byte word.  Every thread keeps the shared-window address of
 // its own column in a register (laundered through an empty asm so that it is not recomputed from the CTA's
 // window base at every use): a push or pop is one multiply-add and one 64-bit shared-memory access.
@@ -82,43 +78,6 @@ struct SmemStack {
 #define RT_DECLARE_STACK(stack)                                                                              \
   SmemStack stack;                                                                                           \
   stack.init()
-#else
-struct SmemStack {
-  static constexpr bool has_fast_push = false;
-  static constexpr int fast_depth = 0;
-  int *s_ref;
-  float *s_t;
-  StackEntry spill[RT_STACK - RT_STACK_SMEM];
-  __device__ __forceinline__ void set_fast_if(int i, int ref, float t, bool p) {
-    if (p)
-      set(i, ref, t);
-  }
-  __device__ __forceinline__ void set(int i, int ref, float t) {
-    if (i < RT_STACK_SMEM) {
-      s_ref[i * RT_BLOCK] = ref;
-      s_t[i * RT_BLOCK] = t;
-    } else {
-      spill[i - RT_STACK_SMEM].ref = ref;
-      spill[i - RT_STACK_SMEM].t = t;
-    }
-  }
-  __device__ __forceinline__ void get(int i, int &ref, float &t) const {
-    if (i < RT_STACK_SMEM) {
-      ref = s_ref[i * RT_BLOCK];
-      t = s_t[i * RT_BLOCK];
-    } else {
-      ref = spill[i - RT_STACK_SMEM].ref;
-      t = spill[i - RT_STACK_SMEM].t;
-    }
-  }
-};
-#define RT_DECLARE_STACK(stack)                                                                              \
-  __shared__ int s_ref[RT_STACK_SMEM * RT_BLOCK];                                                            \
-  __shared__ float s_t[RT_STACK_SMEM * RT_BLOCK];                                                            \
-  SmemStack stack;                                                                                           \
-  stack.s_ref = s_ref + threadIdx.x;                                                                         \
-  stack.s_t = s_t + threadIdx.x
-#endif
 
 // A path ends exactly once.  In a one-sample pass it is the only path of its pixel, so its contribution goes
 // straight into the film (bit-identical to k_accumulate's film + radiance); multi-sample passes park it per

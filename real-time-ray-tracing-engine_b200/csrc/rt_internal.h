@@ -53,7 +53,9 @@ struct StageTimer {
 struct rt_context {
   int device = 0;
   int sm_count = 0;
-  int wave_bounces = 3; // bounces run as separate extend / shade launches before the tail kernel takes over
+  // Bounces run as separate extend / shade launches before the tail kernel takes over; < 0 = by scene size
+  // (rt_api.cu, wave_depth).  RT_WAVE_BOUNCES overrides.
+  int wave_bounces = -1;
   int tail_span = 1 << 20; // bounces covered by one tail launch (measured: one launch for the whole tail is
                            // fastest, even at depth 50; shorter spans chain launches through the queues)
   int64_t pass_paths = (int64_t)16 << 20; // static renders: paths per wavefront pass (queue storage ~110 B per

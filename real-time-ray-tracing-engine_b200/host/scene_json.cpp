@@ -85,6 +85,7 @@ public:
 private:
   const std::string &m_text;
   size_t m_pos = 0;
+  int m_depth = 0;
   [[noreturn]] void fail(const std::string &what) {
     throw std::runtime_error("JSON: " + what + " at offset " + std::to_string(m_pos));
   }
@@ -104,6 +105,15 @@ private:
     m_pos++;
   }
   Json value() {
+    // scene files nest a handful of levels (world -> wrapper chain -> object -> vector); a bound keeps a
+    // damaged or hostile file from exhausting the stack of this recursive parser
+    struct Depth {
+      int &d;
+      explicit Depth(int &depth) : d(depth) { ++d; }
+      ~Depth() { --d; }
+    } guard(m_depth);
+    if (m_depth > 256)
+      fail("nesting deeper than 256 levels");
     char c = peek();
     Json v;
     if (c == '{') {
@@ -306,6 +316,8 @@ bool read_ppm(const std::string &path, int &w, int &h, std::vector<uint8_t> &rgb
   h = next_int();
   int maxval = next_int();
   if ((magic != "P6" && magic != "P3") || w <= 0 || h <= 0 || maxval != 255)
+    return false;
+  if (int64_t(w) * int64_t(h) > (int64_t(1) << 28)) // the scene description's own limit (rt_flatten.h)
     return false;
   rgb.resize(size_t(w) * size_t(h) * 3);
   if (magic == "P6") {

@@ -199,3 +199,69 @@ def test_json_errors_are_reported(tmp_path):
         host.HostScene.from_json(str(p))
     with pytest.raises(abi.RtError):
         host.HostScene.from_json(str(tmp_path / "missing.json"))
+
+
+def test_damaged_json_scenes_never_crash_the_loader(tmp_path):
+    """Truncations and single-character corruptions of a valid scene file: rth_scene_load_json either loads a
+    scene or reports an error.  Runs in a child process so that a crash of the parser would be seen as one."""
+    import subprocess
+    import sys
+
+    hs = host.HostScene.builtin("final", 5, 2, 6)
+    good = tmp_path / "good.json"
+    hs.save_json(str(good))
+    text = good.read_text()
+    rng = np.random.default_rng(5)
+    cases = []
+    for cut in sorted(set(int(x) for x in rng.integers(1, len(text), 60))):
+        cases.append(text[:cut])
+    for pos in rng.integers(0, len(text), 120):
+        ch = "{}[],:\"0-9.eE xyz\n"[int(rng.integers(0, 18))]
+        cases.append(text[:int(pos)] + ch + text[int(pos) + 1:])
+    cases += ["", "{", "[]", "null", '{"world": 3}', '{"world": [{"type": "Sphere"}]}', '{"world": [{"type": "Nope"}], "camera": {}}',
+              '{"camera": {"image_width": 1e99}, "world": []}', "{" * 5000, "[" * 5000 + "]" * 5000,
+              '{"world":' + "[" * 2000000 + "]" * 2000000 + "}"]  # would overflow the stack of an unbounded recursive parser
+    for i, c in enumerate(cases):
+        (tmp_path / f"case{i}.json").write_text(c)
+    child = f"""
+import sys
+sys.path.insert(0, {os.path.dirname(host.__file__)!r} + "/..")
+from rt_b200 import abi, host
+ok = bad = 0
+for i in range({len(cases)}):
+    try:
+        host.HostScene.from_json({str(tmp_path)!r} + "/case%d.json" % i).close()
+        ok += 1
+    except abi.RtError:
+        bad += 1
+print("loaded", ok, "rejected", bad)
+"""
+    r = subprocess.run([sys.executable, "-c", child], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    ok, bad = int(r.stdout.split()[1]), int(r.stdout.split()[3])
+    assert ok + bad == len(cases) and bad > len(cases) // 3
+
+
+def test_image_texture_files_are_validated(tmp_path):
+    """Image textures come from PPM files beside the JSON: P6 and P3 load, damaged files are refused."""
+    hs = host.HostScene.builtin("earth", 1)
+    good = tmp_path / "earth.json"
+    hs.save_json(str(good))
+    ppm = tmp_path / "earth.json.image0.ppm"
+    assert ppm.exists()
+    data = ppm.read_bytes()
+    header_end = data.index(b"255\n") + 4
+    w, h = [int(x) for x in data[:header_end].split()[1:3]]
+    a = host.HostScene.from_json(str(good))
+    assert a.desc.contents.n_images == 1 and a.desc.contents.images[0].width == w
+    # the same pixels as ASCII P3 with a comment line
+    px = np.frombuffer(data[header_end:], dtype=np.uint8)
+    ppm.write_text("P3\n# comment\n%d %d\n255\n" % (w, h) + " ".join(str(int(v)) for v in px) + "\n")
+    b = host.HostScene.from_json(str(good))
+    n = w * h * 3
+    assert bytes(C.cast(b.desc.contents.images[0].rgb, C.POINTER(C.c_uint8 * n)).contents) == px.tobytes()
+    for bad in (data[:header_end + 100], b"P5\n4 4\n255\n" + bytes(16), b"P6\n4 4\n65535\n" + bytes(96),
+                b"P6\n2000000000 2000000000\n255\n", b"P6\n-4 4\n255\n" + bytes(48), b"P3\n2 2\n255\n1 2 3 999", b""):
+        ppm.write_bytes(bad)
+        with pytest.raises(abi.RtError):
+            host.HostScene.from_json(str(good))

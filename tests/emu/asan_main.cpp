@@ -5,11 +5,24 @@
 #include "../../include/rt_host.h"
 #include <cstdio>
 extern "C" void ora_camera_init(const rt_camera_config *, rt_camera *);
-int main() {
+int main(int argc, char **argv) {
+  const std::string tmp = argc > 1 ? argv[1] : "/tmp";
   const char *names[] = {"spheres", "spheres_textured", "cornell", "cornell_smoke", "final", "earth"};
   int p0s[] = {11, 30, 0, 0, 6, 0};
   for (int k = 0; k < 6; k++) {
     rth_scene *hs = rth_scene_builtin(names[k], 1234, p0s[k], k == 4 ? 100 : -1);
+    { // JSON writer and reader under the sanitizers: save, load back, compare the counts
+      std::string path = tmp + "/asan_" + names[k] + ".json";
+      if (rth_scene_save_json(hs, path.c_str()) != 0) { printf("%s: save failed %s\n", names[k], rth_last_error()); return 1; }
+      rth_scene *back = rth_scene_load_json(path.c_str());
+      if (!back) { printf("%s: load failed %s\n", names[k], rth_last_error()); return 1; }
+      const rt_scene_desc *a = rth_scene_desc(hs), *b = rth_scene_desc(back);
+      if (a->n_spheres != b->n_spheres || a->n_quads != b->n_quads || a->n_media != b->n_media || a->n_materials != b->n_materials) {
+        printf("%s: JSON round trip changed the scene\n", names[k]);
+        return 1;
+      }
+      rth_scene_free(back);
+    }
     const rt_scene_desc *d = rth_scene_desc(hs);
     EmuScene *es = emu_scene_create(d);
     if (!es) { printf("%s: create failed %s\n", names[k], emu_last_error()); return 1; }

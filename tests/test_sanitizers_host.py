@@ -1,5 +1,5 @@
-"""AddressSanitizer + UBSan over the per-thread device functions (host test build) and the host scene code, on
-every built-in scene.  compute-sanitizer is closed on the GPU pool; this is the memory-safety check of the code
+"""AddressSanitizer + UBSan over the per-thread device functions (host test build) and the host scene code (builders, JSON
+writer + reader), on every built-in scene.  compute-sanitizer is closed on the GPU pool; this is the memory-safety check of the code
 the kernels are made of (scene flattening, LBVH build bodies, traversal, shading).  CPU only."""
 import os
 import subprocess
@@ -17,7 +17,7 @@ def test_device_functions_under_asan_ubsan(tmp_path):
                            *[os.path.join(host, f) for f in ("scene_builder.cpp", "scenes.cpp", "host_api.cpp",
                                                              "scene_json.cpp", "cli.cpp")], obj, "-lm", "-o", exe])
     env = dict(os.environ, ASAN_OPTIONS="detect_leaks=0", LD_PRELOAD="")
-    r = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=600)
+    r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "runtime error" not in r.stderr and "AddressSanitizer" not in r.stderr, r.stderr
     lines = [l for l in r.stdout.splitlines() if "bvh check" in l]

@@ -274,6 +274,8 @@ int rt_scene_get_info(rt_scene *scene, rt_scene_info *out);
  * built; rt_scene_create rebuilds (<= 2 ms for 10^6 primitives).  Boundary spheres of media cannot be updated
  * (RT_ERR_UNSUPPORTED).  Ordered after earlier work on the context's stream; returns when the update is done. */
 int rt_scene_update_spheres(rt_scene *scene, int first_sphere, int n_spheres, const rt_sphere *spheres);
+/* The same for quads [first_quad, first_quad + n_quads): corner, sides, material, instance chain. */
+int rt_scene_update_quads(rt_scene *scene, int first_quad, int n_quads, const rt_quad *quads);
 
 /* ----------------------------------------------------------------------------------------------
  * Closest-hit parity hook

@@ -368,6 +368,13 @@ int rt_scene_update_spheres(rt_scene *scene, int first_sphere, int n_spheres, co
   return rt_scene_update_spheres_impl(scene, first_sphere, n_spheres, spheres);
 }
 
+int rt_scene_update_quads(rt_scene *scene, int first_quad, int n_quads, const rt_quad *quads) {
+  if (!scene)
+    return invalid("rt_scene_update_quads: null scene");
+  RT_CUDA(cudaSetDevice(scene->ctx->device));
+  return rt_scene_update_quads_impl(scene, first_quad, n_quads, quads);
+}
+
 int rt_scene_get_info(rt_scene *scene, rt_scene_info *out) {
   if (!scene || !out)
     return invalid("rt_scene_get_info: null argument");

@@ -86,7 +86,8 @@ struct rt_scene {
   std::vector<rt_xform> h_xforms;
   std::vector<rt_xform_op> h_xform_ops;
   std::vector<rt_sphere> h_spheres;
-  std::vector<int> sphere_leaf; // -1: boundary sphere of a medium (not a leaf of its own)
+  std::vector<rt_quad> h_quads;
+  std::vector<int> sphere_leaf, quad_leaf; // -1: boundary primitive of a medium (not a leaf of its own)
   std::vector<float4> h_mats;
   int *leaf_up = nullptr;            // device: per leaf, parent node * 4 + slot
   unsigned int *arrivals = nullptr;  // device: per node refit counter
@@ -115,6 +116,7 @@ int rt_cuda_fail(cudaError_t e, const char *what);
 int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *scene);
 void rt_scene_release(rt_scene *scene);
 int rt_scene_update_spheres_impl(rt_scene *scene, int first, int count, const rt_sphere *spheres);
+int rt_scene_update_quads_impl(rt_scene *scene, int first, int count, const rt_quad *quads);
 
 // ---- kernel launch wrappers (rt_kernels.cu); all asynchronous on `stream` ----
 struct LaunchShape {

@@ -221,11 +221,16 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
     for (int j = 0; j < n; j++)
       leaf_of_record[order[j]] = j;
     sc->sphere_leaf.assign(desc->n_spheres, -1);
-    int record = 0; // surface spheres are the first records, in description order (rt_flatten.h)
+    sc->quad_leaf.assign(desc->n_quads, -1);
+    int record = 0; // surface spheres are the first records, then the surface quads, in description order (rt_flatten.h)
     for (int i = 0; i < desc->n_spheres; i++)
       if (!(desc->spheres[i].flags & RT_PRIM_BOUNDARY))
         sc->sphere_leaf[i] = leaf_of_record[record++];
+    for (int i = 0; i < desc->n_quads; i++)
+      if (!(desc->quads[i].flags & RT_PRIM_BOUNDARY))
+        sc->quad_leaf[i] = leaf_of_record[record++];
   }
+  sc->h_quads.assign(desc->quads, desc->quads + desc->n_quads);
 
   sc->d.nodes = sc->nodes;
   sc->d.prims = sc->prims;
@@ -257,14 +262,16 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
   return RT_OK;
 }
 
-// rt_scene_update_spheres: re-bakes the given spheres (instance chains, material copy, FP64 parity record, box),
-// scatters them to their leaves and refits the BVH4 bottom-up.  The tree keeps its topology.
-int rt_scene_update_spheres_impl(rt_scene *sc, int first, int count, const rt_sphere *spheres) {
-  const int n_spheres = (int)sc->h_spheres.size();
+// rt_scene_update_spheres / rt_scene_update_quads: re-bakes the given primitives (instance chains, material copy,
+// FP64 parity record, box), scatters them to their leaves and refits the BVH4 bottom-up.  The tree keeps its topology.
+static int update_primitives(rt_scene *sc, int first, int count, const rt_sphere *spheres, const rt_quad *quads) {
+  const bool is_sphere = spheres != nullptr;
+  const char *what = is_sphere ? "rt_scene_update_spheres" : "rt_scene_update_quads";
+  const int n_have = is_sphere ? (int)sc->h_spheres.size() : (int)sc->h_quads.size();
   if (count == 0)
     return RT_OK;
-  if (!spheres || first < 0 || count < 0 || first > n_spheres - count) {
-    rt_set_error("rt_scene_update_spheres: sphere range out of bounds");
+  if ((!spheres && !quads) || first < 0 || count < 0 || first > n_have - count) {
+    rt_set_error(std::string(what) + ": primitive range out of bounds");
     return RT_ERR_INVALID;
   }
   rt_scene_desc d{};
@@ -274,26 +281,34 @@ int rt_scene_update_spheres_impl(rt_scene *sc, int first, int count, const rt_sp
   d.n_xform_ops = (int)sc->h_xform_ops.size();
   Baker bk{&d};
   const int n_materials = (int)(sc->h_mats.size() / RT_MAT_F4);
+  const int n_spheres_total = (int)sc->h_spheres.size();
   std::vector<float4> records;
   std::vector<PrimExact> exact;
   std::vector<BuildBox> boxes;
   std::vector<int> leaves;
   for (int k = 0; k < count; k++) {
-    const rt_sphere &s = spheres[k];
     const int i = first + k;
-    if (sc->sphere_leaf[i] < 0 || (s.flags & RT_PRIM_BOUNDARY)) {
-      rt_set_error("rt_scene_update_spheres: boundary spheres of media cannot be updated");
+    const int leaf = is_sphere ? sc->sphere_leaf[i] : sc->quad_leaf[i];
+    const int flags = is_sphere ? spheres[k].flags : quads[k].flags;
+    const int xform = is_sphere ? spheres[k].xform : quads[k].xform;
+    const int material = is_sphere ? spheres[k].material : quads[k].material;
+    if (leaf < 0 || (flags & RT_PRIM_BOUNDARY)) {
+      rt_set_error(std::string(what) + ": boundary primitives of media cannot be updated");
       return RT_ERR_UNSUPPORTED;
     }
-    if (s.xform < -1 || s.xform >= d.n_xforms || s.material < 0 || s.material >= n_materials) {
-      rt_set_error("rt_scene_update_spheres: instance chain or material index out of range");
+    if (xform < -1 || xform >= d.n_xforms || material < 0 || material >= n_materials) {
+      rt_set_error(std::string(what) + ": instance chain or material index out of range");
       return RT_ERR_INVALID;
     }
     BoxD box;
-    push_sphere(bk, s, i, s.material, records, exact, box);
-    embed_sphere_material(&records[records.size() - RT_PRIM_F4], sc->h_mats);
+    if (is_sphere) {
+      push_sphere(bk, spheres[k], i, material, records, exact, box);
+      embed_sphere_material(&records[records.size() - RT_PRIM_F4], sc->h_mats);
+    } else {
+      push_quad(bk, quads[k], n_spheres_total + i, material, records, exact, box); // unified id: spheres first
+    }
     boxes.push_back(to_build_box(box));
-    leaves.push_back(sc->sphere_leaf[i]);
+    leaves.push_back(leaf);
   }
   cudaStream_t st = sc->ctx->stream;
   const int n_nodes = (int)sc->info.n_nodes;
@@ -320,8 +335,26 @@ int rt_scene_update_spheres_impl(rt_scene *sc, int first, int count, const rt_sp
   launch_refit_wide(st, sc->nodes, sc->leaf_up, sc->arrivals, sc->n_leaf);
   RT_CUDA(cudaStreamSynchronize(st)); // the staging buffers go out of scope
   RT_CUDA(cudaGetLastError());
-  std::copy(spheres, spheres + count, sc->h_spheres.begin() + first);
+  if (is_sphere)
+    std::copy(spheres, spheres + count, sc->h_spheres.begin() + first);
+  else
+    std::copy(quads, quads + count, sc->h_quads.begin() + first);
   return RT_OK;
+}
+
+int rt_scene_update_spheres_impl(rt_scene *sc, int first, int count, const rt_sphere *spheres) {
+  if (!spheres && count != 0) {
+    rt_set_error("rt_scene_update_spheres: null spheres");
+    return RT_ERR_INVALID;
+  }
+  return update_primitives(sc, first, count, spheres, nullptr);
+}
+int rt_scene_update_quads_impl(rt_scene *sc, int first, int count, const rt_quad *quads) {
+  if (!quads && count != 0) {
+    rt_set_error("rt_scene_update_quads: null quads");
+    return RT_ERR_INVALID;
+  }
+  return update_primitives(sc, first, count, nullptr, quads);
 }
 
 void rt_scene_release(rt_scene *sc) {

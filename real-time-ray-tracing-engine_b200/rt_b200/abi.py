@@ -135,6 +135,7 @@ RT_B200_SYMBOLS = {
     "rt_scene_destroy": (None, [C.c_void_p]),
     "rt_scene_get_info": (C.c_int, [C.c_void_p, P(rt_scene_info)]),
     "rt_scene_update_spheres": (C.c_int, [C.c_void_p, C.c_int, C.c_int, P(rt_sphere)]),
+    "rt_scene_update_quads": (C.c_int, [C.c_void_p, C.c_int, C.c_int, P(rt_quad)]),
     "rt_trace_rays": (C.c_int, [C.c_void_p, P(rt_ray), C.c_int64, C.c_int, C.c_uint64, P(rt_hit)]),
     "rt_film_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, VOIDPP]),
     "rt_film_destroy": (None, [C.c_void_p]),

@@ -73,6 +73,10 @@ class Scene:
         spheres: ctypes array of rt_sphere."""
         abi.check(self.lib, self.lib.rt_scene_update_spheres(self._h, first, len(spheres), spheres), "rt_scene_update_spheres")
 
+    def update_quads(self, first, quads):
+        """The same for quads; quads: ctypes array of rt_quad."""
+        abi.check(self.lib, self.lib.rt_scene_update_quads(self._h, first, len(quads), quads), "rt_scene_update_quads")
+
     def trace(self, rays, mode=abi.RT_TRACE_EXACT_F64, seed=0):
         """rays: ctypes array of rt_ray.  Returns a ctypes array of rt_hit."""
         n = len(rays)

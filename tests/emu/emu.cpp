@@ -28,7 +28,7 @@ struct EmuScene {
   ExactScene ex{};
   int n_wide = 0;
   const rt_scene_desc *desc = nullptr; // caller-owned, alive as long as the scene (tests)
-  std::vector<int> sphere_leaf;
+  std::vector<int> sphere_leaf, quad_leaf;
 };
 
 // The build stages of rt_scene.cu, one serial loop per kernel.
@@ -129,6 +129,10 @@ static void build_bvh(EmuScene &s) {
     for (int i = 0; i < s.desc->n_spheres; i++)
       if (!(s.desc->spheres[i].flags & RT_PRIM_BOUNDARY))
         s.sphere_leaf[i] = leaf_of_record[record++];
+    s.quad_leaf.assign(s.desc->n_quads, -1);
+    for (int i = 0; i < s.desc->n_quads; i++)
+      if (!(s.desc->quads[i].flags & RT_PRIM_BOUNDARY))
+        s.quad_leaf[i] = leaf_of_record[record++];
   }
   s.leaf_object.assign(std::max(n, 1), -1);
   s.leaf_id.assign(std::max(n, 1), -1);
@@ -180,7 +184,14 @@ EmuScene *emu_scene_create(const rt_scene_desc *desc) {
 void emu_scene_destroy(EmuScene *s) { delete s; }
 
 // rt_scene_update_spheres_impl (rt_scene.cu) with k_leaf_links / k_update_leaves / k_refit_wide as serial loops.
+static int emu_update(EmuScene *s, int first, int count, const rt_sphere *spheres, const rt_quad *quads);
 int emu_scene_update_spheres(EmuScene *s, int first, int count, const rt_sphere *spheres) {
+  return emu_update(s, first, count, spheres, nullptr);
+}
+int emu_scene_update_quads(EmuScene *s, int first, int count, const rt_quad *quads) {
+  return emu_update(s, first, count, nullptr, quads);
+}
+static int emu_update(EmuScene *s, int first, int count, const rt_sphere *spheres, const rt_quad *quads) {
   using namespace rtflat;
   Baker bk{s->desc};
   const int n_leaf = s->d.n_prims;
@@ -188,14 +199,18 @@ int emu_scene_update_spheres(EmuScene *s, int first, int count, const rt_sphere 
   for (int node = 0; node < s->n_wide; node++)
     leaf_links_body(s->nodes.data(), node, leaf_up.data());
   for (int k = 0; k < count; k++) {
-    int leaf = s->sphere_leaf[first + k];
+    int leaf = spheres ? s->sphere_leaf[first + k] : s->quad_leaf[first + k];
     if (leaf < 0)
       return 1;
     std::vector<float4> rec;
     std::vector<PrimExact> ex;
     BoxD box;
-    push_sphere(bk, spheres[k], first + k, spheres[k].material, rec, ex, box);
-    embed_sphere_material(rec.data(), s->flat.mats);
+    if (spheres) {
+      push_sphere(bk, spheres[k], first + k, spheres[k].material, rec, ex, box);
+      embed_sphere_material(rec.data(), s->flat.mats);
+    } else {
+      push_quad(bk, quads[k], s->desc->n_spheres + first + k, quads[k].material, rec, ex, box);
+    }
     for (int q = 0; q < RT_PRIM_F4; q++)
       s->prims[(size_t)leaf * RT_PRIM_F4 + q] = rec[q];
     s->ex_prims[leaf] = ex[0];

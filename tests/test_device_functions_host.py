@@ -255,3 +255,46 @@ def test_update_spheres_refits_the_tree(oracle, emu, host_scenes):
     emu.emu_scene_destroy(fresh)
     oracle.ora_scene_destroy(osc)
     del keep
+
+
+def test_update_quads_refits_the_tree(oracle, emu, host_scenes):
+    """rt_scene_update_quads on the Cornell box: the two boxes' quads and the light move / resize; the refitted
+    scene answers exactly like a scene built from the new description and like the oracle on it."""
+    emu.emu_scene_update_quads.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(abi.rt_quad)]
+    hs = host_scenes("cornell", 0)
+    d = hs.desc.contents
+    rng = np.random.default_rng(2)
+    quads = (abi.rt_quad * d.n_quads)()
+    C.memmove(quads, d.quads, C.sizeof(quads))
+    first, count = 5, d.n_quads - 5  # everything but the five walls
+    for i in range(first, first + count):
+        q = quads[i]
+        for a in range(3):
+            q.corner[a] += float(rng.uniform(-40.0, 40.0))
+            q.u[a] *= float(rng.uniform(0.7, 1.2))
+            q.v[a] *= float(rng.uniform(0.7, 1.2))
+    changed = (abi.rt_quad * count)(*[quads[i] for i in range(first, first + count)])
+    d2 = abi.rt_scene_desc()
+    C.memmove(C.byref(d2), C.byref(d), C.sizeof(d2))
+    d2.quads = C.cast(quads, C.POINTER(abi.rt_quad))
+    es = emu.emu_scene_create(hs.desc)
+    assert emu.emu_scene_update_quads(es, first, count, changed) == 0
+    assert emu.emu_scene_check_bvh(es) == 0
+    fresh = emu.emu_scene_create(C.byref(d2))
+    cfg = hs.camera_config(64, 1, 6)
+    osc = oracle.ora_scene_create(C.byref(d2))
+    _, rays, _ = oracle_segments(oracle, osc, cfg, ol.ORA_RNG_PHILOX, ol.ORA_SAMPLER_POLAR, 4, 1)
+    n = len(rays)
+    want = (abi.rt_hit * n)()
+    oracle.ora_trace(osc, rays, n, 1, ol.ORA_RNG_PHILOX, 4, want)
+    a, b = (abi.rt_hit * n)(), (abi.rt_hit * n)()
+    emu.emu_trace(es, rays, n, abi.RT_TRACE_EXACT_F64, 4, a)
+    emu.emu_trace(fresh, rays, n, abi.RT_TRACE_EXACT_F64, 4, b)
+    w, ha, hb = ol.hits_to_numpy(want), ol.hits_to_numpy(a), ol.hits_to_numpy(b)
+    for k in ("t", "prim", "object", "front_face"):
+        assert np.array_equal(ha[k], hb[k]), k
+        assert np.array_equal(ha[k], w[k]), k
+    assert np.isin(w["prim"], d.n_spheres + np.arange(first, first + count)).sum() > 50
+    emu.emu_scene_destroy(es)
+    emu.emu_scene_destroy(fresh)
+    oracle.ora_scene_destroy(osc)

@@ -482,3 +482,44 @@ def test_garbage_rays_do_not_leave_the_arrays(ctx, host_scenes):
     good[0].t_min, good[0].t_max = 0.001, float("inf")
     assert scene.trace(good, abi.RT_TRACE_FAST_F32, 3)[0].prim >= 0
     scene.close()
+
+
+def test_update_quads_refit(ctx, oracle, host_scenes):
+    """rt_scene_update_quads on the Cornell box (boxes and light moved / resized): bit-exact parity answers against
+    a scene created from the new description and against the oracle."""
+    hs = host_scenes("cornell", 0)
+    d = hs.desc.contents
+    rng = np.random.default_rng(2)
+    quads = (abi.rt_quad * d.n_quads)()
+    C.memmove(quads, d.quads, C.sizeof(quads))
+    first, count = 5, d.n_quads - 5
+    for i in range(first, first + count):
+        q = quads[i]
+        for a in range(3):
+            q.corner[a] += float(rng.uniform(-40.0, 40.0))
+            q.u[a] *= float(rng.uniform(0.7, 1.2))
+            q.v[a] *= float(rng.uniform(0.7, 1.2))
+    changed = (abi.rt_quad * count)(*[quads[i] for i in range(first, first + count)])
+    d2 = abi.rt_scene_desc()
+    C.memmove(C.byref(d2), C.byref(d), C.sizeof(d2))
+    d2.quads = C.cast(quads, C.POINTER(abi.rt_quad))
+    scene = engine.Scene(ctx, hs.desc)
+    scene.update_quads(first, changed)
+    fresh = engine.Scene(ctx, d2)
+    cfg = hs.camera_config(96, 1, 6)
+    osc = oracle.ora_scene_create(C.byref(d2))
+    _, rays, _ = oracle_segments(oracle, osc, cfg, ol.ORA_RNG_PHILOX, ol.ORA_SAMPLER_POLAR, 4, 1)
+    n = len(rays)
+    want = (abi.rt_hit * n)()
+    oracle.ora_trace(osc, rays, n, 1, ol.ORA_RNG_PHILOX, 4, want)
+    w = ol.hits_to_numpy(want)
+    a = ol.hits_to_numpy(scene.trace(rays, abi.RT_TRACE_EXACT_F64, 4))
+    b = ol.hits_to_numpy(fresh.trace(rays, abi.RT_TRACE_EXACT_F64, 4))
+    for k in ("t", "prim", "object", "front_face"):
+        assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(a[k], w[k]), k
+    with pytest.raises(abi.RtError):
+        scene.update_quads(d.n_quads, (abi.rt_quad * 1)(d.quads[0]))
+    scene.close()
+    fresh.close()
+    oracle.ora_scene_destroy(osc)

@@ -265,3 +265,25 @@ def test_image_texture_files_are_validated(tmp_path):
         ppm.write_bytes(bad)
         with pytest.raises(abi.RtError):
             host.HostScene.from_json(str(good))
+
+
+def build_c_example(tmp_path):
+    """examples/render_ppm.c: both headers from plain C11 (-pedantic), linked against the two shared libraries."""
+    exe = str(tmp_path / "render_ppm")
+    host_dir = os.path.dirname(abi.HOST_LIB_PATH)
+    lib_dir = os.path.dirname(abi.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(REPO, "include"),
+                           os.path.join(REPO, "examples", "render_ppm.c"), "-L", host_dir, "-lrt_host", "-L", lib_dir, "-lrt_b200",
+                           "-lm", f"-Wl,-rpath,{host_dir}", f"-Wl,-rpath,{lib_dir}", "-o", exe])
+    return exe
+
+
+def test_c_example_builds_and_refuses_to_render_on_the_cpu(tmp_path):
+    exe = build_c_example(tmp_path)
+    lib = abi.load_library()
+    r = subprocess.run([exe, "cornell", "48", "4", "4", str(tmp_path / "c.ppm")], capture_output=True, text=True, timeout=120)
+    if lib.rt_device_count() == 0:
+        assert r.returncode == 2 and "no CPU fallback" in r.stderr
+    else:
+        assert r.returncode == 0, r.stderr
+        assert (tmp_path / "c.ppm").read_text().startswith("P3\n48 48\n255\n")

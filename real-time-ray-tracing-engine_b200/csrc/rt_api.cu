@@ -138,16 +138,10 @@ int render_pass(rt_scene *scene, const rt_camera *camera, rt_film *film, int fir
   pp.max_depth = max_depth;
   pp.seed = seed;
   pp.film_direct = n_samples == 1 ? film->accum : nullptr;
-  pp.div_owned = fastdiv_make((uint32_t)std::max(pp.n_owned, 1));
-  pp.div_width = fastdiv_make((uint32_t)std::max(pp.map.width, 1));
-  pp.div_tile_rows = fastdiv_make((uint32_t)std::max(pp.map.tile_rows, 1));
   pp.div_sqrt_spp = fastdiv_make((uint32_t)std::max(sqrt_spp, 1));
   {
-    static const bool no_tiles = getenv("RT_PATH_ORDER") && std::string(getenv("RT_PATH_ORDER")) == "rows";
-    const int64_t owned_rows_n = pp.map.width > 0 ? film->n_owned / pp.map.width : 0;
-    pp.tiled = !no_tiles && pp.map.width % 8 == 0 && owned_rows_n % 4 == 0 && pp.map.tile_rows % 4 == 0;
-    pp.blocks_x = std::max(pp.map.width / 8, 1);
-    pp.div_blocks_x = fastdiv_make((uint32_t)pp.blocks_x);
+    static const bool rows_only = getenv("RT_PATH_ORDER") && std::string(getenv("RT_PATH_ORDER")) == "rows";
+    pp.paths = pathmap_make(pp.map, film->n_owned, !rows_only);
   }
   if (pp.n_paths == 0)
     return RT_OK;

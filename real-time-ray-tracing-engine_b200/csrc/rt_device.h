@@ -954,6 +954,53 @@ RT_HD int owned_rows(int height, int rank, int n_ranks, int tile_rows) {
   return rows;
 }
 
+// Path numbering of a pass: path = sample_in_pass * n_owned + k, and k enumerates the rank's owned pixels either
+// scanline by scanline or - when the film's shape allows it - by 8 x 4 pixel blocks, so that 32 consecutive paths
+// (a warp of camera rays, and the hit points its scattered rays start from) form a compact bundle.  The film
+// itself is always row-major over the owned scanlines.
+struct PathMap {
+  DFilmMap map;
+  int n_owned;
+  int tiled, blocks_x; // blocks_x = blocks per band of 4 owned scanlines
+  FastDiv div_owned, div_width, div_tile_rows, div_blocks_x;
+};
+inline PathMap pathmap_make(const DFilmMap &map, long long n_owned, bool allow_blocks) {
+  PathMap m;
+  m.map = map;
+  m.n_owned = (int)n_owned;
+  const long long owned_scanlines = map.width > 0 ? n_owned / map.width : 0;
+  m.tiled = allow_blocks && map.width > 0 && map.width % 8 == 0 && owned_scanlines % 4 == 0 && map.tile_rows % 4 == 0;
+  m.blocks_x = map.width / 8 > 1 ? map.width / 8 : 1;
+  m.div_owned = fastdiv_make((uint32_t)(n_owned > 1 ? n_owned : 1));
+  m.div_width = fastdiv_make((uint32_t)(map.width > 1 ? map.width : 1));
+  m.div_tile_rows = fastdiv_make((uint32_t)(map.tile_rows > 1 ? map.tile_rows : 1));
+  m.div_blocks_x = fastdiv_make((uint32_t)m.blocks_x);
+  return m;
+}
+// path -> sample index within the pass, film index of the pixel (row-major over the owned scanlines), global
+// scanline and column
+RT_HD void path_to_pixel(const PathMap &m, uint32_t path, uint32_t &sample_local, uint32_t &owned_pixel, int &row, int &col) {
+  sample_local = fastdiv(m.div_owned, path);
+  uint32_t k = path - sample_local * (uint32_t)m.n_owned;
+  uint32_t local_row;
+  if (m.tiled) {
+    uint32_t block = k >> 5, lane = k & 31u;
+    uint32_t band = fastdiv(m.div_blocks_x, block);
+    uint32_t bx = block - band * (uint32_t)m.blocks_x;
+    local_row = band * 4u + (lane >> 3);
+    col = (int)(bx * 8u + (lane & 7u));
+    k = local_row * (uint32_t)m.map.width + (uint32_t)col;
+  } else {
+    local_row = fastdiv(m.div_width, k);
+    col = (int)(k - local_row * (uint32_t)m.map.width);
+  }
+  // owned_row_to_global: tile t of this rank is global tile t * n_ranks + rank
+  uint32_t tile_local = fastdiv(m.div_tile_rows, local_row);
+  uint32_t in_tile = local_row - tile_local * (uint32_t)m.map.tile_rows;
+  row = (int)((tile_local * (uint32_t)m.map.n_ranks + (uint32_t)m.map.rank) * (uint32_t)m.map.tile_rows + in_tile);
+  owned_pixel = k;
+}
+
 // to_byte (utils/ColorUtility.hpp:11-26) in the reference's FP64.
 RT_HD unsigned char to_byte_f64(double v) {
   double x = v > 0 ? sqrt(v) : 0;

@@ -25,9 +25,8 @@ struct PassParams {
   int max_depth;
   uint64_t seed;
   float4 *film_direct; // one-sample passes: the film, written by the kernel that ends a path; else null
-  FastDiv div_owned, div_width, div_tile_rows, div_sqrt_spp; // invariant divisors of the path -> pixel mapping
-  int tiled, blocks_x;   // paths enumerate 8 x 4 pixel blocks (blocks_x per band of 4 owned rows) instead of rows
-  FastDiv div_blocks_x;
+  PathMap paths;        // path id -> (sample, pixel) (rt_device.h)
+  FastDiv div_sqrt_spp; // stratum -> (s_i, s_j)
 };
 
 // Per-context wavefront storage (sized for the largest pass so far).

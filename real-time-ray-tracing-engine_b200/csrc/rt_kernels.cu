@@ -106,26 +106,8 @@ __device__ __forceinline__ void path_ends(const PassParams &pp, float4 *__restri
 
 __device__ __forceinline__ void path_to_key(const PassParams &pp, int path, int bounce, RayKey &key, int &owned_pixel,
                                             int &row, int &col) {
-  uint32_t s_local = fastdiv(pp.div_owned, (uint32_t)path);
-  uint32_t k = (uint32_t)path - s_local * (uint32_t)pp.n_owned; // index within the sample
-  uint32_t local_row;
-  if (pp.tiled) {
-    // 32 consecutive paths = an 8 x 4 pixel block (a warp of camera rays is a compact bundle, and so are
-    // the hit points its scattered rays start from); the film stays row-major, only the path order changes
-    uint32_t block = k >> 5, lane = k & 31u;
-    uint32_t band = fastdiv(pp.div_blocks_x, block);
-    uint32_t bx = block - band * (uint32_t)pp.blocks_x;
-    local_row = band * 4u + (lane >> 3);
-    col = (int)(bx * 8u + (lane & 7u));
-    k = local_row * (uint32_t)pp.map.width + (uint32_t)col;
-  } else {
-    local_row = fastdiv(pp.div_width, k);
-    col = (int)(k - local_row * (uint32_t)pp.map.width);
-  }
-  // owned_row_to_global (rt_device.h): tile t of this rank is global tile t * n_ranks + rank
-  uint32_t tile_local = fastdiv(pp.div_tile_rows, local_row);
-  uint32_t in_tile = local_row - tile_local * (uint32_t)pp.map.tile_rows;
-  row = (int)((tile_local * (uint32_t)pp.map.n_ranks + (uint32_t)pp.map.rank) * (uint32_t)pp.map.tile_rows + in_tile);
+  uint32_t s_local, k;
+  path_to_pixel(pp.paths, (uint32_t)path, s_local, k, row, col);
   key.seed = pp.seed;
   key.pixel = (uint32_t)row * (uint32_t)pp.map.width + (uint32_t)col;
   key.sample = (uint32_t)pp.first_sample + s_local;

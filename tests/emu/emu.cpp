@@ -398,6 +398,25 @@ void emu_render(EmuScene *s, const rt_camera *camera, int first_sample, int n_sa
     *segments = segs;
 }
 
+// PathMap (rt_device.h): fills out[4 * i ..] = (sample in pass, film index, global scanline, column) for paths
+// first .. first + count - 1 of a pass over the tiles of `rank`; returns whether the 8 x 4 block order is in use
+int emu_path_map(int width, int height, int rank, int n_ranks, int tile_rows, int allow_blocks, uint32_t first,
+                 uint32_t count, uint32_t *out) {
+  DFilmMap map{width, height, rank, n_ranks, tile_rows};
+  long long n_owned = (long long)owned_rows(height, rank, n_ranks, tile_rows) * width;
+  PathMap m = pathmap_make(map, n_owned, allow_blocks != 0);
+  for (uint32_t i = 0; i < count; i++) {
+    uint32_t s, k;
+    int row, col;
+    path_to_pixel(m, first + i, s, k, row, col);
+    out[4 * i + 0] = s;
+    out[4 * i + 1] = k;
+    out[4 * i + 2] = (uint32_t)row;
+    out[4 * i + 3] = (uint32_t)col;
+  }
+  return m.tiled;
+}
+
 // x / d through the device code's FastDiv
 uint32_t emu_fastdiv(uint32_t d, uint32_t x) { return fastdiv(fastdiv_make(d), x); }
 

@@ -298,3 +298,36 @@ def test_update_quads_refits_the_tree(oracle, emu, host_scenes):
     emu.emu_scene_destroy(es)
     emu.emu_scene_destroy(fresh)
     oracle.ora_scene_destroy(osc)
+
+
+@pytest.mark.parametrize("width,height,n_ranks,tile_rows", [(1920, 1080, 1, 8), (1920, 1080, 3, 8), (400, 225, 1, 8),
+                                                            (64, 48, 2, 4), (40, 40, 4, 8), (33, 21, 2, 8), (8, 4, 1, 4)])
+def test_path_numbering_is_a_bijection(emu, width, height, n_ranks, tile_rows):
+    """PathMap / path_to_pixel (rt_device.h): every owned pixel gets exactly one path per sample, the film index is
+    row-major over the owned scanlines, scanlines follow the tile ownership rule, and when the 8 x 4 block order is
+    in use 32 consecutive paths cover one 8 x 4 pixel block."""
+    from rt_b200 import distributed
+
+    emu.emu_path_map.argtypes = [C.c_int] * 6 + [C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
+    for rank in range(n_ranks):
+        rows = distributed.owned_rows(height, rank, n_ranks, tile_rows)
+        n_owned = len(rows) * width
+        for allow in (1, 0):
+            n_samples = 2
+            out = (C.c_uint32 * (4 * n_owned * n_samples))()
+            tiled = emu.emu_path_map(width, height, rank, n_ranks, tile_rows, allow, 0, n_owned * n_samples, out)
+            m = np.frombuffer(out, dtype=np.uint32).reshape(-1, 4).astype(np.int64)
+            assert tiled == int(bool(allow) and width % 8 == 0 and len(rows) % 4 == 0 and tile_rows % 4 == 0)
+            for s in range(n_samples):
+                part = m[s * n_owned:(s + 1) * n_owned]
+                assert (part[:, 0] == s).all()
+                assert np.array_equal(np.sort(part[:, 1]), np.arange(n_owned))       # every film slot once
+                local_row, col = part[:, 1] // width, part[:, 1] % width
+                assert np.array_equal(col, part[:, 3])
+                assert np.array_equal(np.asarray(rows)[local_row], part[:, 2])       # tile ownership rule
+                if tiled:
+                    blocks = part.reshape(-1, 32, 4)
+                    assert ((blocks[:, :, 3].max(axis=1) - blocks[:, :, 3].min(axis=1)) == 7).all()
+                    assert ((local_row.reshape(-1, 32).max(axis=1) - local_row.reshape(-1, 32).min(axis=1)) == 3).all()
+                else:
+                    assert np.array_equal(part[:, 1], np.arange(n_owned))            # scanline order

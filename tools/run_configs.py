@@ -10,7 +10,9 @@ One process per GPU: python -m torch.distributed.run --nproc-per-node N --master
       and 64 spp depth 50; BVH build time
   c5  "final" scene 3840x2160, 4096 spp, depth 50, image tiles over all ranks + framebuffer gather
 Times are device times (CUDA events on the context stream), max over ranks; scene upload / BVH build excluded
-and reported separately.  `--quick` divides the sample counts of c3/c5 by 16 for smoke runs.
+and reported separately.  A measurement aid, not product code: the c1 leg also times the reference's own CPU
+render (oracle/_ref through tests/oracle_lib.py) and reports the RMSE against it - the checker role the oracle
+has in tests/ and in bench.py's cpu_baseline, nothing the GPU path depends on.  `--quick` divides the sample counts of c3/c5 by 16 for smoke runs.
 """
 import ctypes as C
 import json

@@ -312,9 +312,11 @@ static int update_primitives(rt_scene *sc, int first, int count, const rt_sphere
   }
   cudaStream_t st = sc->ctx->stream;
   const int n_nodes = (int)sc->info.n_nodes;
-  if (!sc->leaf_up) { // first update: where every leaf hangs, and the refit counters
-    RT_CUDA(cudaMalloc((void **)&sc->leaf_up, sizeof(int) * std::max(sc->n_leaf, 1)));
-    RT_CUDA(cudaMalloc((void **)&sc->arrivals, sizeof(unsigned int) * std::max(n_nodes, 1)));
+  if (!sc->leaf_up || !sc->arrivals) { // first update: where every leaf hangs, and the refit counters
+    if (!sc->leaf_up)
+      RT_CUDA(cudaMalloc((void **)&sc->leaf_up, sizeof(int) * std::max(sc->n_leaf, 1)));
+    if (!sc->arrivals)
+      RT_CUDA(cudaMalloc((void **)&sc->arrivals, sizeof(unsigned int) * std::max(n_nodes, 1)));
     launch_leaf_links(st, sc->nodes, n_nodes, sc->leaf_up);
   }
   Scratch scratch;

@@ -24,6 +24,21 @@ int invalid(const char *msg) {
   return RT_ERR_INVALID;
 }
 
+// The context's staging area, at least `bytes` large.  Callers synchronise the stream before they return, so
+// one area serves every call.
+int ctx_scratch(rt_context *ctx, size_t bytes, void **out) {
+  if (bytes > ctx->scratch_bytes) {
+    RT_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->scratch);
+    ctx->scratch = nullptr;
+    ctx->scratch_bytes = 0;
+    RT_CUDA(cudaMalloc(&ctx->scratch, bytes));
+    ctx->scratch_bytes = bytes;
+  }
+  *out = ctx->scratch;
+  return RT_OK;
+}
+
 // Grow the per-context wavefront storage.
 int ensure_wave(rt_context *ctx, size_t n_paths, size_t n_counts) {
   WaveBuffers &w = ctx->wave;
@@ -312,6 +327,7 @@ void rt_context_destroy(rt_context *ctx) {
   cudaFree(w.radiance);
   cudaFree(w.counts);
   cudaFree(w.stats);
+  cudaFree(ctx->scratch);
   for (cudaEvent_t e : ctx->timer.pool)
     cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
@@ -551,14 +567,16 @@ int rt_film_read_rgb(rt_film *film, double scale, float *host_rgb) {
     return RT_OK;
   rt_context *ctx = film->ctx;
   RT_CUDA(cudaSetDevice(ctx->device));
-  float *d = nullptr;
-  RT_CUDA(cudaMalloc((void **)&d, (size_t)film->n_owned * 3 * sizeof(float)));
+  void *scratch = nullptr;
+  int st = ctx_scratch(ctx, (size_t)film->n_owned * 3 * sizeof(float), &scratch);
+  if (st != RT_OK)
+    return st;
+  float *d = static_cast<float *>(scratch);
   launch_resolve_rgb(ctx->stream, film->accum, film->n_owned, scale, d);
   ctx->counters.kernel_launches += 1;
   cudaError_t e = cudaMemcpyAsync(host_rgb, d, (size_t)film->n_owned * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess)
     e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(d);
   if (e != cudaSuccess)
     return rt_cuda_fail(e, "rt_film_read_rgb");
   return RT_OK;
@@ -581,16 +599,18 @@ int rt_film_resolve_rgb8(rt_film *film, double scale, uint8_t *host_rgb8) {
     return RT_OK;
   rt_context *ctx = film->ctx;
   RT_CUDA(cudaSetDevice(ctx->device));
-  uint8_t *d = nullptr;
-  RT_CUDA(cudaMalloc((void **)&d, (size_t)film->n_owned * 3));
-  int st = rt_film_resolve_rgb8_device(film, scale, d);
+  void *scratch = nullptr;
+  int st = ctx_scratch(ctx, (size_t)film->n_owned * 3, &scratch);
+  if (st != RT_OK)
+    return st;
+  uint8_t *d = static_cast<uint8_t *>(scratch);
+  st = rt_film_resolve_rgb8_device(film, scale, d);
   cudaError_t e = cudaSuccess;
   if (st == RT_OK) {
     e = cudaMemcpyAsync(host_rgb8, d, (size_t)film->n_owned * 3, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess)
       e = cudaStreamSynchronize(ctx->stream);
   }
-  cudaFree(d);
   if (st != RT_OK)
     return st;
   if (e != cudaSuccess)

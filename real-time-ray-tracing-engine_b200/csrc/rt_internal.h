@@ -55,6 +55,10 @@ struct rt_context {
   // Bounces run as separate extend / shade launches before the tail kernel takes over; < 0 = by scene size
   // (rt_api.cu, wave_depth).  RT_WAVE_BOUNCES overrides.
   int wave_bounces = -1;
+  // device staging area of the host-pointer convenience calls (rt_film_resolve_rgb8, rt_film_read_rgb): kept
+  // across calls so that a frame loop does not pay a cudaMalloc / cudaFree pair per frame
+  void *scratch = nullptr;
+  size_t scratch_bytes = 0;
   int tail_span = 1 << 20; // bounces covered by one tail launch (measured: one launch for the whole tail is
                            // fastest, even at depth 50; shorter spans chain launches through the queues)
   int64_t pass_paths = (int64_t)16 << 20; // static renders: paths per wavefront pass (queue storage ~110 B per

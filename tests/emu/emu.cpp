@@ -417,6 +417,24 @@ int emu_path_map(int width, int height, int rank, int n_ranks, int tile_rows, in
   return m.tiled;
 }
 
+// The FP32 slab test of node_visit (rt_device.h) on one box: returns 1 when the box would be entered.
+int emu_box_test(const float *lo, const float *hi, const float *o, const float *d, float tmin, float tmax) {
+  float4 node[RT_NODE_F4];
+  const float inf = RT_INF_F;
+  for (int a = 0; a < 3; a++) {
+    node[2 * a] = make_float4(lo[a], inf, inf, inf);
+    node[2 * a + 1] = make_float4(hi[a], -inf, -inf, -inf);
+  }
+  node[6] = make_float4(i2f(~0), i2f(RT_EMPTY), i2f(RT_EMPTY), i2f(RT_EMPTY));
+  node[7] = make_float4(i2f(-1), 0.f, 0.f, 0.f);
+  DScene sc{};
+  sc.nodes = node;
+  RayTrav rt = make_trav(F3(o[0], o[1], o[2]), F3(d[0], d[1], d[2]));
+  LocalStack stack;
+  int sp = 0, next = 0;
+  return node_visit(sc, 0, rt, tmin, tmax, stack, sp, next) ? 1 : 0;
+}
+
 // x / d through the device code's FastDiv
 uint32_t emu_fastdiv(uint32_t d, uint32_t x) { return fastdiv(fastdiv_make(d), x); }
 

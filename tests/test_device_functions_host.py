@@ -331,3 +331,69 @@ def test_path_numbering_is_a_bijection(emu, width, height, n_ranks, tile_rows):
                     assert ((local_row.reshape(-1, 32).max(axis=1) - local_row.reshape(-1, 32).min(axis=1)) == 3).all()
                 else:
                     assert np.array_equal(part[:, 1], np.arange(n_owned))            # scanline order
+
+
+def test_fp32_slab_test_never_rejects_a_box_the_exact_test_enters(emu):
+    """node_visit's slab test (FP32, fused multiply-adds, precomputed o/d) may enter boxes the exact test would
+    skip, never the other way round - otherwise the fast traversal could lose hits.  Checked against the slab test
+    in exact rational arithmetic on the same FP32 inputs, over magnitudes from 1e-3 to 1e6, axis-parallel and
+    grazing rays, origins inside, on and far outside the box."""
+    from fractions import Fraction
+
+    emu.emu_box_test.argtypes = [C.POINTER(C.c_float)] * 4 + [C.c_float, C.c_float]
+    rng = np.random.default_rng(17)
+
+    def exact_accepts(lo, hi, o, d, tmin, tmax):
+        t0, t1 = Fraction(float(tmin)), Fraction(float(tmax)) if np.isfinite(tmax) else None
+        for a in range(3):
+            if d[a] == 0:
+                if not (lo[a] <= o[a] <= hi[a]):
+                    return False
+                continue
+            ta = (Fraction(float(lo[a])) - Fraction(float(o[a]))) / Fraction(float(d[a]))
+            tb = (Fraction(float(hi[a])) - Fraction(float(o[a]))) / Fraction(float(d[a]))
+            near, far = min(ta, tb), max(ta, tb)
+            t0 = max(t0, near)
+            t1 = far if t1 is None else min(t1, far)
+        return t1 is None or t0 <= t1
+
+    rejected_but_exact = 0
+    entered = exact = 0
+    for trial in range(6000):
+        scale = np.float32(10.0 ** rng.uniform(-3, 6))
+        centre = (rng.uniform(-1, 1, 3) * scale).astype(np.float32)
+        half = (rng.uniform(1e-3, 1, 3) * scale * 10.0 ** rng.uniform(-3, 0)).astype(np.float32)
+        lo, hi = (centre - half).astype(np.float32), (centre + half).astype(np.float32)
+        kind = trial % 5
+        if kind == 0:    # origin far away, aimed at a point of the box surface (grazing / corner hits)
+            target = np.where(rng.random(3) < 0.5, lo, hi).astype(np.float32)
+            o = (centre + rng.normal(size=3) * scale * 10.0 ** rng.uniform(0, 3)).astype(np.float32)
+            d = (target.astype(np.float64) - o.astype(np.float64)).astype(np.float32)
+        elif kind == 1:  # axis-parallel ray along an edge plane
+            o = (centre + rng.normal(size=3) * scale * 3).astype(np.float32)
+            d = np.zeros(3, dtype=np.float32)
+            a = int(rng.integers(0, 3))
+            d[a] = np.float32(rng.choice([-1.0, 1.0]) * 10.0 ** rng.uniform(-3, 3))
+            b = (a + 1) % 3
+            o[b] = lo[b] if rng.random() < 0.5 else hi[b]
+        elif kind == 2:  # origin inside the box
+            o = (lo + (hi - lo) * rng.random(3)).astype(np.float32)
+            d = rng.normal(size=3).astype(np.float32)
+        elif kind == 3:  # tiny direction components
+            o = (centre + rng.normal(size=3) * scale * 5).astype(np.float32)
+            d = (rng.normal(size=3) * 10.0 ** rng.uniform(-12, 0, 3)).astype(np.float32)
+        else:            # generic
+            o = (centre + rng.normal(size=3) * scale * 5).astype(np.float32)
+            d = (centre.astype(np.float64) + rng.normal(size=3) * half * 1.5 - o).astype(np.float32)
+        if not np.any(d != 0):
+            continue
+        tmin, tmax = np.float32(0.001), np.float32(np.inf if trial % 3 else 10.0 ** rng.uniform(-2, 7))
+        fast = emu.emu_box_test(lo.ctypes.data_as(C.POINTER(C.c_float)), hi.ctypes.data_as(C.POINTER(C.c_float)),
+                                o.ctypes.data_as(C.POINTER(C.c_float)), d.ctypes.data_as(C.POINTER(C.c_float)), tmin, tmax)
+        want = exact_accepts(lo, hi, o, d, tmin, tmax)
+        entered += fast
+        exact += want
+        if want and not fast:
+            rejected_but_exact += 1
+    assert rejected_but_exact == 0
+    assert exact > 1500 and entered >= exact  # the cases do exercise both outcomes

@@ -435,6 +435,15 @@ int emu_box_test(const float *lo, const float *hi, const float *o, const float *
   return node_visit(sc, 0, rt, tmin, tmax, stack, sp, next) ? 1 : 0;
 }
 
+// sphere_hit (rt_device.h) on one static sphere: returns 1 and *t on a hit
+int emu_sphere_test(const float *center, float radius, const float *o, const float *d, float tmin, float tmax, float *t) {
+  Ray r;
+  r.o = F3(o[0], o[1], o[2]);
+  r.d = F3(d[0], d[1], d[2]);
+  r.time = 0.f;
+  return sphere_hit(make_float4(center[0], center[1], center[2], radius), make_float4(0.f, 0.f, 0.f, 0.f), r, tmin, tmax, *t) ? 1 : 0;
+}
+
 // x / d through the device code's FastDiv
 uint32_t emu_fastdiv(uint32_t d, uint32_t x) { return fastdiv(fastdiv_make(d), x); }
 

@@ -397,3 +397,56 @@ def test_fp32_slab_test_never_rejects_a_box_the_exact_test_enters(emu):
             rejected_but_exact += 1
     assert rejected_but_exact == 0
     assert exact > 1500 and entered >= exact  # the cases do exercise both outcomes
+
+
+def test_fp32_sphere_test_stays_accurate_far_from_the_sphere(emu):
+    """sphere_hit evaluates the discriminant as a (r^2 - |oc - (h/a) d|^2): no cancellation between |oc|^2 and r^2,
+    so a radius-1000 ground sphere seen from its surface and a unit sphere seen from 10^4 radii away are both
+    intersected at the distance high-precision arithmetic gives (relative error of t below 1e-4 whenever the ray is
+    not grazing), where the textbook h^2 - a c form loses every digit in FP32."""
+    from decimal import Decimal, getcontext
+
+    getcontext().prec = 60
+    emu.emu_sphere_test.argtypes = [C.POINTER(C.c_float), C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                    C.c_float, C.c_float, C.POINTER(C.c_float)]
+    rng = np.random.default_rng(29)
+    fp = lambda v: v.ctypes.data_as(C.POINTER(C.c_float))  # noqa: E731
+    checked = textbook_bad = 0
+    for trial in range(3000):
+        radius = np.float32(10.0 ** rng.uniform(-2, 3))
+        centre = (rng.normal(size=3) * 10.0 ** rng.uniform(0, 3)).astype(np.float32)
+        # aim at a point well inside the silhouette from `dist` radii away
+        dist = 10.0 ** rng.uniform(0.01, 4)
+        direction = rng.normal(size=3)
+        direction /= np.linalg.norm(direction)
+        o = (centre.astype(np.float64) - direction * float(radius) * dist).astype(np.float32)
+        off = rng.normal(size=3)
+        off -= off.dot(direction) * direction
+        off *= float(radius) * rng.uniform(0, 0.8) / max(np.linalg.norm(off), 1e-30)
+        d = ((centre.astype(np.float64) + off - o) * 10.0 ** rng.uniform(-2, 2)).astype(np.float32)
+        D = lambda x: Decimal(float(x))  # noqa: E731
+        oc = [D(centre[k]) - D(o[k]) for k in range(3)]
+        a = sum(D(d[k]) * D(d[k]) for k in range(3))
+        h = sum(D(d[k]) * oc[k] for k in range(3))
+        c = sum(x * x for x in oc) - D(radius) * D(radius)
+        disc = h * h - a * c
+        if disc <= 0 or c <= 0:  # grazing, or the origin is inside the sphere
+            continue
+        t_exact = (h - disc.sqrt()) / a
+        if t_exact <= Decimal("0.002"):
+            continue
+        t = C.c_float()
+        hit = emu.emu_sphere_test(fp(centre), radius, fp(o), fp(d), np.float32(0.001), np.float32(np.inf), C.byref(t))
+        assert hit == 1, (trial, float(radius), dist)
+        rel = abs(Decimal(t.value) - t_exact) / t_exact
+        assert rel < Decimal("1e-4"), (trial, float(radius), dist, float(rel))
+        checked += 1
+        # the textbook FP32 discriminant for comparison
+        oc32 = (centre - o).astype(np.float32)
+        a32, h32 = np.float32(d @ d), np.float32(d @ oc32)
+        c32 = np.float32(np.float32(oc32 @ oc32) - radius * radius)
+        disc32 = np.float32(h32 * h32 - a32 * c32)
+        if disc32 < 0 or abs(Decimal(float((h32 - np.sqrt(max(disc32, np.float32(0)))) / a32)) - t_exact) / t_exact > Decimal("1e-4"):
+            textbook_bad += 1
+    assert checked > 2000
+    assert textbook_bad > 50  # the formulation matters: the plain FP32 form fails on a visible fraction of these rays

@@ -444,6 +444,25 @@ int emu_sphere_test(const float *center, float radius, const float *o, const flo
   return sphere_hit(make_float4(center[0], center[1], center[2], radius), make_float4(0.f, 0.f, 0.f, 0.f), r, tmin, tmax, *t) ? 1 : 0;
 }
 
+// quad_hit (rt_device.h) on one quad given as the reference's Plane(Q, u, v): record made by rt_flatten.h
+int emu_quad_test(const double *corner, const double *u, const double *v, const float *o, const float *d, float tmin,
+                  float tmax, float *t) {
+  rt_quad q{};
+  for (int k = 0; k < 3; k++)
+    q.corner[k] = corner[k], q.u[k] = u[k], q.v[k] = v[k];
+  q.xform = -1;
+  rtflat::Baker bk{nullptr};
+  std::vector<float4> rec;
+  std::vector<PrimExact> ex;
+  rtflat::BoxD box;
+  rtflat::push_quad(bk, q, 0, 0, rec, ex, box);
+  Ray r;
+  r.o = F3(o[0], o[1], o[2]);
+  r.d = F3(d[0], d[1], d[2]);
+  r.time = 0.f;
+  return quad_hit(rec[0], rec[1], rec[2], rec[3].x, r, tmin, tmax, *t) ? 1 : 0;
+}
+
 // x / d through the device code's FastDiv
 uint32_t emu_fastdiv(uint32_t d, uint32_t x) { return fastdiv(fastdiv_make(d), x); }
 

@@ -450,3 +450,56 @@ def test_fp32_sphere_test_stays_accurate_far_from_the_sphere(emu):
             textbook_bad += 1
     assert checked > 2000
     assert textbook_bad > 50  # the formulation matters: the plain FP32 form fails on a visible fraction of these rays
+
+
+def test_fp32_quad_test_against_exact_arithmetic(emu):
+    """quad_hit on records baked by rt_flatten.h: rays aimed at points well inside a quad hit it at the distance
+    rational arithmetic gives, rays aimed well outside miss, for quads of size 1e-2 .. 1e3 placed up to 1e3 from
+    the origin and seen from up to 1e3 sizes away."""
+    from fractions import Fraction
+
+    emu.emu_quad_test.argtypes = [C.POINTER(C.c_double)] * 3 + [C.POINTER(C.c_float)] * 2 + [C.c_float, C.c_float,
+                                                                                             C.POINTER(C.c_float)]
+    rng = np.random.default_rng(31)
+    dp = lambda v: v.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
+    fp = lambda v: v.ctypes.data_as(C.POINTER(C.c_float))  # noqa: E731
+    inside = outside = 0
+    for trial in range(3000):
+        size = 10.0 ** rng.uniform(-2, 3)
+        Q = rng.normal(size=3) * 10.0 ** rng.uniform(0, 3)
+        u = rng.normal(size=3)
+        v = rng.normal(size=3)
+        v -= 0.5 * v.dot(u) / u.dot(u) * u  # not degenerate, not necessarily orthogonal
+        u *= size / np.linalg.norm(u)
+        v *= size * rng.uniform(0.3, 1.0) / np.linalg.norm(v)
+        n = np.cross(u, v)
+        n /= np.linalg.norm(n)
+        want_inside = trial % 2 == 0
+        if want_inside:
+            al, be = rng.uniform(0.05, 0.95, 2)
+        else:
+            al, be = rng.uniform(1.05, 3.0) * rng.choice([-1, 1]) + 0.5, rng.uniform(-1, 2)
+        target = Q + al * u + be * v
+        away = n * rng.choice([-1, 1]) + 0.7 * rng.normal(size=3)
+        o = (target + away / np.linalg.norm(away) * size * 10.0 ** rng.uniform(-1, 3)).astype(np.float32)
+        d = ((target - o.astype(np.float64)) * 10.0 ** rng.uniform(-1, 1)).astype(np.float32)
+        t = C.c_float()
+        hit = emu.emu_quad_test(dp(Q), dp(u), dp(v), fp(o), fp(d), np.float32(0.001), np.float32(np.inf), C.byref(t))
+        # exact plane distance of the FP32 ray against the FP64 quad
+        F = lambda x: Fraction(float(x))  # noqa: E731
+        nn = [F(x) for x in np.cross(u, v)]
+        denom = sum(nn[k] * F(d[k]) for k in range(3))
+        t_exact = sum(nn[k] * (F(Q[k]) - F(o[k])) for k in range(3)) / denom
+        if want_inside:
+            assert hit == 1, (trial, size)
+            # FP32 coordinates of magnitude m carry m * 2^-24 of position error: that, or 1e-4 of the distance
+            m = max(np.abs(Q).max() + size, np.abs(o).max())
+            dn = d.astype(np.float64)
+            cos = abs(dn.dot(n)) / np.linalg.norm(dn)  # grazing incidence stretches a position error along the ray
+            allowed = max(t_exact / 10000, Fraction(float(32 * 2.0 ** -24 * m / (np.linalg.norm(dn) * cos))))
+            assert abs(Fraction(t.value) - t_exact) < allowed, (trial, size)
+            inside += 1
+        else:
+            assert hit == 0, (trial, size, al, be)
+            outside += 1
+    assert inside == 1500 and outside == 1500

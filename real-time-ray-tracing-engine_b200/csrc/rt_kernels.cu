@@ -379,9 +379,9 @@ __global__ void __launch_bounds__(RT_SHADE_THREADS, RT_SHADE_BLOCKS * RT_BLOCK /
 // ---------------------------------------------------------------------------------------------------
 // tail: the thin end of the path population in ONE launch
 // ---------------------------------------------------------------------------------------------------
-// After the first few bounces only a small fraction of the paths is alive (C2: 4 % at bounce 3, 0.5 % at
-// bounce 7), and a wavefront launch per stage is then pure latency: ~30 us per extend launch for a few
-// ten-thousand rays.  k_tail takes the queue of bounce `first_bounce` and runs every remaining path to
+// After the first bounces the path population thins out (C2: the bounces from the fourth on are 15 % of the
+// frame's segments, spread over five bounces), and every wavefront launch ends with its slowest rays - a cost
+// that no longer amortises over a small queue and that grows with the scene (rt_api.cu, wave_depth).  k_tail takes the queue of bounce `first_bounce` and runs every remaining path to
 // its end inside the kernel: persistent warps fetch paths dynamically, traverse (same while-while loop as
 // k_extend) and, when too few lanes are still traversing, shade the finished segments in place; a lane
 // whose path continues re-enters traversal with the scattered ray (written back to its own queue slot), a

@@ -217,6 +217,8 @@ inline void push_quad(const Baker &bk, const rt_quad &q, int id, int material, s
   box.grow(Q + u + v);
 }
 
+constexpr double kMaxCoordinate = 1e18; // FP32 box areas stay finite: 6 * (2e18)^2 < FLT_MAX
+
 inline int fail_invalid(const std::string &msg) {
   rt_set_error("invalid scene: " + msg);
   return RT_ERR_INVALID;
@@ -385,6 +387,14 @@ inline int flatten(const rt_scene_desc *d, Flat &f) {
 
   for (size_t r = 0; r + RT_PRIM_F4 <= f.prims.size(); r += RT_PRIM_F4)
     embed_sphere_material(&f.prims[r], f.mats);
+
+  // Geometry the FP32 build cannot order is refused here, not rendered: a NaN / infinite coordinate, or a box
+  // whose FP32 surface area overflows (|coordinate| above ~1e18), would leave the SAH sweep without a finite
+  // cost and the Morton codes without a scale.
+  for (const BoxD &b : f.boxes)
+    for (int a = 0; a < 3; a++)
+      if (!(std::fabs(b.lo[a]) <= kMaxCoordinate) || !(std::fabs(b.hi[a]) <= kMaxCoordinate))
+        return fail_invalid("primitive with a non-finite or too large coordinate (|x| must stay below 1e18)");
 
   for (int i = 0; i < d->n_perlins; i++) {
     const rt_perlin &p = d->perlins[i];

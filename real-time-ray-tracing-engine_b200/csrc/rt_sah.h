@@ -131,9 +131,13 @@ inline void build(const BuildBox *boxes, int n, HostTree &t) {
           }
         }
       }
-      for (int k = 0; k < task.count; k++)
-        idx[k] = sorted[best_axis][k];
-      mid = best_k;
+      if (best_axis >= 0) {
+        for (int k = 0; k < task.count; k++)
+          idx[k] = sorted[best_axis][k];
+        mid = best_k;
+      } else { // no finite cost (flatten() refuses such geometry; kept as a guard): split in the middle as they lie
+        mid = task.count / 2;
+      }
     } else {
       // binned SAH over the three axes of the centroid bounds
       float best_cost = RT_INF_F;

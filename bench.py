@@ -316,7 +316,7 @@ def run_ours(args):
     stage_ms, stage_n = ctx.stage_times()
     ctx.set_stage_timing(False)
     roof_counters = ctx.counters()
-    seg = roof_counters.segments - roof_counters.nodes_visited  # segments of the k_extend launches (tail excluded)
+    seg = roof_counters.segments - roof_counters.tail_segments  # segments of the k_extend launches (tail excluded)
     if rank == 0:
         sampler.stop_flag.set()
         sampler.join()
@@ -391,7 +391,7 @@ def run_ours(args):
                                       if extend_ms_per_launch > 0 else 0.0},
                          "stage_ms_per_frame": {k: stage_ms[i] / roof_steps / strata_per_step
                                                 for i, k in enumerate(["generate", "extend", "shade", "accumulate", "tail"])},
-                         "tail_segments_per_frame": roof_counters.nodes_visited / roof_steps / strata_per_step},
+                         "tail_segments_per_frame": roof_counters.tail_segments / roof_steps / strata_per_step},
             "cpu_baseline": dict(cpu_desc, value=cpu_value, unit="Mpath-samples/s"),
             "clocks": sampler.summary(),
         }

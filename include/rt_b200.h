@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 1
+#define RT_B200_ABI_VERSION 2 /* 2: rt_counters.tail_segments + true node / primitive-test counts, parity audit, frames */
 
 typedef enum rt_status {
   RT_OK = 0,
@@ -378,13 +378,53 @@ int rt_film_gather_p2p_rgb8(rt_film **films, int n_ranks, double scale, uint8_t 
 
 typedef struct rt_counters {
   uint64_t paths;          /* camera samples generated */
-  uint64_t segments;       /* rays traced by extend */
+  uint64_t segments;       /* ray segments traced (wavefront extend launches + tail kernel) */
   uint64_t kernel_launches;/* kernels launched by this library since the last reset */
-  uint64_t nodes_visited;  /* segments traced by the tail kernel (part of `segments`) */
-  uint64_t prim_tests;
+  uint64_t tail_segments;  /* the part of `segments` traced by the tail kernel */
+  uint64_t nodes_visited;  /* BVH4 node visits (4 box tests each) - counted only while rt_context_set_stats is on */
+  uint64_t prim_tests;     /* leaf primitive tests                - counted only while rt_context_set_stats is on */
 } rt_counters;
 int rt_get_counters(rt_context *ctx, rt_counters *out);
 int rt_reset_counters(rt_context *ctx);
+/* Traversal statistics: while enabled, the render passes of this context launch instrumented instantiations of
+ * the extend / tail kernels that count node visits and primitive tests (a few per cent slower); the product
+ * kernels carry no counting code. */
+int rt_context_set_stats(rt_context *ctx, int enable);
+/* Queue occupancy of the most recent render pass: out[b] = ray segments queued for bounce b (b < n, at most
+ * max_depth + 1 entries are meaningful; the tail kernel keeps its paths in registers, so bounces it runs to
+ * completion show only what it handed on).  Synchronises the context stream. */
+int rt_get_queue_lengths(rt_context *ctx, uint32_t *out, int n);
+
+/* ----------------------------------------------------------------------------------------------
+ * Parity audit of the FP32 render path (test / measurement aid)
+ * -------------------------------------------------------------------------------------------- */
+
+/* While the audit is on, render passes run every bounce as a wavefront launch and, for EVERY ray segment the
+ * FP32 extend kernel traces, also run the FP64 parity traversal (the reference's arithmetic, rt_trace_rays
+ * RT_TRACE_EXACT_F64) on the very same ray; the tallies say how often the product path names a different
+ * primitive than the reference's arithmetic would.  Slow (FP64 traversal of every segment); images are unchanged. */
+typedef struct rt_audit {
+  uint64_t segments;          /* segments compared */
+  uint64_t prim_mismatch;     /* different primitive, or hit vs miss */
+  uint64_t primary_segments;  /* bounce-0 (camera) rays compared */
+  uint64_t primary_mismatch;
+  uint64_t hit_miss_flips;    /* the part of prim_mismatch where one side missed */
+  uint64_t t_rel_above_1e4;   /* same primitive, |t32 - t64| > 1e-4 * max(|t64|, 1e-3) */
+  double max_rel_t_error;     /* over the segments with the same primitive */
+  uint64_t rechecked;         /* segments whose FP32 answer was flagged uncertain and re-done in FP64 by the product */
+} rt_audit;
+typedef struct rt_audit_sample { /* one mismatching segment (the first RT_AUDIT_MAX_SAMPLES are kept) */
+  float origin[3], time;
+  float direction[3];
+  int32_t bounce;
+  int32_t fast_prim, exact_prim; /* unified primitive ids, -1 = miss */
+  float fast_t;
+  int32_t skip_prim;
+  double exact_t;
+} rt_audit_sample;
+int rt_context_set_audit(rt_context *ctx, int enable);
+int rt_get_audit(rt_context *ctx, rt_audit *out);            /* tallies since the audit was enabled / last reset */
+int rt_get_audit_samples(rt_context *ctx, rt_audit_sample *out, int max_samples); /* returns the count, < 0 on error */
 
 /* Per-stage device timing (profiling aid): while enabled, every kernel launch of the render loop is
  * bracketed by CUDA events on the context stream.  rt_get_stage_times synchronises, adds the elapsed

@@ -78,6 +78,28 @@ int ensure_wave(rt_context *ctx, size_t n_paths, size_t n_counts) {
   return RT_OK;
 }
 
+// Storage of the parity audit, sized like the queues.
+int ensure_audit(rt_context *ctx, size_t n_paths) {
+  WaveBuffers &w = ctx->wave;
+  if (n_paths > w.capacity_audit) {
+    RT_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(w.audit_prim);
+    cudaFree(w.audit_t);
+    w.audit_prim = nullptr;
+    w.audit_t = nullptr;
+    w.capacity_audit = 0;
+    RT_CUDA(cudaMalloc((void **)&w.audit_prim, n_paths * sizeof(int2)));
+    RT_CUDA(cudaMalloc((void **)&w.audit_t, n_paths * sizeof(double)));
+    w.capacity_audit = n_paths;
+  }
+  if (!w.audit_stats) {
+    RT_CUDA(cudaMalloc((void **)&w.audit_stats, RT_AUDIT_WORDS * sizeof(unsigned long long)));
+    RT_CUDA(cudaMemsetAsync(w.audit_stats, 0, RT_AUDIT_WORDS * sizeof(unsigned long long), ctx->stream));
+    RT_CUDA(cudaMalloc((void **)&w.audit_samples, RT_AUDIT_MAX_SAMPLES * sizeof(rt_audit_sample)));
+  }
+  return RT_OK;
+}
+
 DCamera to_device_camera(const rt_camera *c) {
   DCamera d{};
   for (int a = 0; a < 3; a++) {
@@ -128,6 +150,8 @@ struct StageSpan {
 // on 1080p frames of the spheres scene (ms for 1 / 2 / 3 wavefront bounces): 485 primitives 0.681 / 0.657 / 0.657,
 // 4 k 0.896 / 0.865 / 0.873, 16 k 0.968 / 0.965 / 1.020, 65 k 1.33 / 1.39 / 1.60, 10^6 2.15 / 2.70 / 3.50.
 static int wave_depth(const rt_context *ctx, const rt_scene *scene) {
+  if (ctx->audit) // the audit brackets extend launches; the tail kernel traces inside one launch
+    return 1 << 20;
   if (ctx->wave_bounces >= 0)
     return ctx->wave_bounces;
   // participating media make single rays expensive (boundary tests + free-flight sampling at every candidate):
@@ -166,23 +190,35 @@ int render_pass(rt_scene *scene, const rt_camera *camera, rt_film *film, int fir
   DScene sc = scene->d;
   for (int a = 0; a < 3; a++)
     sc.bg[a] = (float)camera->background[a];
+  if (ctx->audit && (st = ensure_audit(ctx, (size_t)pp.n_paths)) != RT_OK)
+    return st;
   WaveBuffers &w = ctx->wave;
   RT_CUDA(cudaMemsetAsync(w.counts, 0, 2 * ((size_t)max_depth + 2) * sizeof(unsigned int), ctx->stream));
-  {
-    StageSpan span(ctx, RT_STAGE_GENERATE);
-    launch_generate(ctx, pp, w);
-  }
   // wavefront launches while the path population is large, then one tail kernel that runs whatever is
   // left to completion (rt_kernels.cu, k_tail)
   const int wave_bounces = std::min(max_depth, wave_depth(ctx, scene));
+  // The first extend launch derives the camera rays itself and queue 0 is never written (k_extend<GEN>), unless
+  // something else reads queue 0: a tail-only schedule, the parity audit, RT_FUSED_GENERATE=0 (A/B aid).
+  const bool fused_generate = wave_bounces >= 1 && !ctx->audit && ctx->fused_generate;
+  if (!fused_generate) {
+    StageSpan span(ctx, RT_STAGE_GENERATE);
+    launch_generate(ctx, pp, w);
+  }
   for (int bounce = 0; bounce < wave_bounces; bounce++) {
+    const bool gen = fused_generate && bounce == 0;
+    if (ctx->audit)
+      launch_audit_trace(ctx, scene->ex, pp, w, bounce, sc.n_media > 0);
     {
       StageSpan span(ctx, RT_STAGE_EXTEND);
-      launch_extend(ctx, sc, pp, w, bounce);
+      launch_extend(ctx, sc, pp, w, bounce, gen);
+    }
+    if (ctx->audit) {
+      launch_audit_compare(ctx, pp, w, bounce, scene->leaf_id);
+      ctx->counters.kernel_launches += 2;
     }
     {
       StageSpan span(ctx, RT_STAGE_SHADE);
-      launch_shade(ctx, sc, pp, w, bounce);
+      launch_shade(ctx, sc, pp, w, bounce, gen);
     }
   }
   // each tail launch covers at most tail_span bounces and queues its survivors for the next one
@@ -196,8 +232,9 @@ int render_pass(rt_scene *scene, const rt_camera *camera, rt_film *film, int fir
     StageSpan span(ctx, RT_STAGE_ACCUMULATE);
     launch_accumulate(ctx, pp, w, film->accum);
   }
-  ctx->counters.kernel_launches += (pp.film_direct ? 1 : 2) + 2 * (uint64_t)wave_bounces + (uint64_t)tail_launches;
+  ctx->counters.kernel_launches += (fused_generate ? 0 : 1) + (pp.film_direct ? 0 : 1) + 2 * (uint64_t)wave_bounces + (uint64_t)tail_launches;
   ctx->counters.paths += (uint64_t)pp.n_paths;
+  w.last_counts = (size_t)max_depth + 1;
   RT_CUDA(cudaGetLastError());
   return RT_OK;
 }
@@ -303,6 +340,8 @@ int rt_context_create(int device, rt_context **out) {
   ctx->sm_count = prop.multiProcessorCount;
   if (const char *env = std::getenv("RT_WAVE_BOUNCES")) // tuning / A-B aid: bounces run as wavefront launches
     ctx->wave_bounces = std::max(0, std::atoi(env));
+  if (const char *env = std::getenv("RT_FUSED_GENERATE"))
+    ctx->fused_generate = std::atoi(env) != 0;
   if (const char *env = std::getenv("RT_TAIL_SPAN"))
     ctx->tail_span = std::max(1, std::atoi(env));
   if (const char *env = std::getenv("RT_PASS_PATHS"))
@@ -327,6 +366,10 @@ void rt_context_destroy(rt_context *ctx) {
   cudaFree(w.radiance);
   cudaFree(w.counts);
   cudaFree(w.stats);
+  cudaFree(w.audit_prim);
+  cudaFree(w.audit_t);
+  cudaFree(w.audit_stats);
+  cudaFree(w.audit_samples);
   cudaFree(ctx->scratch);
   for (cudaEvent_t e : ctx->timer.pool)
     cudaEventDestroy(e);
@@ -755,9 +798,84 @@ int rt_get_counters(rt_context *ctx, rt_counters *out) {
   }
   *out = ctx->counters;
   out->segments = stats[0] + stats[3]; // wavefront extend launches + tail kernel
-  out->nodes_visited = stats[3];
+  out->tail_segments = stats[3];
+  out->nodes_visited = stats[1]; // counted by the instrumented kernels only (rt_context_set_stats)
   out->prim_tests = stats[2];
   return RT_OK;
+}
+
+int rt_context_set_stats(rt_context *ctx, int enable) {
+  if (!ctx)
+    return invalid("null context");
+  ctx->stats = enable != 0;
+  return RT_OK;
+}
+
+int rt_get_queue_lengths(rt_context *ctx, uint32_t *out, int n) {
+  if (!ctx || !out || n < 0)
+    return invalid("rt_get_queue_lengths: bad argument");
+  RT_CUDA(cudaSetDevice(ctx->device));
+  for (int k = 0; k < n; k++)
+    out[k] = 0;
+  // the first half of `counts` holds the queue lengths, the second the fetch cursors
+  size_t have = std::min<size_t>((size_t)n, ctx->wave.last_counts);
+  if (have && ctx->wave.counts) {
+    RT_CUDA(cudaStreamSynchronize(ctx->stream));
+    RT_CUDA(cudaMemcpy(out, ctx->wave.counts, have * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  }
+  return RT_OK;
+}
+
+int rt_context_set_audit(rt_context *ctx, int enable) {
+  if (!ctx)
+    return invalid("null context");
+  RT_CUDA(cudaSetDevice(ctx->device));
+  RT_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->audit = enable != 0;
+  if (ctx->wave.audit_stats)
+    RT_CUDA(cudaMemsetAsync(ctx->wave.audit_stats, 0, RT_AUDIT_WORDS * sizeof(unsigned long long), ctx->stream));
+  return RT_OK;
+}
+
+int rt_get_audit(rt_context *ctx, rt_audit *out) {
+  if (!ctx || !out)
+    return invalid("rt_get_audit: null argument");
+  RT_CUDA(cudaSetDevice(ctx->device));
+  unsigned long long t[RT_AUDIT_WORDS] = {};
+  if (ctx->wave.audit_stats) {
+    RT_CUDA(cudaStreamSynchronize(ctx->stream));
+    RT_CUDA(cudaMemcpy(t, ctx->wave.audit_stats, sizeof t, cudaMemcpyDeviceToHost));
+  }
+  std::memset(out, 0, sizeof *out);
+  out->segments = t[RT_AUDIT_SEGMENTS];
+  out->prim_mismatch = t[RT_AUDIT_MISMATCH];
+  out->primary_segments = t[RT_AUDIT_PRIMARY];
+  out->primary_mismatch = t[RT_AUDIT_PRIMARY_MISMATCH];
+  out->hit_miss_flips = t[RT_AUDIT_HIT_MISS];
+  out->t_rel_above_1e4 = t[RT_AUDIT_T_ABOVE_1E4];
+  uint32_t bits = (uint32_t)t[RT_AUDIT_MAX_REL_T];
+  float f;
+  std::memcpy(&f, &bits, 4);
+  out->max_rel_t_error = f;
+  out->rechecked = 0;
+  return RT_OK;
+}
+
+int rt_get_audit_samples(rt_context *ctx, rt_audit_sample *out, int max_samples) {
+  if (!ctx || (max_samples > 0 && !out) || max_samples < 0) {
+    invalid("rt_get_audit_samples: bad argument");
+    return -1;
+  }
+  if (!ctx->wave.audit_stats || cudaSetDevice(ctx->device) != cudaSuccess)
+    return 0;
+  unsigned long long n = 0;
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess ||
+      cudaMemcpy(&n, ctx->wave.audit_stats + RT_AUDIT_SAMPLES, sizeof n, cudaMemcpyDeviceToHost) != cudaSuccess)
+    return -1;
+  int have = (int)std::min<unsigned long long>(n, std::min<unsigned long long>(RT_AUDIT_MAX_SAMPLES, (unsigned long long)max_samples));
+  if (have && cudaMemcpy(out, ctx->wave.audit_samples, (size_t)have * sizeof(rt_audit_sample), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return -1;
+  return have;
 }
 
 int rt_context_set_stage_timing(rt_context *ctx, int enable) {

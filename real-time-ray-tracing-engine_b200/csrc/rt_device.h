@@ -269,13 +269,25 @@ struct Hit {
 
 // Camera::get_ray (Camera.cpp:186-205) with the reference CUDA path's polar disk sampler
 // (Vec3Utility.cuh:57-61).  u0 = (jitter x, jitter y, disk r^2, disk angle), u1.x = time.
+// Every multiply-add is written as an explicit fmaf: the same camera ray is computed in more than one kernel
+// (the first extend launch generates it, the first shade launch re-derives it instead of reading it back from
+// memory), and explicit fused operations leave the compiler no contraction choice that could differ between them.
+RT_HD float fma_add(float a, float b, float c) { // a * b + c in one rounding
+#if defined(__CUDA_ARCH__)
+  return __fmaf_rn(a, b, c);
+#else
+  return fmaf(a, b, c);
+#endif
+}
 RT_HD Ray camera_ray(const DCamera &cam, int i, int j, int s_i, int s_j, float recip_sqrt_spp, Uniform4 u0,
                      Uniform4 u1) {
-  float px = ((float)s_i + u0.x) * recip_sqrt_spp - 0.5f;
-  float py = ((float)s_j + u0.y) * recip_sqrt_spp - 0.5f;
+  float px = fma_add((float)s_i + u0.x, recip_sqrt_spp, -0.5f);
+  float py = fma_add((float)s_j + u0.y, recip_sqrt_spp, -0.5f);
   float fx = (float)i + px, fy = (float)j + py;
-  f3 du = F3(cam.du[0], cam.du[1], cam.du[2]), dv = F3(cam.dv[0], cam.dv[1], cam.dv[2]);
-  f3 rel = F3(cam.p00c[0], cam.p00c[1], cam.p00c[2]) + fx * du + fy * dv; // pixel sample - center
+  // pixel sample - center
+  f3 rel = F3(fma_add(fy, cam.dv[0], fma_add(fx, cam.du[0], cam.p00c[0])),
+              fma_add(fy, cam.dv[1], fma_add(fx, cam.du[1], cam.p00c[1])),
+              fma_add(fy, cam.dv[2], fma_add(fx, cam.du[2], cam.p00c[2])));
   f3 lens = F3(0.f, 0.f, 0.f);
   if (cam.defocus) {
     float r = sqrtf(u0.z);
@@ -287,8 +299,9 @@ RT_HD Ray camera_ray(const DCamera &cam, int i, int j, int s_i, int s_j, float r
     sn = sinf(th);
     cs = cosf(th);
 #endif
-    lens = (r * cs) * F3(cam.disk_u[0], cam.disk_u[1], cam.disk_u[2]) +
-           (r * sn) * F3(cam.disk_v[0], cam.disk_v[1], cam.disk_v[2]);
+    float lu = r * cs, lv = r * sn;
+    lens = F3(fma_add(lv, cam.disk_v[0], lu * cam.disk_u[0]), fma_add(lv, cam.disk_v[1], lu * cam.disk_u[1]),
+              fma_add(lv, cam.disk_v[2], lu * cam.disk_u[2]));
   }
   Ray ray;
   ray.o = F3(cam.center[0], cam.center[1], cam.center[2]) + lens;

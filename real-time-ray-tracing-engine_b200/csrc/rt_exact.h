@@ -219,8 +219,10 @@ RT_HD void leaf_test_exact(const ExactScene &sc, int prim, const RayD &ray, doub
   }
 }
 
+// skip_prim (leaf order, -1 = none): the primitive the ray starts on and cannot hit again (a flat primitive the
+// render path's previous segment ended on, rt_device.h shade_segment); the parity hook passes -1.
 RT_HD void traverse_exact(const ExactScene &sc, const RayD &ray, double tmin, double tmax, HitD &hit,
-                          const RayKey &key) {
+                          const RayKey &key, int skip_prim = -1) {
   hit.t = tmax;
   hit.prim = -1;
   hit.front = 0;
@@ -233,7 +235,8 @@ RT_HD void traverse_exact(const ExactScene &sc, const RayD &ray, double tmin, do
   while (sp > 0) {
     int ref = stack[--sp];
     if (ref < 0) {
-      leaf_test_exact(sc, ~ref, ray, tmin, hit, key);
+      if (~ref != skip_prim)
+        leaf_test_exact(sc, ~ref, ray, tmin, hit, key);
       continue;
     }
     const float4 *n = sc.nodes + (size_t)ref * RT_NODE_F4;

@@ -29,6 +29,27 @@ struct PassParams {
   FastDiv div_sqrt_spp; // stratum -> (s_i, s_j)
 };
 
+// Philox key and film index of a path at a bounce (shared by the render kernels and the parity audit).
+RT_HD void path_to_key(const PassParams &pp, int path, int bounce, RayKey &key, int &owned_pixel, int &row, int &col) {
+  uint32_t s_local, k;
+  path_to_pixel(pp.paths, (uint32_t)path, s_local, k, row, col);
+  key.seed = pp.seed;
+  key.pixel = (uint32_t)row * (uint32_t)pp.map.width + (uint32_t)col;
+  key.sample = (uint32_t)pp.first_sample + s_local;
+  key.bounce = (uint32_t)bounce;
+  owned_pixel = (int)k;
+}
+RT_HD void path_to_key(const PassParams &pp, int path, int bounce, RayKey &key, int &owned_pixel) {
+  int row, col;
+  path_to_key(pp, path, bounce, key, owned_pixel, row, col);
+}
+
+// Parity audit (rt_context_set_audit): per queue slot, the FP64 parity traversal's answer for the ray the FP32
+// extend kernel is about to trace, and the tallies of the comparison.
+enum { RT_AUDIT_SEGMENTS = 0, RT_AUDIT_MISMATCH = 1, RT_AUDIT_PRIMARY = 2, RT_AUDIT_PRIMARY_MISMATCH = 3,
+       RT_AUDIT_HIT_MISS = 4, RT_AUDIT_T_ABOVE_1E4 = 5, RT_AUDIT_MAX_REL_T = 6, RT_AUDIT_SAMPLES = 7, RT_AUDIT_WORDS = 8 };
+#define RT_AUDIT_MAX_SAMPLES 4096
+
 // Per-context wavefront storage (sized for the largest pass so far).
 struct WaveBuffers {
   float4 *ray_a[2] = {nullptr, nullptr}; // origin.xyz, time
@@ -37,7 +58,16 @@ struct WaveBuffers {
   float4 *throughput = nullptr;          // per path
   float4 *radiance = nullptr;            // per path: final contribution
   unsigned int *counts = nullptr;        // queue length per bounce (max_depth + 2 entries)
-  unsigned long long *stats = nullptr;   // [0] segments traced  [1] nodes visited  [2] primitive tests
+  unsigned long long *stats = nullptr;   // [0] segments of the extend launches  [1] node visits  [2] primitive tests
+                                         // ([1], [2]: only counted by the instrumented kernels, rt_context_set_stats)
+                                         // [3] segments of the tail kernel
+  // parity audit (allocated on first use)
+  int2 *audit_prim = nullptr;            // per queue slot: leaf-order primitive of the FP64 traversal (-1 = miss), skipped primitive
+  double *audit_t = nullptr;             // per queue slot: its t
+  unsigned long long *audit_stats = nullptr; // RT_AUDIT_WORDS tallies
+  rt_audit_sample *audit_samples = nullptr;  // first RT_AUDIT_MAX_SAMPLES mismatching segments
+  size_t capacity_audit = 0;
+  size_t last_counts = 0; // queue-length entries the most recent pass used
   size_t capacity_paths = 0;
   size_t capacity_counts = 0;
 };
@@ -63,6 +93,9 @@ struct rt_context {
                            // fastest, even at depth 50; shorter spans chain launches through the queues)
   int64_t pass_paths = (int64_t)16 << 20; // static renders: paths per wavefront pass (queue storage ~110 B per
                                           // path; measured 4 M / 8 M / 16 M / 32 M: 16 M is fastest on C1 and C3)
+  bool fused_generate = true; // the first extend launch derives the camera rays (no k_generate, no queue 0)
+  bool audit = false; // every extend launch is checked against the FP64 parity traversal (all-wavefront schedule)
+  bool stats = false; // instrumented extend / tail kernels count node visits and primitive tests
   cudaStream_t stream = nullptr;
   WaveBuffers wave;
   rt_counters counters{};
@@ -140,8 +173,8 @@ void launch_gather_records(cudaStream_t s, const void *in, const uint32_t *index
 
 // wavefront render
 void launch_generate(const rt_context *ctx, const PassParams &pp, WaveBuffers &w);
-void launch_extend(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int bounce);
-void launch_shade(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int bounce);
+void launch_extend(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int bounce, bool gen);
+void launch_shade(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int bounce, bool gen);
 void launch_tail(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int first_bounce,
                  int end_bounce, int buffer);
 void launch_leaf_links(cudaStream_t s, const float4 *nodes, int n_nodes, int *leaf_up);
@@ -153,6 +186,11 @@ void launch_resolve_rgb8(cudaStream_t s, const float4 *film, int64_t n, double s
 void launch_resolve_rgb(cudaStream_t s, const float4 *film, int64_t n, double scale, float *out);
 void launch_scatter_gathered(cudaStream_t s, int width, int height, int n_ranks, int tile_rows, const void *gathered,
                              void *full, int bytes_per_pixel); // 16: float4 sums, 3: RGB8
+
+// parity audit (rt_exact.cu)
+void launch_audit_trace(const rt_context *ctx, const ExactScene &sc, const PassParams &pp, WaveBuffers &w, int bounce,
+                        int has_media);
+void launch_audit_compare(const rt_context *ctx, const PassParams &pp, WaveBuffers &w, int bounce, const int *leaf_id);
 
 // parity hook
 void launch_trace_fast(const rt_context *ctx, const DScene &sc, const rt_ray *d_rays, int64_t n, uint64_t seed,

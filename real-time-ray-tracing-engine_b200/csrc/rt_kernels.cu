@@ -104,36 +104,28 @@ __device__ __forceinline__ void path_ends(const PassParams &pp, float4 *__restri
   }
 }
 
-__device__ __forceinline__ void path_to_key(const PassParams &pp, int path, int bounce, RayKey &key, int &owned_pixel,
-                                            int &row, int &col) {
-  uint32_t s_local, k;
-  path_to_pixel(pp.paths, (uint32_t)path, s_local, k, row, col);
-  key.seed = pp.seed;
-  key.pixel = (uint32_t)row * (uint32_t)pp.map.width + (uint32_t)col;
-  key.sample = (uint32_t)pp.first_sample + s_local;
-  key.bounce = (uint32_t)bounce;
-  owned_pixel = (int)k;
-}
-__device__ __forceinline__ void path_to_key(const PassParams &pp, int path, int bounce, RayKey &key, int &owned_pixel) {
-  int row, col;
-  path_to_key(pp, path, bounce, key, owned_pixel, row, col);
-}
-
 // ---------------------------------------------------------------------------------------------------
 // generate
 // ---------------------------------------------------------------------------------------------------
+// The camera ray of path p (Camera::get_ray, Camera.cpp:186-205): a pure function of the pass parameters and the
+// path's Philox key, so any kernel can derive it instead of reading it from memory.
+__device__ __forceinline__ Ray path_camera_ray(const PassParams &pp, int p) {
+  RayKey key;
+  int k, row, col;
+  path_to_key(pp, p, 0, key, k, row, col);
+  int s_j = (int)fastdiv(pp.div_sqrt_spp, key.sample), s_i = (int)key.sample - s_j * pp.sqrt_spp;
+  Uniform4 u0 = philox_uniform4(pp.seed, key.pixel, key.sample, 0, RT_STREAM_CAMERA, 0);
+  Uniform4 u1 = philox_uniform4(pp.seed, key.pixel, key.sample, 0, RT_STREAM_CAMERA, 1);
+  return camera_ray(pp.cam, col, row, s_i, s_j, pp.recip_sqrt_spp, u0, u1);
+}
+
+// Only launched when the first bounce does not generate its own rays (tail-only schedules, the parity audit).
 __global__ void __launch_bounds__(RT_BLOCK)
     k_generate(const __grid_constant__ PassParams pp, float4 *__restrict__ ray_a, float4 *__restrict__ ray_b,
                unsigned int *__restrict__ counts) {
   int stride = gridDim.x * blockDim.x;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < pp.n_paths; p += stride) {
-    RayKey key;
-    int k, row, col;
-    path_to_key(pp, p, 0, key, k, row, col);
-    int s_j = (int)fastdiv(pp.div_sqrt_spp, key.sample), s_i = (int)key.sample - s_j * pp.sqrt_spp;
-    Uniform4 u0 = philox_uniform4(pp.seed, key.pixel, key.sample, 0, RT_STREAM_CAMERA, 0);
-    Uniform4 u1 = philox_uniform4(pp.seed, key.pixel, key.sample, 0, RT_STREAM_CAMERA, 1);
-    Ray r = camera_ray(pp.cam, col, row, s_i, s_j, pp.recip_sqrt_spp, u0, u1);
+    Ray r = path_camera_ray(pp, p);
     ray_a[p] = make_float4(r.o.x, r.o.y, r.o.z, r.time);
     ray_b[p] = make_float4(r.d.x, r.d.y, r.d.z, __int_as_float(p));
     // no per-path initialisation is written: at bounce 0 the throughput is 1 and no primitive is skipped
@@ -165,15 +157,45 @@ __global__ void __launch_bounds__(RT_BLOCK)
 #endif
 #define RT_DONE 0x7fffffff
 
+// STATS: the instrumented instantiation (rt_context_set_stats) counts node visits and primitive tests; the
+// product instantiation carries no counting code.
+template <bool STATS>
+__device__ __forceinline__ void traversal_stats(unsigned long long *stats, unsigned int n_nodes, unsigned int n_tests) {
+  if (STATS) {
+    for (int o = 16; o > 0; o >>= 1) {
+      n_nodes += __shfl_xor_sync(0xffffffffu, n_nodes, o);
+      n_tests += __shfl_xor_sync(0xffffffffu, n_tests, o);
+    }
+    if ((threadIdx.x & 31u) == 0 && (n_nodes | n_tests)) {
+      atomicAdd(&stats[1], (unsigned long long)n_nodes);
+      atomicAdd(&stats[2], (unsigned long long)n_tests);
+    }
+  }
+}
+
+// GEN (bounce 0 only): the kernel derives the camera ray of path q itself instead of reading queue 0, which is
+// then never written (k_generate is not launched, k_shade<GEN> re-derives the ray as well): one launch and
+// 2 x 32 B per path of queue traffic less.  The ray a lane is tracing is parked in shared memory for the
+// primitive tests (origin, direction and time are not needed by node visits and would not fit in registers).
+#ifndef RT_RAY_SMEM
+#define RT_RAY_SMEM 0 // 1: bounces > 0 also park the fetched ray in shared memory instead of re-reading the queue
+#endif
+__shared__ float4 rt_ray_smem_a[RT_BLOCK], rt_ray_smem_b[RT_BLOCK];
+
+template <bool STATS, bool GEN>
 __global__ void __launch_bounds__(RT_BLOCK, 8)
     k_extend(const __grid_constant__ DScene sc, const __grid_constant__ PassParams pp,
              const float4 *__restrict__ ray_a, const float4 *__restrict__ ray_b, float2 *__restrict__ hit,
-             const unsigned int *__restrict__ counts, unsigned int *__restrict__ cursor, int bounce, int has_media,
+             unsigned int *__restrict__ counts, unsigned int *__restrict__ cursor, int bounce, int has_media,
              unsigned long long *stats) {
   RT_DECLARE_STACK(stack);
-  const unsigned int n = counts[bounce];
-  if (blockIdx.x == 0 && threadIdx.x == 0)
+  constexpr bool PARK = GEN || RT_RAY_SMEM;
+  const unsigned int n = GEN ? (unsigned int)pp.n_paths : counts[bounce];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
     atomicAdd(&stats[0], (unsigned long long)n);
+    if (GEN)
+      counts[0] = n; // the length of the (virtual) queue 0, read by the shade launch that follows
+  }
   const unsigned int lane = threadIdx.x & 31u;
   const unsigned int lt_mask = (1u << lane) - 1u;
 
@@ -183,7 +205,7 @@ __global__ void __launch_bounds__(RT_BLOCK, 8)
   RayTrav rt = make_trav(F3(0.f, 0.f, 0.f), F3(1.f, 1.f, 1.f));
   Hit best;
   int sp = 0, ref = RT_DONE;
-  unsigned int q = 0;
+  unsigned int q = 0, n_nodes = 0, n_tests = 0;
   bool exhausted = false; // the queue has no more rays to hand out
   best.t = -1.0f;         // no ray held
   best.prim = -1;
@@ -201,7 +223,19 @@ __global__ void __launch_bounds__(RT_BLOCK, 8)
         unsigned int mine = base + (unsigned int)__popc(idle & lt_mask);
         if (mine < n) {
           q = mine;
-          float4 a = ray_a[q], b = ray_b[q];
+          float4 a, b;
+          if (GEN) {
+            Ray r = path_camera_ray(pp, (int)q);
+            a = make_float4(r.o.x, r.o.y, r.o.z, r.time);
+            b = make_float4(r.d.x, r.d.y, r.d.z, __int_as_float((int)q));
+          } else {
+            a = ray_a[q];
+            b = ray_b[q];
+          }
+          if (PARK) {
+            rt_ray_smem_a[threadIdx.x] = a;
+            rt_ray_smem_b[threadIdx.x] = b;
+          }
           rt = make_trav(F3(a.x, a.y, a.z), F3(b.x, b.y, b.z));
           best.t = RT_INF_F;
           best.prim = -1;
@@ -218,13 +252,22 @@ __global__ void __launch_bounds__(RT_BLOCK, 8)
     for (;;) {
       // inner nodes only
       while (ref >= 0 && ref != RT_DONE) {
+        if (STATS)
+          n_nodes++;
         if (!node_visit(sc, ref, rt, RT_T_MIN, best.t, stack, sp, ref))
           if (!stack_pop(stack, sp, best.t, ref))
             ref = RT_DONE;
       }
       // leaves only
       if (ref < 0) {
-        float4 a = ray_a[q], b = ray_b[q];
+        float4 a, b;
+        if (PARK) {
+          a = rt_ray_smem_a[threadIdx.x];
+          b = rt_ray_smem_b[threadIdx.x];
+        } else {
+          a = ray_a[q];
+          b = ray_b[q];
+        }
         Ray r;
         r.o = F3(a.x, a.y, a.z);
         r.d = F3(b.x, b.y, b.z);
@@ -239,6 +282,8 @@ __global__ void __launch_bounds__(RT_BLOCK, 8)
           path_to_key(pp, __float_as_int(b.w), bounce, key, k);
         }
         do {
+          if (STATS)
+            n_tests += ~ref != skip;
           leaf_test(sc, ~ref, r, RT_T_MIN, best, skip, key);
           if (!stack_pop(stack, sp, best.t, ref))
             ref = RT_DONE;
@@ -254,6 +299,7 @@ __global__ void __launch_bounds__(RT_BLOCK, 8)
         break;
     }
   }
+  traversal_stats<STATS>(stats, n_nodes, n_tests);
 }
 
 // The straightforward variant (one ray per thread, grid stride, single if/else loop); kept for A/B
@@ -300,16 +346,25 @@ __global__ void __launch_bounds__(RT_BLOCK)
 #define RT_SHADE_THREADS 256
 #endif
 #define RT_SHADE_WARPS (RT_SHADE_THREADS / 32)
+#ifndef RT_SHADE_SORT
+#define RT_SHADE_SORT 0
+#endif
 // Queue compaction: every warp counts its continuing paths with a ballot, the block adds the counts up in
 // shared memory and reserves the slots of all its warps with ONE atomicAdd on the next queue's length.  All
 // atomics of a launch hit the same address and the L2 serialises them (~0.85 clocks each): one per warp
 // (65 k per launch at 1080p) kept every warp waiting on that queue; one per block is 8 times fewer.
+// GEN (bounce 0 of a pass whose first extend launch generated the camera rays): queue slot q is path q and its
+// ray is re-derived from the path's Philox key instead of being read.
+template <bool GEN>
 __global__ void __launch_bounds__(RT_SHADE_THREADS, RT_SHADE_BLOCKS * RT_BLOCK / RT_SHADE_THREADS)
     k_shade(const __grid_constant__ DScene sc, const __grid_constant__ PassParams pp, const float4 *__restrict__ ray_a,
             const float4 *__restrict__ ray_b, const float2 *__restrict__ hit, float4 *__restrict__ next_a,
             float4 *__restrict__ next_b, float2 *__restrict__ next_hit, float4 *__restrict__ throughput,
             float4 *__restrict__ radiance, unsigned int *__restrict__ counts, int bounce) {
   __shared__ unsigned int s_count[RT_SHADE_WARPS], s_first[RT_SHADE_WARPS];
+#if RT_SHADE_SORT
+  __shared__ unsigned int s_sort[8 * RT_SHADE_WARPS];
+#endif
   const int n = (int)counts[bounce];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool last_bounce = bounce + 1 >= pp.max_depth;
@@ -323,18 +378,24 @@ __global__ void __launch_bounds__(RT_SHADE_THREADS, RT_SHADE_BLOCKS * RT_BLOCK /
     int path = 0;
     if (active) {
       // all three queue reads go out before anything waits on one of them
-      float4 a = ldg4_now(ray_a + q), b = ldg4_now(ray_b + q);
       float2 h = ldg2_now(hit + q);
-      path = __float_as_int(b.w);
       Ray r;
-      r.o = F3(a.x, a.y, a.z);
-      r.d = F3(b.x, b.y, b.z);
-      r.time = a.w;
       Hit ht;
       ht.t = h.x;
-      // a ray with a NaN time counts as a miss; the test also ties the miss branch to ray_a, which keeps
-      // that read next to the other two instead of behind the branch (one exposed memory latency less)
-      ht.prim = a.w == a.w ? __float_as_int(h.y) : -1;
+      if (GEN) {
+        path = q;
+        r = path_camera_ray(pp, q);
+        ht.prim = __float_as_int(h.y);
+      } else {
+        float4 a = ldg4_now(ray_a + q), b = ldg4_now(ray_b + q);
+        path = __float_as_int(b.w);
+        r.o = F3(a.x, a.y, a.z);
+        r.d = F3(b.x, b.y, b.z);
+        r.time = a.w;
+        // a ray with a NaN time counts as a miss; the test also ties the miss branch to ray_a, which keeps
+        // that read next to the other two instead of behind the branch (one exposed memory latency less)
+        ht.prim = a.w == a.w ? __float_as_int(h.y) : -1;
+      }
       RayKey key;
       int k;
       path_to_key(pp, path, bounce, key, k);
@@ -345,6 +406,55 @@ __global__ void __launch_bounds__(RT_SHADE_THREADS, RT_SHADE_BLOCKS * RT_BLOCK /
       else
         throughput[path] = make_float4(res.throughput.x, res.throughput.y, res.throughput.z, 0.f);
     }
+#if RT_SHADE_SORT
+    // Block-local counting sort of the continuing rays by direction octant: the block's slots are handed out
+    // octant by octant (and warp by warp within an octant), so 32 consecutive queue entries - a warp of the next
+    // extend launch - mostly share the signs of their direction, i.e. the order in which they walk the tree.
+    static_assert(RT_SHADE_WARPS == 8, "the 64-entry scan below assumes 8 warps per block");
+    const unsigned int oct = cont ? ((res.next.d.x < 0.f ? 1u : 0u) | (res.next.d.y < 0.f ? 2u : 0u) |
+                                     (res.next.d.z < 0.f ? 4u : 0u))
+                                  : 8u;
+    unsigned int rank = 0, my_count = 0;
+#pragma unroll
+    for (unsigned int k = 0; k < 8; k++) {
+      unsigned int m = __ballot_sync(0xffffffffu, oct == k);
+      if (oct == k)
+        rank = (unsigned int)__popc(m & ((1u << lane) - 1u));
+      if ((unsigned int)lane == k)
+        my_count = (unsigned int)__popc(m);
+    }
+    if (lane < 8)
+      s_sort[lane * RT_SHADE_WARPS + warp] = my_count; // octant-major
+    __syncthreads();
+    if (warp == 0) {
+      unsigned int a = s_sort[lane], b = s_sort[lane + 32];
+      unsigned int ia = a, ib = b;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        unsigned int ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+        if (lane >= o) {
+          ia += ta;
+          ib += tb;
+        }
+      }
+      unsigned int total_a = __shfl_sync(0xffffffffu, ia, 31), total = total_a + __shfl_sync(0xffffffffu, ib, 31);
+      unsigned int first = 0;
+      if (lane == 0 && total)
+        first = atomicAdd(&counts[bounce + 1], total);
+      first = __shfl_sync(0xffffffffu, first, 0);
+      s_sort[lane] = first + ia - a;
+      s_sort[lane + 32] = first + total_a + ib - b;
+    }
+    __syncthreads();
+    if (cont) {
+      unsigned int slot = s_sort[oct * RT_SHADE_WARPS + warp] + rank;
+      next_a[slot] = make_float4(res.next.o.x, res.next.o.y, res.next.o.z, res.next.time);
+      next_b[slot] = make_float4(res.next.d.x, res.next.d.y, res.next.d.z, __int_as_float(path));
+      next_hit[slot] = make_float2(0.f, __int_as_float(res.next_skip_prim));
+    }
+    __syncthreads(); // s_sort is rewritten by the next iteration
+    continue;
+#endif
     unsigned int mask = __ballot_sync(0xffffffffu, cont);
     if (lane == 0)
       s_count[warp] = (unsigned int)__popc(mask);
@@ -387,6 +497,20 @@ __global__ void __launch_bounds__(RT_SHADE_THREADS, RT_SHADE_BLOCKS * RT_BLOCK /
 // whose path continues re-enters traversal with the scattered ray (written back to its own queue slot), a
 // lane whose path ended fetches the next path.  Philox keys carry the lane's own bounce index, so the
 // image is identical to the all-wavefront schedule.
+#ifndef RT_TAIL_NOINLINE
+#define RT_TAIL_NOINLINE 0 // 1: the tail kernel calls the shading step as a function (its registers are then live only
+                           // during the call, so the traversal loop can run at a higher occupancy)
+#endif
+#if RT_TAIL_NOINLINE
+__device__ __noinline__ bool shade_segment_call(const DScene &sc, const Ray &ray, Hit hit, f3 throughput, const RayKey &key,
+                                                bool last_bounce, ShadeResult &out) {
+  return shade_segment(sc, ray, hit, throughput, key, last_bounce, out);
+}
+#else
+#define shade_segment_call shade_segment
+#endif
+
+template <bool STATS>
 __global__ void __launch_bounds__(RT_BLOCK, RT_TAIL_BLOCKS)
     k_tail(const __grid_constant__ DScene sc, const __grid_constant__ PassParams pp, float4 *__restrict__ ray_a,
            float4 *__restrict__ ray_b, float2 *__restrict__ hit, float4 *__restrict__ next_a,
@@ -401,7 +525,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_TAIL_BLOCKS)
   RayTrav rt = make_trav(F3(0.f, 0.f, 0.f), F3(1.f, 1.f, 1.f));
   Hit best;
   int sp = 0, ref = RT_DONE, bounce = first_bounce;
-  unsigned int q = 0, segments = 0;
+  unsigned int q = 0, segments = 0, n_nodes = 0, n_tests = 0;
   bool exhausted = false;
   best.t = -1.0f; // no segment held
   best.prim = -1;
@@ -437,6 +561,8 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_TAIL_BLOCKS)
     // ---- traverse until too few lanes are still inside the tree ----
     for (;;) {
       while (ref >= 0 && ref != RT_DONE) {
+        if (STATS)
+          n_nodes++;
         if (!node_visit(sc, ref, rt, RT_T_MIN, best.t, stack, sp, ref))
           if (!stack_pop(stack, sp, best.t, ref))
             ref = RT_DONE;
@@ -457,6 +583,8 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_TAIL_BLOCKS)
           path_to_key(pp, __float_as_int(b.w), bounce, key, k);
         }
         do {
+          if (STATS)
+            n_tests += ~ref != skip;
           leaf_test(sc, ~ref, r, RT_T_MIN, best, skip, key);
           if (!stack_pop(stack, sp, best.t, ref))
             ref = RT_DONE;
@@ -480,7 +608,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_TAIL_BLOCKS)
       path_to_key(pp, path, bounce, key, k);
       float4 tp = bounce == 0 ? make_float4(1.f, 1.f, 1.f, 0.f) : throughput[path];
       ShadeResult res;
-      bool cont = shade_segment(sc, r, best, F3(tp.x, tp.y, tp.z), key, bounce + 1 >= pp.max_depth, res);
+      bool cont = shade_segment_call(sc, r, best, F3(tp.x, tp.y, tp.z), key, bounce + 1 >= pp.max_depth, res);
       if (cont && bounce + 1 >= end_bounce) {
         // the launch covers bounces [first_bounce, end_bounce): survivors are queued for the next launch,
         // so one very long path (glass, mirrors) cannot keep a whole launch waiting on a single lane
@@ -513,6 +641,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_TAIL_BLOCKS)
     segments += __shfl_xor_sync(0xffffffffu, segments, o);
   if (lane == 0 && segments)
     atomicAdd(&stats[3], (unsigned long long)segments);
+  traversal_stats<STATS>(stats, n_nodes, n_tests);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -854,7 +983,7 @@ void launch_generate(const rt_context *ctx, const PassParams &pp, WaveBuffers &w
   k_generate<<<need < sh.blocks ? need : sh.blocks, RT_BLOCK, 0, ctx->stream>>>(pp, w.ray_a[0], w.ray_b[0], w.counts);
 }
 
-void launch_extend(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int bounce) {
+void launch_extend(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int bounce, bool gen) {
   int b = bounce & 1;
   static const bool simple = getenv("RT_EXTEND") && std::string(getenv("RT_EXTEND")) == "simple";
   if (simple) {
@@ -868,16 +997,19 @@ void launch_extend(const rt_context *ctx, const DScene &sc, const PassParams &pp
   LaunchShape sh = rt_persistent_shape(ctx, RT_BLOCK, 8);
   int need = ceil_div(pp.n_paths, RT_BLOCK);
   unsigned int *cursor = w.counts + (pp.max_depth + 2) + bounce;
-  k_extend<<<need < sh.blocks ? need : sh.blocks, RT_BLOCK, 0, ctx->stream>>>(sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b],
-                                                                              w.counts, cursor, bounce, sc.n_media > 0,
-                                                                              w.stats);
+  const int blocks = need < sh.blocks ? need : sh.blocks;
+  auto kernel = gen ? (ctx->stats ? k_extend<true, true> : k_extend<false, true>)
+                    : (ctx->stats ? k_extend<true, false> : k_extend<false, false>);
+  kernel<<<blocks, RT_BLOCK, 0, ctx->stream>>>(sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b], w.counts, cursor, bounce,
+                                               sc.n_media > 0, w.stats);
 }
 
-void launch_shade(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int bounce) {
+void launch_shade(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int bounce, bool gen) {
   LaunchShape sh = rt_persistent_shape(ctx, RT_SHADE_THREADS, RT_SHADE_BLOCKS * RT_BLOCK / RT_SHADE_THREADS);
   int need = ceil_div(pp.n_paths, RT_SHADE_THREADS);
   int b = bounce & 1, nb = b ^ 1;
-  k_shade<<<need < sh.blocks ? need : sh.blocks, RT_SHADE_THREADS, 0, ctx->stream>>>(
+  auto kernel = gen ? k_shade<true> : k_shade<false>;
+  kernel<<<need < sh.blocks ? need : sh.blocks, RT_SHADE_THREADS, 0, ctx->stream>>>(
       sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b], w.ray_a[nb], w.ray_b[nb], w.hit[nb], w.throughput, w.radiance, w.counts,
       bounce);
 }
@@ -888,9 +1020,15 @@ void launch_tail(const rt_context *ctx, const DScene &sc, const PassParams &pp, 
   int need = ceil_div(pp.n_paths, RT_BLOCK);
   int b = buffer, nb = buffer ^ 1;
   unsigned int *cursor = w.counts + (pp.max_depth + 2) + first_bounce;
-  k_tail<<<need < sh.blocks ? need : sh.blocks, RT_BLOCK, 0, ctx->stream>>>(
-      sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b], w.ray_a[nb], w.ray_b[nb], w.hit[nb], w.throughput, w.radiance, w.counts,
-      cursor, first_bounce, end_bounce, sc.n_media > 0, w.stats);
+  const int blocks = need < sh.blocks ? need : sh.blocks;
+  if (ctx->stats)
+    k_tail<true><<<blocks, RT_BLOCK, 0, ctx->stream>>>(sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b], w.ray_a[nb], w.ray_b[nb],
+                                                       w.hit[nb], w.throughput, w.radiance, w.counts, cursor, first_bounce,
+                                                       end_bounce, sc.n_media > 0, w.stats);
+  else
+    k_tail<false><<<blocks, RT_BLOCK, 0, ctx->stream>>>(sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b], w.ray_a[nb], w.ray_b[nb],
+                                                        w.hit[nb], w.throughput, w.radiance, w.counts, cursor, first_bounce,
+                                                        end_bounce, sc.n_media > 0, w.stats);
 }
 
 void launch_accumulate(const rt_context *ctx, const PassParams &pp, WaveBuffers &w, float4 *film) {

@@ -11,6 +11,7 @@ REPO_DIR = os.path.dirname(PKG_DIR)
 LIB_PATH = os.environ.get("RT_B200_LIB") or os.path.join(PKG_DIR, "csrc", "librt_b200.so")  # override: A/B builds
 HOST_LIB_PATH = os.path.join(PKG_DIR, "host", "librt_host.so")
 
+RT_B200_ABI_VERSION = 2
 RT_OK, RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_NO_DEVICE, RT_ERR_UNSUPPORTED = range(5)
 RT_MAT_LAMBERTIAN, RT_MAT_METAL, RT_MAT_DIELECTRIC, RT_MAT_DIFFUSE_LIGHT, RT_MAT_ISOTROPIC = range(5)
 RT_TEX_SOLID, RT_TEX_CHECKER, RT_TEX_NOISE, RT_TEX_IMAGE = range(4)
@@ -115,7 +116,19 @@ class rt_hit(C.Structure):
 
 class rt_counters(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("segments", C.c_uint64), ("kernel_launches", C.c_uint64),
-                ("nodes_visited", C.c_uint64), ("prim_tests", C.c_uint64)]
+                ("tail_segments", C.c_uint64), ("nodes_visited", C.c_uint64), ("prim_tests", C.c_uint64)]
+
+
+class rt_audit(C.Structure):
+    _fields_ = [("segments", C.c_uint64), ("prim_mismatch", C.c_uint64), ("primary_segments", C.c_uint64),
+                ("primary_mismatch", C.c_uint64), ("hit_miss_flips", C.c_uint64), ("t_rel_above_1e4", C.c_uint64),
+                ("max_rel_t_error", C.c_double), ("rechecked", C.c_uint64)]
+
+
+class rt_audit_sample(C.Structure):
+    _fields_ = [("origin", C.c_float * 3), ("time", C.c_float), ("direction", C.c_float * 3), ("bounce", C.c_int32),
+                ("fast_prim", C.c_int32), ("exact_prim", C.c_int32), ("fast_t", C.c_float), ("skip_prim", C.c_int32),
+                ("exact_t", C.c_double)]
 
 
 P = C.POINTER
@@ -159,6 +172,11 @@ RT_B200_SYMBOLS = {
     "rt_film_gather_p2p_rgb8": (C.c_int, [P(C.c_void_p), C.c_int, C.c_double, P(C.c_uint8)]),
     "rt_get_counters": (C.c_int, [C.c_void_p, P(rt_counters)]),
     "rt_reset_counters": (C.c_int, [C.c_void_p]),
+    "rt_context_set_stats": (C.c_int, [C.c_void_p, C.c_int]),
+    "rt_get_queue_lengths": (C.c_int, [C.c_void_p, P(C.c_uint32), C.c_int]),
+    "rt_context_set_audit": (C.c_int, [C.c_void_p, C.c_int]),
+    "rt_get_audit": (C.c_int, [C.c_void_p, P(rt_audit)]),
+    "rt_get_audit_samples": (C.c_int, [C.c_void_p, P(rt_audit_sample), C.c_int]),
     "rt_context_set_stage_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "rt_get_stage_times": (C.c_int, [C.c_void_p, P(C.c_double), P(C.c_uint64)]),
 }
@@ -185,7 +203,7 @@ def load_library(path=None):
         fn = getattr(lib, name)  # AttributeError if the ABI is incomplete
         fn.restype = res
         fn.argtypes = args
-    if lib.rt_abi_version() != 1:
+    if lib.rt_abi_version() != RT_B200_ABI_VERSION:
         raise RtError("librt_b200.so ABI version mismatch")
     if path is None:
         _lib = lib

@@ -44,6 +44,31 @@ class Context:
         abi.check(self.lib, self.lib.rt_get_stage_times(self._h, ms, n), "rt_get_stage_times")
         return list(ms), list(n)
 
+    def set_stats(self, enable):
+        """Instrumented extend / tail kernels: counters() then reports node visits and primitive tests."""
+        abi.check(self.lib, self.lib.rt_context_set_stats(self._h, int(enable)), "rt_context_set_stats")
+
+    def queue_lengths(self, n):
+        out = (C.c_uint32 * n)()
+        abi.check(self.lib, self.lib.rt_get_queue_lengths(self._h, out, n), "rt_get_queue_lengths")
+        return list(out)
+
+    def set_audit(self, enable):
+        """Parity audit: every segment of the following render passes is also traced by the FP64 parity traversal."""
+        abi.check(self.lib, self.lib.rt_context_set_audit(self._h, int(enable)), "rt_context_set_audit")
+
+    def audit(self):
+        a = abi.rt_audit()
+        abi.check(self.lib, self.lib.rt_get_audit(self._h, C.byref(a)), "rt_get_audit")
+        return a
+
+    def audit_samples(self, max_samples=4096):
+        buf = (abi.rt_audit_sample * max_samples)()
+        n = self.lib.rt_get_audit_samples(self._h, buf, max_samples)
+        if n < 0:
+            raise abi.RtError("rt_get_audit_samples failed")
+        return buf[:n]
+
     def reset_counters(self):
         abi.check(self.lib, self.lib.rt_reset_counters(self._h), "rt_reset_counters")
 

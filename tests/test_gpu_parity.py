@@ -11,6 +11,11 @@ from rt_b200 import abi, distributed, engine
 
 pytestmark = pytest.mark.gpu
 
+# FP32 product path vs the FP64 parity traversal of the same ray (rt_context_set_audit): fraction of segments that
+# name a different primitive.  Bounds = 2 x the largest rate measured at the BASELINE sizes (profiles/r02_audit.md).
+AUDIT_MISMATCH_BOUND = 2e-3
+AUDIT_PRIMARY_BOUND = 2e-3
+
 SCENES = [("spheres", 11, -1, 96), ("spheres", 40, -1, 64), ("spheres_textured", 12, -1, 64), ("cornell", 0, -1, 48),
           ("cornell_smoke", 0, -1, 48), ("final", 5, 60, 64)]
 
@@ -523,3 +528,77 @@ def test_update_quads_refit(ctx, oracle, host_scenes):
     scene.close()
     fresh.close()
     oracle.ora_scene_destroy(osc)
+
+
+def test_fused_generate_is_bit_identical(host_scenes, monkeypatch):
+    """The first extend launch derives the camera rays itself (no k_generate, no queue 0) and the first shade launch
+    re-derives them: the image must be bit-identical to the schedule that writes and reads queue 0."""
+    hs = host_scenes("spheres", 11, -1)
+    cfg = hs.camera_config(256, 4, 8)
+    cam = engine.camera_from_config(cfg)
+    images = []
+    for fused in ("1", "0"):
+        monkeypatch.setenv("RT_FUSED_GENERATE", fused)
+        c = engine.Context(0)
+        scene = engine.Scene(c, hs.desc)
+        film = engine.Film(c, cam.image_width, cam.image_height)
+        engine.render_static(scene, cam, film, 2, 8, 21)          # multi-sample pass
+        engine.render_accumulate(scene, cam, film, 0, 0, 1, 8, 22)  # one-sample pass (film written directly)
+        images.append(film.read_rgb(1.0))
+        launches = c.counters().kernel_launches
+        # static pass: 3 x (extend, shade) + tail + accumulate; frame: 3 x (extend, shade) + tail; + the resolve of
+        # read_rgb; the unfused schedule adds one k_generate per pass
+        assert launches == (16 if fused == "1" else 18), launches
+        film.close()
+        scene.close()
+        c.close()
+    assert np.array_equal(images[0], images[1])
+
+
+@pytest.mark.parametrize("name,p0,width,depth", [("spheres", 11, 320, 8), ("cornell", 0, 200, 12), ("final", 5, 256, 8)])
+def test_parity_audit_and_traversal_counters(ctx, host_scenes, name, p0, width, depth):
+    """rt_context_set_audit: every segment of a frame is also answered by the FP64 parity traversal of the same ray.
+    The audit must see every segment, leave the image alone, and the FP32 path must name the same primitive on all
+    but a small fraction of the segments (bound: 2 x the rate measured at the BASELINE sizes, profiles/r02_audit.md).
+    rt_context_set_stats: node visits and primitive tests are only counted by the instrumented kernels."""
+    hs = host_scenes(name, p0, 60 if name == "final" else -1)
+    cam = engine.camera_from_config(hs.camera_config(width, 1, depth))
+    scene = engine.Scene(ctx, hs.desc)
+    film = engine.Film(ctx, cam.image_width, cam.image_height)
+    ctx.reset_counters()
+    engine.render_accumulate(scene, cam, film, 0, 0, 1, depth, 5)
+    plain = film.read_rgb(1.0)
+    c0 = ctx.counters()
+    assert c0.nodes_visited == 0 and c0.prim_tests == 0 and 0 < c0.tail_segments < c0.segments
+    film.clear()
+    ctx.set_audit(True)
+    ctx.reset_counters()
+    engine.render_accumulate(scene, cam, film, 0, 0, 1, depth, 5)
+    a = ctx.audit()
+    c1 = ctx.counters()
+    ctx.set_audit(False)
+    assert a.segments == c1.segments and a.primary_segments == cam.image_width * cam.image_height
+    assert c1.tail_segments == 0  # the audit runs every bounce as a wavefront launch
+    assert abs(int(c1.segments) - int(c0.segments)) <= 2e-3 * c0.segments
+    assert a.prim_mismatch <= AUDIT_MISMATCH_BOUND * a.segments, (a.prim_mismatch, a.segments)
+    assert a.primary_mismatch <= max(1, AUDIT_PRIMARY_BOUND * a.primary_segments), (a.primary_mismatch, a.primary_segments)
+    assert a.hit_miss_flips <= a.prim_mismatch
+    samples = ctx.audit_samples()
+    assert len(samples) == min(a.prim_mismatch, 4096)
+    audited = film.read_rgb(1.0)
+    same = np.abs(audited.astype(np.float64) - plain).max(axis=1) <= 1e-4 * np.maximum(1.0, plain.max(axis=1))
+    assert same.mean() > 0.995  # another schedule (all wavefront), same paths
+    # traversal statistics
+    ctx.set_stats(True)
+    ctx.reset_counters()
+    film.clear()
+    engine.render_accumulate(scene, cam, film, 0, 0, 1, depth, 5)
+    c2 = ctx.counters()
+    ctx.set_stats(False)
+    assert np.array_equal(film.read_rgb(1.0), plain)  # the instrumented kernels trace the same paths
+    assert c2.segments == c0.segments
+    assert 1.0 <= c2.nodes_visited / c2.segments < 40 and 0.1 < c2.prim_tests / c2.segments < 40
+    q = ctx.queue_lengths(depth + 1)
+    assert q[0] == cam.image_width * cam.image_height and q[1] < q[0] and q[1] > 0
+    film.close()
+    scene.close()

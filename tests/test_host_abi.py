@@ -28,7 +28,7 @@ def test_cuda_library_exports_every_declared_symbol():
     assert declared == set(abi.RT_B200_SYMBOLS), "abi.py must mirror include/rt_b200.h"
     assert declared <= exported(abi.LIB_PATH)
     lib = abi.load_library()
-    assert lib.rt_abi_version() == 1
+    assert lib.rt_abi_version() == abi.RT_B200_ABI_VERSION == 2
 
 
 def test_host_library_exports_every_declared_symbol():
@@ -38,16 +38,17 @@ def test_host_library_exports_every_declared_symbol():
 
 def test_struct_sizes_match_the_header():
     # sizes the C compiler gives the same declarations (compiled once from the header)
-    src = '#include <stdio.h>\n#include "rt_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu",' \
+    src = '#include <stdio.h>\n#include "rt_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu",' \
           "sizeof(rt_sphere),sizeof(rt_quad),sizeof(rt_xform_op),sizeof(rt_xform),sizeof(rt_medium),sizeof(rt_material)," \
           "sizeof(rt_texture),sizeof(rt_perlin),sizeof(rt_light),sizeof(rt_scene_desc),sizeof(rt_camera_config)," \
-          "sizeof(rt_camera),sizeof(rt_ray),sizeof(rt_hit),sizeof(rt_counters));return 0;}"
+          "sizeof(rt_camera),sizeof(rt_ray),sizeof(rt_hit),sizeof(rt_counters),sizeof(rt_audit),sizeof(rt_audit_sample));return 0;}"
     exe = "/tmp/rt_sizes_test"
     subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(REPO, "include"), "-o", exe], input=src, text=True, check=True)
     sizes = list(map(int, subprocess.check_output([exe], text=True).split()))
     mine = [C.sizeof(t) for t in (abi.rt_sphere, abi.rt_quad, abi.rt_xform_op, abi.rt_xform, abi.rt_medium,
                                   abi.rt_material, abi.rt_texture, abi.rt_perlin, abi.rt_light, abi.rt_scene_desc,
-                                  abi.rt_camera_config, abi.rt_camera, abi.rt_ray, abi.rt_hit, abi.rt_counters)]
+                                  abi.rt_camera_config, abi.rt_camera, abi.rt_ray, abi.rt_hit, abi.rt_counters,
+                                  abi.rt_audit, abi.rt_audit_sample)]
     assert sizes == mine
 
 

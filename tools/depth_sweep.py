@@ -25,5 +25,5 @@ for depth in [int(d) for d in sys.argv[5:]]:
     c = ctx.counters()
     print(f"{name} depth {depth:3d}: total {sum(ms):9.2f} ms  " +
           " ".join(f"{k}={v:.2f}({int(m)})" for k, v, m in zip(["gen", "ext", "shade", "acc", "tail"], ms, n)) +
-          f"  seg/path {c.segments / c.paths:.3f} tail segs {c.nodes_visited}", flush=True)
+          f"  seg/path {c.segments / c.paths:.3f} tail segs {c.tail_segments}", flush=True)
     film.close()

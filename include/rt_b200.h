@@ -373,6 +373,43 @@ int rt_film_gather_p2p(rt_film **films, int n_ranks, double scale, float *host_r
 int rt_film_gather_p2p_rgb8(rt_film **films, int n_ranks, double scale, uint8_t *host_rgb8);
 
 /* ----------------------------------------------------------------------------------------------
+ * Displayed frames of a multi-GPU render: tiles stored straight into the owner's image over NVLink
+ * -------------------------------------------------------------------------------------------- */
+
+/* A frame is a row-major width x height RGB8 image in the memory of one GPU (its owner, normally rank 0: the GPU
+ * that shows or downloads it) plus one arrival flag per rank.  Every rank holds a HANDLE to the same memory:
+ *   owner                      rt_frame_create
+ *   another process            rt_frame_export on the owner -> 64 opaque bytes (a CUDA IPC handle; send them by any
+ *                              means) -> rt_frame_open in the other process
+ *   another GPU, same process  rt_frame_attach (peer access)
+ * Per displayed frame, in the same order on every rank (replaces DynamicCamera::update_texture + the per-frame
+ * full-buffer copy, DynamicCamera.cpp:280-306,519-554):
+ *   every rank (owner included)  rt_film_present   to_byte(scale * sum) of the film's own tiles, stored into their
+ *                                                  rows of the frame (remote ranks: NVLink stores), then the rank's
+ *                                                  arrival flag; first waits until the owner consumed the frame's
+ *                                                  previous content
+ *   owner                        rt_frame_wait     the owner's stream waits (on the device) for all ranks
+ *                                rt_frame_download copy to host memory on the frame's own copy stream (overlaps the
+ *                                                  next render), then mark the frame consumed
+ *                             or rt_frame_release  mark it consumed without a copy
+ * All calls are asynchronous except rt_frame_download_wait.  Waits are bounded: a rank that never presents sets
+ * the frame's error word (rt_frame_error) after ~3 s instead of hanging the device.  No cudaMalloc, no collective
+ * and no staging copy happens per frame. */
+typedef struct rt_frame rt_frame;
+int rt_frame_create(rt_context *ctx, int width, int height, int n_ranks, rt_frame **out);
+int rt_frame_export(rt_frame *frame, unsigned char handle[64]);
+int rt_frame_open(rt_context *ctx, const unsigned char handle[64], int width, int height, int n_ranks, rt_frame **out);
+int rt_frame_attach(rt_context *ctx, rt_frame *owner_frame, rt_frame **out);
+void rt_frame_destroy(rt_frame *frame);
+uint64_t rt_frame_device_ptr(rt_frame *frame); /* the RGB8 image, as seen from this handle's device */
+int rt_film_present(rt_film *film, double scale, rt_frame *frame);
+int rt_frame_wait(rt_frame *frame);
+int rt_frame_release(rt_frame *frame);
+int rt_frame_download(rt_frame *frame, uint8_t *host_rgb8); /* host_rgb8: width*height*3 bytes, pinned for overlap */
+int rt_frame_download_wait(rt_frame *frame);                /* blocks until the download is in host memory */
+int rt_frame_error(rt_frame *frame);                        /* 0 = fine, 1 = a wait timed out, < 0 = CUDA error */
+
+/* ----------------------------------------------------------------------------------------------
  * Counters (tracing / profiling aid)
  * -------------------------------------------------------------------------------------------- */
 

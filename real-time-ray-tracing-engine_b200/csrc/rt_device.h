@@ -366,6 +366,30 @@ RT_HD bool sphere_hit(float4 r0, float4 r1, const Ray &ray, float tmin, float tm
   return true;
 }
 
+// The same for a ray that STARTS on this sphere (the segment before ended on it): of the two roots, the one at the
+// origin is not a hit.  In the reference's FP64 that root is ~1e-13 and the interval's lower bound 0.001 removes
+// it (Camera.cpp:242); in FP32 the origin lies up to a few 1e-5 off a radius-1000 sphere and, at grazing
+// directions, the spurious root lands on either side of 0.001 by rounding noise alone.  So the decision is taken
+// geometrically: a ray leaving towards the outside (h <= 0) cannot meet a sphere again, a ray entering it meets
+// the far root only.
+RT_HD bool sphere_hit_from_surface(float4 r0, float4 r1, const Ray &ray, float tmin, float tmax, float &t_out) {
+  f3 center = F3(r0.x, r0.y, r0.z) + ray.time * F3(r1.x, r1.y, r1.z);
+  float radius = r0.w;
+  f3 oc = center - ray.o;
+  float h = dot(ray.d, oc);
+  if (!(h > 0.f))
+    return false;
+  float a = dot(ray.d, ray.d);
+  float inv_a = 1.0f / a;
+  f3 perp = oc - (h * inv_a) * ray.d;
+  float disc = a * (radius * radius - dot(perp, perp));
+  float root = (h + sqrtf(fmaxf(disc, 0.f))) * inv_a; // on the surface |perp| <= radius up to rounding
+  if (!(tmin < root && root < tmax))
+    return false;
+  t_out = root;
+  return true;
+}
+
 // Plane::hit (Plane.cpp:78-112): closed interval on t and on the planar coordinates.
 RT_HD bool quad_hit(float4 r0, float4 r1, float4 r2, float qz, const Ray &ray, float tmin, float tmax,
                     float &t_out) {
@@ -449,10 +473,11 @@ struct RayKey {
 #define RT_STAT_LEAF()
 #endif
 
-RT_HD void leaf_test(const DScene &sc, int prim, const Ray &ray, float tmin, Hit &hit, int skip_prim,
+// start_prim: the surface primitive the ray starts on (the previous segment's hit; -1 for camera rays, rays
+// scattered inside a medium and the parity hook).  A flat primitive cannot be met again, a sphere only at its
+// far root (sphere_hit_from_surface).
+RT_HD void leaf_test(const DScene &sc, int prim, const Ray &ray, float tmin, Hit &hit, int start_prim,
                      const RayKey &key) {
-  if (prim == skip_prim)
-    return;
   RT_STAT_LEAF();
   const float4 *rec = sc.prims + (size_t)prim * RT_PRIM_F4;
   float4 r0 = ldg4(rec), r3 = ldg4(rec + 3);
@@ -460,9 +485,10 @@ RT_HD void leaf_test(const DScene &sc, int prim, const Ray &ray, float tmin, Hit
   float t;
   bool ok;
   if (type == RT_PT_SPHERE) {
-    ok = sphere_hit(r0, ldg4(rec + 1), ray, tmin, hit.t, t);
+    float4 r1 = ldg4(rec + 1);
+    ok = prim == start_prim ? sphere_hit_from_surface(r0, r1, ray, tmin, hit.t, t) : sphere_hit(r0, r1, ray, tmin, hit.t, t);
   } else if (type == RT_PT_QUAD) {
-    ok = quad_hit(r0, ldg4(rec + 1), ldg4(rec + 2), r3.x, ray, tmin, hit.t, t);
+    ok = prim != start_prim && quad_hit(r0, ldg4(rec + 1), ldg4(rec + 2), r3.x, ray, tmin, hit.t, t);
   } else {
     Uniform4 u = philox_uniform4(key.seed, key.pixel, key.sample, key.bounce,
                                  (uint32_t)(RT_STREAM_MEDIUM0 + f2i(r0.w)), 0);
@@ -847,6 +873,7 @@ RT_HD bool shade_segment(const DScene &sc, const Ray &ray, Hit hit, f3 throughpu
     p = center + r0.w * outward; // keep the point on the surface (FP32 drift on large spheres)
     front = dot(ray.d, outward) < 0.f;
     normal = front ? outward : -outward;
+    out.next_skip_prim = hit.prim; // the next ray starts on this sphere: only its far root counts (leaf_test)
     if (wants_uv)
       sphere_uv(outward, tex_u, tex_v);
   } else if (type == RT_PT_QUAD) {
@@ -900,7 +927,6 @@ RT_HD bool shade_segment(const DScene &sc, const Ray &ray, Hit hit, f3 throughpu
       out.next.d = perp + parallel;
     }
     out.throughput = throughput;
-    out.next_skip_prim = -1;
     return true;
   }
 

@@ -185,8 +185,30 @@ RT_HD bool medium_hit_exact(const ExactScene &sc, const PrimExact &m, const RayD
 // Leaf test with the reference list's tie rule: of two primitives hitting at exactly the same t,
 // the one later in the reference's scan order (object, then member order) wins iff it uses the
 // closed interval test (quads); see oracle/rt_oracle.c bvh_walk.
+// The render path's rule for the primitive a ray starts on (rt_device.h, sphere_hit_from_surface), in FP64: a
+// sphere is met at its far root only, and only by a ray that enters it.
+RT_HD bool sphere_hit_from_surface_exact(const PrimExact &p, const RayD &r, double tmin, double tmax, bool closed_max,
+                                         double &t_out, int &front) {
+  double center[3] = {p.a[0] + r.time * p.b[0], p.a[1] + r.time * p.b[1], p.a[2] + r.time * p.b[2]};
+  double oc[3] = {center[0] - r.o[0], center[1] - r.o[1], center[2] - r.o[2]};
+  double a = dot3(r.d, r.d);
+  double h = dot3(r.d, oc);
+  if (!(h > 0))
+    return false;
+  double c = dot3(oc, oc) - p.s * p.s;
+  double disc = h * h - a * c;
+  double root = (h + sqrt(disc > 0 ? disc : 0)) / a;
+  if (!(tmin < root && (closed_max ? root <= tmax : root < tmax)))
+    return false;
+  t_out = root;
+  front = 0; // leaving through the far side
+  return true;
+}
+
+// start_prim: -1 for the parity hook (the reference's own semantics); the audit of the render path passes the
+// primitive the ray starts on.
 RT_HD void leaf_test_exact(const ExactScene &sc, int prim, const RayD &ray, double tmin, HitD &hit,
-                           const RayKey &key) {
+                           const RayKey &key, int start_prim = -1) {
   const PrimExact &p = sc.prims[prim];
   bool have = hit.prim >= 0;
   double t;
@@ -199,9 +221,10 @@ RT_HD void leaf_test_exact(const ExactScene &sc, int prim, const RayD &ray, doub
   } else {
     RayD r = to_object_space(sc, p.xform, ray);
     if (p.type == RT_PT_SPHERE)
-      ok = sphere_hit_exact(p, r, tmin, hit.t, have, t, front);
+      ok = prim == start_prim ? sphere_hit_from_surface_exact(p, r, tmin, hit.t, have, t, front)
+                              : sphere_hit_exact(p, r, tmin, hit.t, have, t, front);
     else
-      ok = quad_hit_exact(p, r, tmin, hit.t, t, front);
+      ok = prim != start_prim && quad_hit_exact(p, r, tmin, hit.t, t, front);
     if (ok && have && t == hit.t) {
       const PrimExact &b = sc.prims[hit.prim];
       bool later = p.object > b.object || (p.object == b.object && p.id > b.id);
@@ -219,10 +242,10 @@ RT_HD void leaf_test_exact(const ExactScene &sc, int prim, const RayD &ray, doub
   }
 }
 
-// skip_prim (leaf order, -1 = none): the primitive the ray starts on and cannot hit again (a flat primitive the
-// render path's previous segment ended on, rt_device.h shade_segment); the parity hook passes -1.
+// start_prim (leaf order, -1 = none): the surface primitive the ray starts on (rt_device.h leaf_test); the parity
+// hook passes -1.
 RT_HD void traverse_exact(const ExactScene &sc, const RayD &ray, double tmin, double tmax, HitD &hit,
-                          const RayKey &key, int skip_prim = -1) {
+                          const RayKey &key, int start_prim = -1) {
   hit.t = tmax;
   hit.prim = -1;
   hit.front = 0;
@@ -235,8 +258,7 @@ RT_HD void traverse_exact(const ExactScene &sc, const RayD &ray, double tmin, do
   while (sp > 0) {
     int ref = stack[--sp];
     if (ref < 0) {
-      if (~ref != skip_prim)
-        leaf_test_exact(sc, ~ref, ray, tmin, hit, key);
+      leaf_test_exact(sc, ~ref, ray, tmin, hit, key, start_prim);
       continue;
     }
     const float4 *n = sc.nodes + (size_t)ref * RT_NODE_F4;

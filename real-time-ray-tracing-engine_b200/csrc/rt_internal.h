@@ -93,7 +93,12 @@ struct rt_context {
                            // fastest, even at depth 50; shorter spans chain launches through the queues)
   int64_t pass_paths = (int64_t)16 << 20; // static renders: paths per wavefront pass (queue storage ~110 B per
                                           // path; measured 4 M / 8 M / 16 M / 32 M: 16 M is fastest on C1 and C3)
-  bool fused_generate = true; // the first extend launch derives the camera rays (no k_generate, no queue 0)
+  // RT_FUSED_GENERATE=1: the first extend launch derives the camera rays itself and the first shade launch
+  // re-derives them (no k_generate launch, queue 0 never written: 64 B per path of queue memory and traffic less).
+  // Measured on B200 (profiles/r02_experiments.md): the saved launch (0.025 ms on C2) and traffic are paid back by
+  // the camera-ray arithmetic done twice at the extend kernel's lane utilisation (+0.014 ms extend, +0.013 ms
+  // shade), so the separate k_generate stays the default.
+  bool fused_generate = false;
   bool audit = false; // every extend launch is checked against the FP64 parity traversal (all-wavefront schedule)
   bool stats = false; // instrumented extend / tail kernels count node visits and primitive tests
   cudaStream_t stream = nullptr;
@@ -186,6 +191,11 @@ void launch_resolve_rgb8(cudaStream_t s, const float4 *film, int64_t n, double s
 void launch_resolve_rgb(cudaStream_t s, const float4 *film, int64_t n, double scale, float *out);
 void launch_scatter_gathered(cudaStream_t s, int width, int height, int n_ranks, int tile_rows, const void *gathered,
                              void *full, int bytes_per_pixel); // 16: float4 sums, 3: RGB8
+
+// displayed frames (rt_frame.cu)
+void launch_present_rgb8(const rt_context *ctx, cudaStream_t stream, const float4 *accum, int64_t n_owned, int width,
+                         int tile_rows, int rank, int n_ranks, double scale, uint8_t *frame, unsigned int *blocks_done,
+                         uint32_t *flag, uint32_t ticket);
 
 // parity audit (rt_exact.cu)
 void launch_audit_trace(const rt_context *ctx, const ExactScene &sc, const PassParams &pp, WaveBuffers &w, int bounce,

@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(RT_BLOCK, 8)
         }
         do {
           if (STATS)
-            n_tests += ~ref != skip;
+            n_tests++;
           leaf_test(sc, ~ref, r, RT_T_MIN, best, skip, key);
           if (!stack_pop(stack, sp, best.t, ref))
             ref = RT_DONE;
@@ -385,6 +385,8 @@ __global__ void __launch_bounds__(RT_SHADE_THREADS, RT_SHADE_BLOCKS * RT_BLOCK /
       if (GEN) {
         path = q;
         r = path_camera_ray(pp, q);
+        // opaque to the optimiser from here on, like the loaded ray of the other instantiation
+        asm volatile("" : "+f"(r.o.x), "+f"(r.o.y), "+f"(r.o.z), "+f"(r.d.x), "+f"(r.d.y), "+f"(r.d.z), "+f"(r.time));
         ht.prim = __float_as_int(h.y);
       } else {
         float4 a = ldg4_now(ray_a + q), b = ldg4_now(ray_b + q);
@@ -584,7 +586,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_TAIL_BLOCKS)
         }
         do {
           if (STATS)
-            n_tests += ~ref != skip;
+            n_tests++;
           leaf_test(sc, ~ref, r, RT_T_MIN, best, skip, key);
           if (!stack_pop(stack, sp, best.t, ref))
             ref = RT_DONE;

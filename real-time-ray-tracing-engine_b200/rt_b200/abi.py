@@ -170,6 +170,18 @@ RT_B200_SYMBOLS = {
                                                 C.c_void_p]),
     "rt_film_gather_p2p": (C.c_int, [P(C.c_void_p), C.c_int, C.c_double, P(C.c_float)]),
     "rt_film_gather_p2p_rgb8": (C.c_int, [P(C.c_void_p), C.c_int, C.c_double, P(C.c_uint8)]),
+    "rt_frame_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, VOIDPP]),
+    "rt_frame_export": (C.c_int, [C.c_void_p, P(C.c_ubyte)]),
+    "rt_frame_open": (C.c_int, [C.c_void_p, P(C.c_ubyte), C.c_int, C.c_int, C.c_int, VOIDPP]),
+    "rt_frame_attach": (C.c_int, [C.c_void_p, C.c_void_p, VOIDPP]),
+    "rt_frame_destroy": (None, [C.c_void_p]),
+    "rt_frame_device_ptr": (C.c_uint64, [C.c_void_p]),
+    "rt_film_present": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p]),
+    "rt_frame_wait": (C.c_int, [C.c_void_p]),
+    "rt_frame_release": (C.c_int, [C.c_void_p]),
+    "rt_frame_download": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rt_frame_download_wait": (C.c_int, [C.c_void_p]),
+    "rt_frame_error": (C.c_int, [C.c_void_p]),
     "rt_get_counters": (C.c_int, [C.c_void_p, P(rt_counters)]),
     "rt_reset_counters": (C.c_int, [C.c_void_p]),
     "rt_context_set_stats": (C.c_int, [C.c_void_p, C.c_int]),

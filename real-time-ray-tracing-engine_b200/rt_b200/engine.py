@@ -192,3 +192,53 @@ def render_strata(scene, camera, film, first_stratum, n_strata, sqrt_spp, max_de
     """n_strata consecutive strata in one wavefront pass, added to the film.  Asynchronous."""
     abi.check(scene.lib, scene.lib.rt_render_strata(scene._h, C.byref(camera), film._h, first_stratum, n_strata,
                                                     sqrt_spp, max_depth, seed), "rt_render_strata")
+
+
+class Frame:
+    """The displayed RGB8 frame of a (multi-GPU) render in its owner's memory (include/rt_b200.h, "Displayed
+    frames"): every rank stores its own tiles straight into it (`present`), the owner waits / downloads."""
+
+    def __init__(self, ctx, width, height, n_ranks=1, ipc_handle=None, attach_to=None):
+        self.ctx, self.lib = ctx, ctx.lib
+        self.width, self.height, self.n_ranks = width, height, n_ranks
+        h = C.c_void_p()
+        if ipc_handle is not None:  # another process's frame
+            buf = (C.c_ubyte * 64).from_buffer_copy(bytes(ipc_handle))
+            abi.check(self.lib, self.lib.rt_frame_open(ctx._h, buf, width, height, n_ranks, C.byref(h)), "rt_frame_open")
+        elif attach_to is not None:  # another GPU of this process
+            abi.check(self.lib, self.lib.rt_frame_attach(ctx._h, attach_to._h, C.byref(h)), "rt_frame_attach")
+        else:
+            abi.check(self.lib, self.lib.rt_frame_create(ctx._h, width, height, n_ranks, C.byref(h)), "rt_frame_create")
+        self._h = h
+
+    def export(self):
+        buf = (C.c_ubyte * 64)()
+        abi.check(self.lib, self.lib.rt_frame_export(self._h, buf), "rt_frame_export")
+        return bytes(buf)
+
+    @property
+    def device_ptr(self):
+        return self.lib.rt_frame_device_ptr(self._h)
+
+    def present(self, film, scale):
+        abi.check(self.lib, self.lib.rt_film_present(film._h, scale, self._h), "rt_film_present")
+
+    def wait(self):
+        abi.check(self.lib, self.lib.rt_frame_wait(self._h), "rt_frame_wait")
+
+    def release(self):
+        abi.check(self.lib, self.lib.rt_frame_release(self._h), "rt_frame_release")
+
+    def download(self, host_ptr):
+        abi.check(self.lib, self.lib.rt_frame_download(self._h, C.c_void_p(host_ptr)), "rt_frame_download")
+
+    def download_wait(self):
+        abi.check(self.lib, self.lib.rt_frame_download_wait(self._h), "rt_frame_download_wait")
+
+    def error(self):
+        return self.lib.rt_frame_error(self._h)
+
+    def close(self):
+        if self._h:
+            self.lib.rt_frame_destroy(self._h)
+            self._h = None

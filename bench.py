@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Benchmark of the path-tracing hot path (BASELINE.json: Mpath-samples/s, ms/frame at 1 spp).
+"""Benchmark of the path-tracing hot path (BASELINE.json: Mpath-samples/s, ms/frame at 1 spp, RMSE vs ref).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
@@ -7,22 +7,32 @@ Workload (BASELINE.json configs[1]): the reference's random-spheres scene (485 o
 1920x1080, depth 8, progressive dynamic-mode frames.  One step = one frame: one new stratum for every
 pixel.  With N GPUs the image is cut into 8-scanline tiles interleaved over the ranks and per-GPU work is
 kept constant (weak scaling): a step renders N strata of the whole frame, each rank tracing N strata of
-its own 1/N of the tiles, and the compact films are gathered to rank 0 (NCCL over NVLink) and scattered
-into the full frame at the end of every step (RGB8, after the device tone map).
+its own 1/N of the tiles; every step ends with the displayed frame: each rank tone-maps its tiles and stores
+them straight into rank 0's row-major RGB8 frame over NVLink (rt_film_present, CUDA IPC peer stores + one
+arrival flag per rank), rank 0 waits for the flags on the device.
 
 Printed JSON (one line, rank 0):
-  value      whole-job Mpath-samples/s with the scene resident in HBM, device-timed (CUDA events, max over ranks)
-  e2e        the same metric through the reference-facing call sequence with HOST buffers: camera parameters
-             in (kernel arguments), render, device to_byte resolve, RGB8 frame copied back to host memory
-  roofline   the extend kernel (BVH traversal + primitive tests): algorithmic bytes / its measured duration
-  cpu_baseline  the reference's own CPU implementation (oracle/_ref, all host threads) on the same frame
+  value        whole-job Mpath-samples/s with the scene resident in HBM, device-timed (CUDA events, max over ranks)
+  e2e          the same metric through the reference-facing call sequence with HOST buffers: camera parameters
+               in (kernel arguments), render, present, RGB8 frame copied back to pinned host memory
+  roofline     the extend kernel (BVH traversal + primitive tests): algorithmic flops / its measured duration
+               against the FP32 issue peak (the kernel is issue / divergence bound, not HBM bound), with the
+               issue-slot, HBM, L1 and L2 views beside it
+  rmse         BASELINE config 1 (400x225, 100 spp, depth 50) rendered on the GPU against the reference's own CPU
+               render of it (oracle/_ref): RMSE, the reference-vs-reference RMSE floor, ratio, luminance
+  parity       fast_vs_exact: the FP32 product traversal against the FP64 parity traversal (the reference's
+               arithmetic) on EVERY segment of one 1080p frame; how often they name a different primitive
+  static_4k    strong scaling: the final scene at 3840x2160, 16 spp, depth 50 - fixed total work over the N GPUs -
+               with the SHA-256 of the assembled RGB8 frame (identical for every N)
+  frame_sha    SHA-256 of one assembled 1080p frame of the benchmark scene (stratum 0, fixed seed; identical for every N)
+  cpu_baseline the reference's own CPU implementation (oracle/_ref, all host threads) on the same frame
 `--impl reference` times only that CPU implementation.
 """
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -38,6 +48,7 @@ METRIC = "Mpath-samples/s (spheres scene, 1920x1080, 1 spp per frame, depth 8)"
 NODE_TESTS_PER_SEGMENT, SPHERE_TESTS_PER_SEGMENT = 26.0, 1.71
 BYTES_PER_SEGMENT = 32.0 * NODE_TESTS_PER_SEGMENT + 32.0 * SPHERE_TESTS_PER_SEGMENT + 128.0
 FLOPS_PER_SEGMENT = 20.0 * NODE_TESTS_PER_SEGMENT + 30.0 * SPHERE_TESTS_PER_SEGMENT + 150.0
+LUM = (0.2126, 0.7152, 0.0722)
 
 
 class ClockSampler(threading.Thread):
@@ -117,6 +128,58 @@ def cpu_reference_frame(n_frames, threads=None):
                                        "sample": f"rows {(height - rows) // 2}..{(height - rows) // 2 + rows} of one 1920x1080 frame, 1 spp, depth 8"}
 
 
+def reference_render(name, p0, p1, width, spp, depth, seed, aspect=None):
+    """The reference's own CPU render (oracle/_ref, all host threads) of a built-in scene: (image [H,W,3] f64, s, cores)."""
+    import numpy as np
+
+    import oracle_lib as ol
+    from rt_b200 import abi
+
+    r = ol.ref()
+    h = r.ref_scene_build(name.encode(), SCENE_SEED, p0, p1)
+    cfg = abi.rt_camera_config()
+    r.ref_scene_camera_config(h, width, spp, depth, cfg)
+    if aspect:
+        cfg.aspect_ratio = aspect
+    cam = abi.rt_camera()
+    r.ref_camera_init(cfg, cam)
+    n = cam.image_width * cam.image_height
+    img = (C.c_double * (n * 3))()
+    seg = C.c_uint64()
+    cores = r.ref_hardware_threads()
+    r.ref_render(h, 32, 1, 2, 1, 1, 1, 0, -1, -1, img, C.byref(seg))  # build the BVH outside the timed call
+    secs = r.ref_render(h, width, spp, depth, seed, 1, cores, 0, cam.image_height, -1, img, C.byref(seg))
+    out = np.nan_to_num(np.frombuffer(img, dtype=np.float64).reshape(cam.image_height, cam.image_width, 3).copy())
+    r.ref_scene_free(h)
+    return out, secs, cores
+
+
+def image_distance(got, ref_a, ref_b):
+    """RMSE of `got` against the reference render `ref_a`, beside the RMSE between two reference renders with
+    different seeds (the Monte-Carlo noise floor at this sample count), per pixel and on 8x8-pixel block means
+    (noise / 8, so a spatially coherent bias shows); values clipped at 4.0 (fireflies)."""
+    import numpy as np
+
+    def clip(x):
+        return np.minimum(x, 4.0)
+
+    def blocks(x, b=8):
+        h, w = (x.shape[0] // b) * b, (x.shape[1] // b) * b
+        return x[:h, :w].reshape(h // b, b, w // b, b, 3).mean(axis=(1, 3))
+
+    def rmse(a, b):
+        return float(np.sqrt(np.mean((a - b) ** 2)))
+
+    g, a, b = clip(got.astype(np.float64)), clip(ref_a), clip(ref_b)
+    lum = np.array(LUM)
+    l_ref = float(0.5 * ((ref_a @ lum).mean() + (ref_b @ lum).mean()))
+    l_got = float((got.astype(np.float64) @ lum).mean())
+    floor, floor_b = rmse(a, b), rmse(blocks(a), blocks(b))
+    return {"rmse": rmse(g, a), "rmse_floor_ref_vs_ref": floor, "ratio": rmse(g, a) / floor,
+            "block8_rmse": rmse(blocks(g), blocks(a)), "block8_floor": floor_b, "block8_ratio": rmse(blocks(g), blocks(a)) / floor_b,
+            "mean_luminance": l_got, "mean_luminance_reference": l_ref, "luminance_rel_diff": (l_got - l_ref) / l_ref}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -140,11 +203,10 @@ def run_reference(args):
 
 
 def run_ours(args):
-    import numpy as np
     import torch
     import torch.distributed as dist
 
-    from rt_b200 import abi, distributed, engine, host
+    from rt_b200 import abi, engine, host
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -171,14 +233,53 @@ def run_ours(args):
     while sqrt_spp * sqrt_spp < strata_per_step:  # smallest stratification grid holding N strata
         sqrt_spp += 1
 
-    owned = distributed.owned_pixels(W, H, rank, world, TILE_ROWS)
-    accum = torch.zeros((owned, 4), dtype=torch.float32, device="cuda")
-    own_rgb8 = torch.zeros((owned, 3), dtype=torch.uint8, device="cuda")  # this rank's tiles, tone-mapped
-    rgb8_dev = torch.zeros((npix, 3), dtype=torch.uint8, device="cuda") if rank == 0 else None
-    rgb8_host = torch.zeros((npix, 3), dtype=torch.uint8).pin_memory() if rank == 0 else None
-    torch.cuda.synchronize()
-    film = engine.Film(ctx, W, H, rank, world, TILE_ROWS, external_accum=accum.data_ptr())
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def all_max(x):
+        t = torch.tensor([float(x)], device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_sum(values):
+        t = torch.tensor([float(v) for v in values], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t)
+        return [float(v) for v in t.tolist()]
+
+    def shared_frames(width, height, count):
+        """`count` displayed frames in rank 0's memory; every other rank maps them through CUDA IPC."""
+        if rank == 0:
+            made = [engine.Frame(ctx, width, height, world) for _ in range(count)]
+            handles = [f.export() for f in made] if world > 1 else []
+        else:
+            made, handles = [], None
+        if world > 1:
+            box = [handles]
+            dist.broadcast_object_list(box, src=0)
+            if rank != 0:
+                made = [engine.Frame(ctx, width, height, world, ipc_handle=h) for h in box[0]]
+            dist.barrier()
+        return made
+
+    def close_frames(made):
+        barrier()
+        if rank != 0:  # mappings go before the allocation they map
+            for f in made:
+                f.close()
+        barrier()
+        if rank == 0:
+            for f in made:
+                f.close()
+
+    film = engine.Film(ctx, W, H, rank, world, TILE_ROWS)
+    frames = shared_frames(W, H, 2)  # two displayed frames: the copy of one overlaps the render of the next
+    rgb8_host = [torch.zeros((npix, 3), dtype=torch.uint8).pin_memory() for _ in range(2)] if rank == 0 else None
     l2_flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
 
     def render_step(step):
         """One progressive step on the context stream: `strata_per_step` strata for this rank's tiles."""
@@ -187,28 +288,13 @@ def run_ours(args):
         else:  # the step's strata in ONE wavefront pass (same launch count as a single-GPU frame)
             engine.render_strata(scene, cam, film, 0, strata_per_step, sqrt_spp, DEPTH, 1000 + step)
 
-    def present(step, frame_dev):
-        """The displayed frame: every rank tone-maps its own tiles to RGB8 on the device (DynamicCamera::
-        update_texture, to_byte); with several GPUs the RGB8 tiles (3 bytes per pixel) are gathered to rank 0 over
-        NCCL / NVLink and scattered into the row-major frame."""
-        scale = 1.0 / max(1, film.samples)
-        if world == 1:
-            abi.check(ctx.lib, ctx.lib.rt_film_resolve_rgb8_device(film._h, scale, frame_dev.data_ptr()),
-                      "rt_film_resolve_rgb8_device")
-            return
-        abi.check(ctx.lib, ctx.lib.rt_film_resolve_rgb8_device(film._h, scale, own_rgb8.data_ptr()),
-                  "rt_film_resolve_rgb8_device")
-        with torch.cuda.stream(stream):
-            gathered = distributed.gather_film(own_rgb8, W, H, TILE_ROWS, dst=0)
-            if rank == 0:
-                abi.check(ctx.lib, ctx.lib.rt_film_scatter_gathered_rgb8(ctx._h, W, H, world, TILE_ROWS,
-                                                                         gathered.data_ptr(), frame_dev.data_ptr()),
-                          "rt_film_scatter_gathered_rgb8")
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def present(frame):
+        """The displayed frame: to_byte of this rank's tiles (DynamicCamera::update_texture) stored into their rows of
+        rank 0's frame - local stores on rank 0, NVLink stores elsewhere - and the rank's arrival flag; rank 0's
+        stream then waits for every rank's flag."""
+        frame.present(film, 1.0 / max(1, film.samples))
+        if rank == 0:
+            frame.wait()
 
     def flush_only(s):
         with torch.cuda.stream(stream):
@@ -217,7 +303,9 @@ def run_ours(args):
     def device_step(s):
         flush_only(s)
         render_step(s)
-        present(s, rgb8_dev)
+        present(frames[0])
+        if rank == 0:
+            frames[0].release()
 
     def timed(n_steps):
         """Device time of n_steps steps on the context stream (ms per step, max over ranks).  Every step is
@@ -229,13 +317,12 @@ def run_ours(args):
             flush_only(s)
             e0.record(stream)
             render_step(s)
-            present(s, rgb8_dev)
+            present(frames[0])
+            if rank == 0:
+                frames[0].release()
             e1.record(stream)
         barrier()
-        ms = torch.tensor([sum(e0.elapsed_time(e1) for e0, e1 in pairs) / n_steps], device="cuda")
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return all_max(sum(e0.elapsed_time(e1) for e0, e1 in pairs) / n_steps)
 
     # ---- device-resident throughput ----
     for s in range(args.warmup):
@@ -254,57 +341,50 @@ def run_ours(args):
     #  here the tone map runs on the device and 3 bytes per pixel cross PCIe instead of 24)
     def e2e_step(s):
         render_step(s)
-        present(s, rgb8_dev)
+        present(frames[0])
         if rank == 0:
-            with torch.cuda.stream(stream):
-                rgb8_host.copy_(rgb8_dev, non_blocking=True)
-        ctx.synchronize()
+            frames[0].download(rgb8_host[0].data_ptr())
+            frames[0].download_wait()
+        else:
+            ctx.synchronize()
 
-    def wall_ms_per_step(step_fn):
+    def wall_ms_per_step(step_fn, finish=None):
         for s in range(args.warmup):
             step_fn(s)
+        if finish:
+            finish()
         ctx.synchronize()
         barrier()
         t0 = time.perf_counter()
         for s in range(args.steps):
             step_fn(s)
+        if finish:
+            finish()
         ctx.synchronize()
         barrier()
-        wall = torch.tensor([(time.perf_counter() - t0) / args.steps * 1e3], device="cuda")
-        if world > 1:
-            dist.all_reduce(wall, op=dist.ReduceOp.MAX)
-        return float(wall.item())
+        return all_max((time.perf_counter() - t0) / args.steps * 1e3)
 
     e2e_sync_ms = wall_ms_per_step(e2e_step)  # frame latency: host blocks until the frame is in host memory
 
-    # Pipelined presentation (what an interactive viewer does): the RGB8 frame of step s is copied to pinned
-    # host memory on a copy stream while step s+1 renders; two device + two host buffers, every frame still
-    # reaches the host.
-    copy_stream = torch.cuda.Stream()
-    if rank == 0:
-        rgb8_dev2 = [rgb8_dev, torch.zeros_like(rgb8_dev)]
-        rgb8_host2 = [rgb8_host, torch.zeros((npix, 3), dtype=torch.uint8).pin_memory()]
-        resolved = [torch.cuda.Event(), torch.cuda.Event()]
-        copied = [torch.cuda.Event(), torch.cuda.Event()]
-        for ev in copied:
-            ev.record(copy_stream)
-
+    # Pipelined presentation (what an interactive viewer does): the RGB8 frame of step s goes to pinned host memory
+    # on the frame's copy stream while step s+1 renders; two frames + two host buffers, every frame reaches the host.
     def e2e_pipelined_step(s):
-        render_step(s)
         k = s & 1
+        render_step(s)
+        if rank == 0 and s >= 2:
+            frames[k].download_wait()  # host buffer k (frame s-2) is complete before it is reused
+        present(frames[k])
         if rank == 0:
-            stream.wait_event(copied[k])  # the buffer's previous frame has left the device
-        present(s, rgb8_dev2[k] if rank == 0 else None)
-        if rank == 0:
-            resolved[k].record(stream)
-            copy_stream.wait_event(resolved[k])
-            with torch.cuda.stream(copy_stream):
-                rgb8_host2[k].copy_(rgb8_dev2[k], non_blocking=True)
-            copied[k].record(copy_stream)
+            frames[k].download(rgb8_host[k].data_ptr())
 
-    e2e_ms = wall_ms_per_step(e2e_pipelined_step)
-    copy_stream.synchronize()
+    def drain():
+        if rank == 0:
+            frames[0].download_wait()
+            frames[1].download_wait()
+
+    e2e_ms = wall_ms_per_step(e2e_pipelined_step, drain)
     e2e_value = paths_per_step / e2e_ms / 1e3
+    frame_error = (frames[0].error() | frames[1].error()) if rank == 0 else 0
 
     # ---- roofline of the dominant kernel (k_extend), measured live with per-launch events ----
     ctx.set_stage_timing(True)
@@ -322,32 +402,52 @@ def run_ours(args):
         sampler.join()
     extend_ms_per_launch = stage_ms[1] / max(1, stage_n[1])
     seg_per_launch = seg / max(1, stage_n[1])
+
+    # ---- traversal statistics measured on the GPU (instrumented kernels, outside any timed region) ----
+    ctx.set_stats(True)
+    ctx.reset_counters()
+    render_step(0)
+    stat = ctx.counters()
+    queues = ctx.queue_lengths(DEPTH + 1)
+    ctx.set_stats(False)
+    stat_sum = all_sum([stat.nodes_visited, stat.prim_tests, stat.segments])
+
+    # ---- parity of the FP32 product traversal: every segment of one frame against the FP64 parity traversal ----
+    film.clear()
+    ctx.set_audit(True)
+    engine.render_accumulate(scene, cam, film, 0, 0, 1, DEPTH, 1000)
+    a = ctx.audit()
+    ctx.set_audit(False)
+    audit_sum = all_sum([a.segments, a.prim_mismatch, a.primary_segments, a.primary_mismatch, a.hit_miss_flips])
+    audit_max_t = all_max(a.max_rel_t_error)
+
+    # ---- SHA of one assembled frame (stratum 0, fixed seed): the same bytes for every GPU count ----
+    film.clear()
+    engine.render_accumulate(scene, cam, film, 0, 0, 1, DEPTH, 4242)
+    present(frames[1])
+    frame_sha = None
+    if rank == 0:
+        frames[1].download(rgb8_host[1].data_ptr())
+        frames[1].download_wait()
+        frame_sha = hashlib.sha256(rgb8_host[1].numpy().tobytes()).hexdigest()
+    barrier()
+
+    # ---- strong scaling: the final scene at 4K, fixed total work over the N GPUs ----
+    static_4k = static_4k_leg(ctx, stream, world, rank, shared_frames, close_frames, barrier, all_max, all_sum)
+
+    # ---- BASELINE config 1 against the reference's own render (rank 0) ----
+    rmse = rmse_leg(ctx) if rank == 0 else None
+
     peaks = {}
     try:
         with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
             peaks = json.load(f)
     except Exception:
         pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = seg_per_launch * BYTES_PER_SEGMENT / (extend_ms_per_launch * 1e-3) / 1e9 if extend_ms_per_launch > 0 else 0.0
-    fp32_peak = 148 * 128 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
-    flops = seg_per_launch * FLOPS_PER_SEGMENT / (extend_ms_per_launch * 1e-3) / 1e12 if extend_ms_per_launch > 0 else 0.0
-    cache = {}
-    try:  # L1- / L2-resident read bandwidth measured on this pool (tools/cache_peaks): the levels that serve the BVH
-        with open(os.path.join(REPO, "profiles", "cache_peaks.json")) as f:
-            cache = json.load(f)
-    except Exception:
-        pass
-    traffic = None
-    try:
-        with open(os.path.join(REPO, "profiles", "extend_traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
-    except Exception:
-        pass
 
-    line = None
     if rank == 0:
         cpu_value, cpu_desc = cpu_reference_frame(3)
+        clocks = sampler.summary()
         line = {
             "metric": METRIC, "value": value, "unit": "Mpath-samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -356,53 +456,47 @@ def run_ours(args):
                 "workload": f"spheres scene (485 objects, seed 1234) 1920x1080, depth 8, dynamic-mode frames: "
                             f"{strata_per_step} stratum/strata of the whole frame per step (= 1 per GPU), "
                             f"{TILE_ROWS}-scanline tiles interleaved over {world} GPU(s), scene replicated; every step ends with "
-                            f"the displayed frame: device to_byte resolve of each rank's tiles, RGB8 tiles gathered to rank 0 "
-                            f"(NCCL) and scattered into the row-major frame",
+                            f"the displayed frame: each rank's to_byte tiles stored into rank 0's row-major RGB8 frame "
+                            f"(NVLink peer stores through CUDA IPC + arrival flags; no collective)",
                 "paths_per_step": paths_per_step, "segments_per_path": counters.segments / max(1, counters.paths),
                 "bvh": {"primitives": info.n_prims, "nodes4": info.n_nodes, "device_build_ms": info.build_ms},
                 "l2": "192 MiB buffer written before every timed step (outside the step's CUDA-event pair)"},
             "frame_ms": ms_step / strata_per_step,
             "e2e": {"value": e2e_value, "unit": "Mpath-samples/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": C.sizeof(abi.rt_camera), "d2h_bytes_per_step": npix * 3,
-                    "path": "rt_render_accumulate / rt_render_strata -> rt_film_resolve_rgb8_device -> pinned host RGB8 "
-                            "(copy of frame s overlaps the render of frame s+1; every frame reaches the host)",
+                    "path": "rt_render_accumulate / rt_render_strata -> rt_film_present -> rt_frame_wait -> rt_frame_download "
+                            "into pinned host RGB8 (the copy of frame s overlaps the render of frame s+1; every frame reaches the host)",
                     "frame_latency_ms": e2e_sync_ms,
-                    "frame_latency_note": "same call sequence with the host blocking until each frame is in host memory"},
+                    "frame_latency_note": "same call sequence with the host blocking until each frame is in host memory",
+                    "frame_wait_timeouts": int(frame_error)},
             "gpu_launches": int(counters.kernel_launches),
-            "roofline": {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": traffic,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
-                         "algorithmic_bytes_per_segment": BYTES_PER_SEGMENT, "segments_per_launch": seg_per_launch,
-                         "launch_ms": extend_ms_per_launch,
-                         "note": "working set is L1/L2 resident (0.06 MB scene); the algorithmic bytes are node/primitive "
-                                 "fetches + queue traffic, so this is an L1/L2 figure set against the HBM copy peak",
-                         "fp32": {"achieved_tflops": flops, "peak_tflops": fp32_peak, "frac": flops / fp32_peak},
-                         "on_chip": ({"note": "the same algorithmic bytes against the measured L1- and L2-resident read "
-                                              "bandwidth (profiles/cache_peaks.json, tools/cache_peaks): the BVH is served by L1",
-                                      "l1_peak": cache["l1_read_gbs"], "l1_frac": achieved / cache["l1_read_gbs"],
-                                      "l2_peak": cache["l2_read_gbs"], "l2_frac": achieved / cache["l2_read_gbs"]}
-                                     if cache.get("l1_read_gbs") and cache.get("l2_read_gbs") else None),
-                         "hbm_only": {"note": "bytes that must come from HBM per segment: the ray queue entry read (32 B) "
-                                              "+ skip primitive read and hit written (16 B); the BVH stays in L1/L2",
-                                      "bytes_per_segment": 48.0,
-                                      "achieved": seg_per_launch * 48.0 / (extend_ms_per_launch * 1e-3) / 1e9
-                                      if extend_ms_per_launch > 0 else 0.0,
-                                      "frac": (seg_per_launch * 48.0 / (extend_ms_per_launch * 1e-3) / 1e9 / hbm_peak)
-                                      if extend_ms_per_launch > 0 else 0.0},
-                         "stage_ms_per_frame": {k: stage_ms[i] / roof_steps / strata_per_step
-                                                for i, k in enumerate(["generate", "extend", "shade", "accumulate", "tail"])},
-                         "tail_segments_per_frame": roof_counters.tail_segments / roof_steps / strata_per_step},
+            "roofline": roofline_block(peaks, seg_per_launch, extend_ms_per_launch, stage_ms, roof_steps,
+                                       strata_per_step, roof_counters, clocks),
+            "traversal": {"note": "counted on the GPU by the instrumented kernels (rt_context_set_stats), one step",
+                          "node_visits_per_segment": stat_sum[0] / max(1.0, stat_sum[2]),
+                          "box_tests_per_segment": 4.0 * stat_sum[0] / max(1.0, stat_sum[2]),
+                          "primitive_tests_per_segment": stat_sum[1] / max(1.0, stat_sum[2]),
+                          "queue_lengths_rank0": queues},
+            "parity": {"fast_vs_exact": {
+                "what": "every ray segment of one 1920x1080 depth-8 frame: the FP32 product traversal (k_extend) against the "
+                        "FP64 parity traversal (the reference's arithmetic, bit-exact against the reference in tests/) of the same ray",
+                "segments": int(audit_sum[0]), "prim_mismatch": int(audit_sum[1]),
+                "mismatch_rate": audit_sum[1] / max(1.0, audit_sum[0]),
+                "primary_segments": int(audit_sum[2]), "primary_mismatch": int(audit_sum[3]),
+                "primary_mismatch_rate": audit_sum[3] / max(1.0, audit_sum[2]),
+                "hit_miss_flips": int(audit_sum[4]), "max_rel_t_error_same_prim": audit_max_t}},
+            "rmse": rmse,
+            "frame_sha": frame_sha,
+            "static_4k": static_4k,
             "cpu_baseline": dict(cpu_desc, value=cpu_value, unit="Mpath-samples/s"),
-            "clocks": sampler.summary(),
+            "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     # tear down in dependency order: torch buffers that were used on the context's stream go first (the
     # pinned-memory allocator records an event on that stream when a block is released)
-    barrier()
+    close_frames(frames)
     film.close()
-    if rank == 0:
-        del rgb8_dev2, rgb8_host2, resolved, copied
-    del accum, own_rgb8, rgb8_dev, rgb8_host, l2_flush, copy_stream
+    del rgb8_host, l2_flush
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
     scene.close()
@@ -412,6 +506,148 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def roofline_block(peaks, seg_per_launch, launch_ms, stage_ms, roof_steps, strata_per_step, roof_counters, clocks):
+    """The dominant kernel (k_extend) against the bound that limits it.  BVH traversal of an L1/L2-resident scene is
+    bound by instruction issue at the lane utilisation incoherent rays allow (ncu: 2.4-2.8 of 4 issue slots, 14-27
+    of 32 lanes, DRAM at 4-8 % of peak), so the headline fraction is the algorithmic FP32 rate over the FP32 issue
+    peak; the issue-slot, HBM, L1 and L2 views are sub-blocks.  ncu-derived constants come from the tracked
+    profiles/extend_ncu.json (tools/summarize_ncu.py); everything else is measured live."""
+    secs = launch_ms * 1e-3
+    sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+    flops = seg_per_launch * FLOPS_PER_SEGMENT / secs / 1e12 if secs > 0 else 0.0
+    gbs = seg_per_launch * BYTES_PER_SEGMENT / secs / 1e9 if secs > 0 else 0.0
+    ncu, cache = {}, {}
+    for name, target in (("extend_ncu.json", ncu), ("cache_peaks.json", cache)):
+        try:
+            with open(os.path.join(REPO, "profiles", name)) as f:
+                target.update(json.load(f))
+        except Exception:
+            pass
+    sm_mhz = float(clocks.get("sm_mhz") or sm_max)
+    inst_per_seg = ncu.get("warp_inst_per_segment")
+    issue = None
+    if inst_per_seg and secs > 0:
+        per_clk = inst_per_seg * seg_per_launch / secs / (sm_mhz * 1e6) / 148
+        issue = {"warp_inst_per_segment": inst_per_seg, "issue_slots_per_clk_per_sm": per_clk, "peak": 4.0, "frac": per_clk / 4.0,
+                 "lanes_per_inst": ncu.get("lanes_per_inst"),
+                 "useful_lane_issue_frac": per_clk / 4.0 * (ncu.get("lanes_per_inst") or 0) / 32.0,
+                 "source": "warp instructions and lanes per instruction: ncu capture summarised in profiles/extend_ncu.json; "
+                           "duration, segments and SM clock: this run"}
+    dram_per_seg = ncu.get("dram_bytes_per_segment")
+    return {
+        "bound": "issue", "kernel": "k_extend", "achieved": flops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": flops / fp32_peak,
+        "traffic": ncu.get("dram_bytes_per_launch"),
+        "peak_source": (f"FP32 issue peak 148 SMs x 128 lanes x 2 flop x {sm_max:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json; "
+                        "that file holds no FP32 figure)") if peaks else "FP32 issue peak at the fallback 1965 MHz",
+        "algorithmic_flops_per_segment": FLOPS_PER_SEGMENT, "algorithmic_bytes_per_segment": BYTES_PER_SEGMENT,
+        "segments_per_launch": seg_per_launch, "launch_ms": launch_ms,
+        "issue": issue,
+        "hbm": {"note": "the scene (0.06 MB) is L1/L2 resident: the algorithmic bytes are node / primitive fetches served on chip, so "
+                        "their rate may exceed the HBM peak; what HBM actually moves is dram_bytes_per_segment (queue entries)",
+                "algorithmic_gbs": gbs, "peak": hbm_peak, "algorithmic_frac_of_hbm": gbs / hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
+                "dram_bytes_per_segment": dram_per_seg,
+                "dram_gbs": dram_per_seg * seg_per_launch / secs / 1e9 if dram_per_seg and secs > 0 else None,
+                "dram_frac": dram_per_seg * seg_per_launch / secs / 1e9 / hbm_peak if dram_per_seg and secs > 0 else None},
+        "on_chip": ({"note": "the same algorithmic bytes against the L1- and L2-resident read bandwidth measured on this pool "
+                             "(profiles/cache_peaks.json, tools/cache_peaks; not in MEASURED_PEAKS.json)",
+                     "l1_peak": cache["l1_read_gbs"], "l1_frac": gbs / cache["l1_read_gbs"],
+                     "l2_peak": cache["l2_read_gbs"], "l2_frac": gbs / cache["l2_read_gbs"]}
+                    if cache.get("l1_read_gbs") and cache.get("l2_read_gbs") else None),
+        "stage_ms_per_frame": {k: stage_ms[i] / roof_steps / strata_per_step
+                               for i, k in enumerate(["generate", "extend", "shade", "accumulate", "tail"])},
+        "tail_segments_per_frame": roof_counters.tail_segments / roof_steps / strata_per_step}
+
+
+def static_4k_leg(ctx, stream, world, rank, shared_frames, close_frames, barrier, all_max, all_sum):
+    """Strong scaling (north_star: "near-linear 8-GPU scaling on 4K high-spp static renders"): the final scene
+    (BASELINE config 5's scene) at 3840x2160, depth 50, 16 spp instead of 4096 so that the default run stays short -
+    FIXED total work, tiles interleaved over the N GPUs, every rank's tiles tone-mapped into rank 0's 4K frame.
+    Device time of render + present (max over ranks), best of 2, and the SHA-256 of the assembled frame."""
+    import torch
+
+    from rt_b200 import engine, host
+
+    WIDTH4K, ROOT, DEPTH4K, SEED = 3840, 4, 50, 77
+    hs = host.HostScene.builtin("final", SCENE_SEED, 20, 1000)
+    scene = engine.Scene(ctx, hs.desc)
+    n_prims = scene.info().n_prims
+    cam = engine.camera_from_config(hs.camera_config(WIDTH4K, ROOT * ROOT, DEPTH4K))
+    W, H = cam.image_width, cam.image_height
+    film = engine.Film(ctx, W, H, rank, world, TILE_ROWS)
+    made = shared_frames(W, H, 1)
+    frame = made[0]
+    host_rgb8 = torch.zeros((W * H, 3), dtype=torch.uint8).pin_memory() if rank == 0 else None
+
+    def one(root):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        engine.render_static(scene, cam, film, root, DEPTH4K, SEED)
+        frame.present(film, 1.0 / (root * root))
+        if rank == 0:
+            frame.wait()
+            frame.release()
+        e1.record(stream)
+        barrier()
+        return all_max(e0.elapsed_time(e1))
+
+    one(1)  # warm-up: sizes the queues
+    ctx.reset_counters()
+    times = [one(ROOT) for _ in range(2)]
+    c = ctx.counters()
+    seg = all_sum([c.segments, c.paths])
+    sha = None
+    frame.present(film, 1.0 / (ROOT * ROOT))
+    if rank == 0:
+        frame.wait()
+        frame.download(host_rgb8.data_ptr())
+        frame.download_wait()
+        sha = hashlib.sha256(host_rgb8.numpy().tobytes()).hexdigest()
+    ms = min(times)
+    paths = W * H * ROOT * ROOT
+    out = {"workload": f"final scene ({n_prims} primitives, two media) {W}x{H}, {ROOT * ROOT} spp, depth {DEPTH4K}, static "
+                       f"render, fixed total work: {TILE_ROWS}-scanline tiles interleaved over {world} GPU(s), tiles tone-mapped into "
+                       f"rank 0's frame over NVLink", "scaling": "strong",
+           "ms": ms, "ms_all_runs": times, "value": paths / ms / 1e3, "unit": "Mpath-samples/s", "paths": paths,
+           "segments_per_path": seg[0] / max(1.0, seg[1]), "frame_sha": sha}
+    close_frames(made)
+    film.close()
+    scene.close()
+    hs.close()
+    del host_rgb8
+    return out
+
+
+def rmse_leg(ctx):
+    """BASELINE config 1 (spheres scene 400x225, 100 spp, depth 50): this library's render against the reference's
+    own CPU render of the same configuration (oracle/_ref, all host threads), with the reference-vs-reference RMSE
+    (two seeds) as the noise floor.  The checker role of oracle/; null where the harness was not built."""
+    import oracle_lib as ol
+    from rt_b200 import engine, host
+
+    if not ol.have_ref():
+        return None
+    hs = host.HostScene.builtin(SCENE, SCENE_SEED, 11)
+    scene = engine.Scene(ctx, hs.desc)
+    cam = engine.camera_from_config(hs.camera_config(400, 100, 50))
+    film = engine.Film(ctx, cam.image_width, cam.image_height)
+    engine.render_static(scene, cam, film, 10, 50, 7)
+    got = film.read_rgb(1.0 / 100).reshape(cam.image_height, cam.image_width, 3)
+    ref_a, secs, cores = reference_render(SCENE, 11, 0, 400, 100, 50, 11)
+    ref_b, _, _ = reference_render(SCENE, 11, 0, 400, 100, 50, 12)
+    out = {"config": "BASELINE config 1: spheres scene 400x225, 100 spp, depth 50; reference = oracle/_ref (unmodified reference "
+                     "sources, all host threads), seeds 11 and 12",
+           "reference_cpu_s": secs, "reference_cores": cores}
+    out.update(image_distance(got, ref_a, ref_b))
+    film.close()
+    scene.close()
+    hs.close()
+    return out
 
 
 def main():

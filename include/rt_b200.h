@@ -33,6 +33,7 @@
 #ifndef RT_B200_H
 #define RT_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -408,6 +409,9 @@ int rt_frame_release(rt_frame *frame);
 int rt_frame_download(rt_frame *frame, uint8_t *host_rgb8); /* host_rgb8: width*height*3 bytes, pinned for overlap */
 int rt_frame_download_wait(rt_frame *frame);                /* blocks until the download is in host memory */
 int rt_frame_error(rt_frame *frame);                        /* 0 = fine, 1 = a wait timed out, < 0 = CUDA error */
+/* Page-locked host memory for rt_frame_download (so that the copy runs asynchronously beside the next render). */
+int rt_host_alloc(size_t bytes, void **out);
+void rt_host_free(void *p);
 
 /* ----------------------------------------------------------------------------------------------
  * Counters (tracing / profiling aid)

@@ -401,6 +401,19 @@ int rt_frame_download_wait(rt_frame *frame) {
   return RT_OK;
 }
 
+int rt_host_alloc(size_t bytes, void **out) {
+  if (!out)
+    return frame_invalid("rt_host_alloc: null output");
+  *out = nullptr;
+  RT_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+  return RT_OK;
+}
+
+void rt_host_free(void *p) {
+  if (p)
+    cudaFreeHost(p);
+}
+
 int rt_frame_error(rt_frame *frame) {
   if (!frame)
     return -1;

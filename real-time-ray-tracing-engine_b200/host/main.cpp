@@ -5,8 +5,10 @@
 // when libSDL3 can be loaded at run time (host/presenter.cpp, dlopen) and --frames is not given; otherwise the
 // dynamic camera runs headless: it renders the progressive frames, resolves each to RGB8 exactly as
 // update_texture does (:280-306), takes its key states from --keys, reports per-frame times and writes the
-// last frame.  Images are partitioned over --gpus devices by interleaved scanline tiles and gathered over
-// NVLink peer copies.  There is no CPU rendering path: without a CUDA device the program fails.
+// last frame.  Images are partitioned over --gpus devices by interleaved scanline tiles; every GPU tone-maps its
+// tiles and stores them straight into GPU 0's frame over NVLink (rt_film_present), and the frame's copy to pinned
+// host memory runs beside the next frame's render.  There is no CPU rendering path: without a CUDA device the
+// program fails.
 #include "../../include/rt_b200.h"
 #include "../../include/rt_host.h"
 
@@ -85,24 +87,46 @@ int main(int argc, char **argv) {
                opt.scene, (long long)info.n_prims, (long long)info.n_nodes, info.build_ms, W, H, sqrt_spp * sqrt_spp,
                opt.depth, n_gpus);
 
-  std::vector<uint8_t> rgb8((size_t)W * H * 3);
+  // The displayed frame: two RGB8 frames in GPU 0's memory (the copy of one to host memory overlaps the render of
+  // the next), every other GPU holds a handle to them and stores its tiles there over NVLink (rt_film_present);
+  // two pinned host buffers receive them.  Nothing is allocated per frame.
+  rt_frame *frame[2] = {nullptr, nullptr};
+  std::vector<rt_frame *> handle[2] = {std::vector<rt_frame *>(n_gpus, nullptr), std::vector<rt_frame *>(n_gpus, nullptr)};
+  uint8_t *rgb8_buf[2] = {nullptr, nullptr};
+  for (int k = 0; k < 2; k++) {
+    CHECK(rt_frame_create(ctx[0], W, H, n_gpus, &frame[k]));
+    handle[k][0] = frame[k];
+    for (int g = 1; g < n_gpus; g++)
+      CHECK(rt_frame_attach(ctx[g], frame[k], &handle[k][g]));
+    void *p = nullptr;
+    CHECK(rt_host_alloc((size_t)W * H * 3, &p));
+    rgb8_buf[k] = static_cast<uint8_t *>(p);
+  }
+  // every GPU tone-maps and stores its tiles, GPU 0 waits for all of them and starts the copy to host memory
+  auto present = [&](int k, double scale) -> int {
+    for (int g = 0; g < n_gpus; g++) {
+      int st = rt_film_present(film[g], scale, handle[k][g]);
+      if (st != RT_OK)
+        return st;
+    }
+    int st = rt_frame_wait(frame[k]);
+    return st != RT_OK ? st : rt_frame_download(frame[k], rgb8_buf[k]);
+  };
+  uint8_t *rgb8 = rgb8_buf[0]; // the most recent frame that is complete in host memory
 
   double t0 = now_ms();
   if (!opt.camera_dynamic) {
     for (int g = 0; g < n_gpus; g++)
       CHECK(rt_render_static(scene[g], &cam, film[g], sqrt_spp, opt.depth, opt.seed));
-    if (n_gpus == 1) {
-      CHECK(rt_film_resolve_rgb8(film[0], 1.0 / opt.samples, rgb8.data())); // pixel_samples_scale = 1/spp
-    } else {
-      CHECK(rt_film_gather_p2p_rgb8(film.data(), n_gpus, 1.0 / opt.samples, rgb8.data()));
-    }
+    CHECK(present(0, 1.0 / opt.samples)); // pixel_samples_scale = 1/spp
+    CHECK(rt_frame_download_wait(frame[0]));
     double t1 = now_ms();
     long long paths = (long long)W * H * sqrt_spp * sqrt_spp;
     std::fprintf(stderr, "[INFO] rendered %lld path samples in %.1f ms (%.1f Mpath-samples/s)\n", paths, t1 - t0,
                  paths / (t1 - t0) / 1e3);
     mkdir("output", 0755);
     std::string path = std::string("output/") + opt.output;
-    if (rth_write_ppm_p3(path.c_str(), W, H, rgb8.data()) != 0) {
+    if (rth_write_ppm_p3(path.c_str(), W, H, rgb8) != 0) {
       std::fprintf(stderr, "[ERROR] %s\n", rth_last_error());
       return 1;
     }
@@ -119,7 +143,7 @@ int main(int argc, char **argv) {
     }
     const bool adaptive = window != nullptr || opt.adaptive;
     int frames = window ? -1 : (opt.frames > 0 ? opt.frames : sqrt_spp * sqrt_spp);
-    int taken = 0, samples = opt.samples, moves = 0, shown = 0;
+    int taken = 0, samples = opt.samples, moves = 0, shown = 0, last_queued = -1;
     // Adaptive quality: the reference doubles / halves its tile size (16..64 px) once a second when the frame
     // rate is above 30 / below 15 FPS (DynamicCamera.cpp:180-193).  A frame is one wavefront pass here, so the
     // knob is the number of strata added per displayed frame (1..64) with the same thresholds.
@@ -169,11 +193,16 @@ int main(int argc, char **argv) {
         taken += n;
       }
       double scale = 1.0 / std::max(1, taken); // DynamicCamera.cpp:285
-      if (n_gpus == 1) {
-        CHECK(rt_film_resolve_rgb8(film[0], scale, rgb8.data()));
-      } else {
-        CHECK(rt_film_gather_p2p_rgb8(film.data(), n_gpus, scale, rgb8.data()));
-      }
+      // Frame f is queued (render, tone map, NVLink stores, copy to pinned host memory) while frame f - 1, whose
+      // copy ran beside this frame's render, is what gets shown: the host never waits for the GPU to go idle.
+      const int k = f & 1;
+      CHECK(present(k, scale));
+      if (f == 0)
+        CHECK(rt_frame_download_wait(frame[0])); // the first frame has no predecessor to show
+      else
+        CHECK(rt_frame_download_wait(frame[k ^ 1]));
+      rgb8 = rgb8_buf[f == 0 ? 0 : (k ^ 1)];
+      last_queued = k;
       shown++;
       fps_frames++;
       double f1 = now_ms();
@@ -190,7 +219,7 @@ int main(int argc, char **argv) {
         char line[160]; // draw_fps (:308-348) as the window title
         std::snprintf(line, sizeof line, "Dynamic Camera - %.1f fps, %d/%d samples%s", fps, std::min(taken, total_strata),
                       total_strata, converged ? " - converged" : "");
-        if (rth_presenter_present(window, rgb8.data(), line) != 0) {
+        if (rth_presenter_present(window, rgb8, line) != 0) {
           std::fprintf(stderr, "[ERROR] %s\n", rth_last_error());
           break;
         }
@@ -200,11 +229,21 @@ int main(int argc, char **argv) {
     }
     if (window)
       rth_presenter_close(window);
+    if (last_queued >= 0) { // the last frame queued is the one written out
+      CHECK(rt_frame_download_wait(frame[last_queued]));
+      rgb8 = rgb8_buf[last_queued];
+    }
     mkdir("output", 0755);
     std::string path = std::string("output/") + opt.output;
-    rth_write_ppm_p3(path.c_str(), W, H, rgb8.data());
+    rth_write_ppm_p3(path.c_str(), W, H, rgb8);
     std::fprintf(stderr, "[INFO] %d progressive frames in %.1f ms (%d camera move(s), %d sample(s) in the last "
                          "accumulation); last frame written to %s\n", shown, now_ms() - t0, moves, taken, path.c_str());
+  }
+  for (int k = 0; k < 2; k++) {
+    for (int g = 1; g < n_gpus; g++)
+      rt_frame_destroy(handle[k][g]);
+    rt_frame_destroy(frame[k]);
+    rt_host_free(rgb8_buf[k]);
   }
   for (int g = 0; g < n_gpus; g++) {
     rt_film_destroy(film[g]);

@@ -182,6 +182,8 @@ RT_B200_SYMBOLS = {
     "rt_frame_download": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rt_frame_download_wait": (C.c_int, [C.c_void_p]),
     "rt_frame_error": (C.c_int, [C.c_void_p]),
+    "rt_host_alloc": (C.c_int, [C.c_size_t, VOIDPP]),
+    "rt_host_free": (None, [C.c_void_p]),
     "rt_get_counters": (C.c_int, [C.c_void_p, P(rt_counters)]),
     "rt_reset_counters": (C.c_int, [C.c_void_p]),
     "rt_context_set_stats": (C.c_int, [C.c_void_p, C.c_int]),

@@ -608,3 +608,44 @@ def test_parity_audit_and_traversal_counters(ctx, host_scenes, name, p0, width, 
     assert q[0] == cam.image_width * cam.image_height and q[1] < q[0] and q[1] > 0
     film.close()
     scene.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# Converged-image parity at the BASELINE configurations' own sizes, against the UNMODIFIED reference
+# (oracle/_ref/libref_harness.so, compiled from /root/reference by oracle/Makefile; travels to the GPU box as a
+# built file).  Tolerances are SURVEY.md section 4's: RMSE <= 1.15 x the reference-vs-reference RMSE at equal spp
+# (two reference renders with different seeds = the Monte-Carlo noise floor), |relative luminance difference|
+# <= 0.5 %; the same ratio on 8x8-pixel block means (noise / 8) bounds a spatially coherent bias.
+# ---------------------------------------------------------------------------------------------------
+AT_SIZE = [
+    # id, scene, p0, p1, width, sqrt_spp, depth, aspect
+    ("c1", "spheres", 11, 0, 400, 10, 50, None),              # BASELINE config 1 exactly: 400x225, 100 spp, depth 50
+    ("c3", "cornell_smoke", 0, 0, 1920, 3, 50, 16.0 / 9.0),   # config 3's scene and size, 9 of its 1024 spp
+    ("c5", "final", 20, 1000, 3840, 1, 50, None),             # config 5's scene and size (3840x2160), 1 of its 4096 spp
+]
+
+
+@pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref/libref_harness.so not built")
+@pytest.mark.parametrize("cid,name,p0,p1,width,root,depth,aspect", AT_SIZE, ids=[c[0] for c in AT_SIZE])
+def test_at_size_rmse_against_the_reference_render(ctx, host_scenes, cid, name, p0, p1, width, root, depth, aspect):
+    import bench
+
+    hs = host_scenes(name, p0, p1 if p1 else -1)
+    cfg = hs.camera_config(width, root * root, depth)
+    if aspect:
+        cfg.aspect_ratio = aspect
+    cam = engine.camera_from_config(cfg)
+    scene = engine.Scene(ctx, hs.desc)
+    film = engine.Film(ctx, cam.image_width, cam.image_height)
+    engine.render_static(scene, cam, film, root, depth, 3)
+    got = film.read_rgb(1.0 / (root * root)).reshape(cam.image_height, cam.image_width, 3)
+    film.close()
+    scene.close()
+    ref_a, _, _ = bench.reference_render(name, p0, p1, width, root * root, depth, 11, aspect)
+    ref_b, _, _ = bench.reference_render(name, p0, p1, width, root * root, depth, 12, aspect)
+    assert ref_a.shape == got.shape
+    d = bench.image_distance(got, ref_a, ref_b)
+    print(cid, {k: round(v, 5) for k, v in d.items()})
+    assert d["ratio"] <= 1.15, d
+    assert d["block8_ratio"] <= 1.15, d
+    assert abs(d["luminance_rel_diff"]) <= 0.005, d

@@ -2,7 +2,9 @@
 
   python tools/summarize_ncu.py launches gpurun_out/launches.csv  profiles/rNN_launches_bench.md  "<command>"
   python tools/summarize_ncu.py full     gpurun_out/prof.ncu-rep  profiles/rNN_kernels_ncu_full.md "<command>"
-      (also rewrites profiles/extend_traffic.json from the k_extend launches of the capture)
+      (a capture of a C2 frame also rewrites profiles/extend_ncu.json - warp instructions, lanes and DRAM bytes per
+       segment of the k_extend launches - which bench.py's roofline block reads)
+  python tools/summarize_ncu.py full     gpurun_out/prof_c4.ncu-rep profiles/rNN_c4_....md "<command>" "<what was captured>"
 
 `launches`: per-kernel totals and shares of a `--metrics gpu__time_duration.sum` launch list.
 `full`:     one column per captured launch of a `--set full` report (read through `ncu -i ... --page raw --csv`).
@@ -42,7 +44,8 @@ FULL_METRICS = [
 
 
 def short(name):
-    return name.split("(")[0].replace("void ", "")[:70]
+    """`void k_extend<0, 1>(DScene, ...)` -> `k_extend` (template arguments dropped)."""
+    return name.split("(")[0].replace("void ", "").split("<")[0][:70]
 
 
 def launches(csv_path, out_path, command):
@@ -85,7 +88,11 @@ def launches(csv_path, out_path, command):
     print("wrote", out_path)
 
 
-def full(rep_path, out_path, command):
+# queue lengths of the three k_extend launches of a C2 frame (bench.py's seed 1000; they move by < 0.1 % with the seed)
+C2_EXTEND_SEGMENTS = [2073600, 1727915, 734978]
+
+
+def full(rep_path, out_path, command, what=None, extend_segments=None):
     raw = subprocess.run(["ncu", "-i", rep_path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
@@ -96,9 +103,10 @@ def full(rep_path, out_path, command):
         k = short(d[kcol]).replace("k_", "")
         names.append(f"{k} #{count[k]}")
         count[k] += 1
-    out = [f"# `ncu --set full` of the render kernels of one C2 frame (1 x B200)", "",
-           f"Command: `{command}` (after the same command exited 0 without ncu). One frame = 1920x1080 paths, 1 spp, "
-           "depth 8, 485-sphere scene; `#k` = the k-th launch of that kernel in the frame (bounce k for extend / shade).", "",
+    what = what or "one C2 frame: 1920x1080 paths, 1 spp, depth 8, 485-sphere scene"
+    out = [f"# `ncu --set full` of the render kernels of {what.split(':')[0]} (1 x B200)", "",
+           f"Command: `{command}` (after the same command exited 0 without ncu). {what[0].upper() + what[1:]}; `#k` = the k-th "
+           "launch of that kernel in the frame (bounce k for extend / shade).", "",
            "| metric | unit | " + " | ".join(names) + " |", "|---|---|" + "---:|" * len(names)]
     for m, label in FULL_METRICS:
         if m not in hdr:
@@ -118,11 +126,21 @@ def full(rep_path, out_path, command):
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     per = [float(d[r].replace(",", "")) * scale[units[r]] + float(d[w].replace(",", "")) * scale[units[w]]
            for d in data if short(d[kcol]) == "k_extend"]
-    if per:
-        tpath = os.path.join(REPO, "profiles", "extend_traffic.json")
-        json.dump({"dram_bytes_per_launch": sum(per) / len(per), "per_launch": per,
-                   "launches": "k_extend launches of one C2 frame (the launches bench.py times)",
-                   "source": os.path.relpath(out_path, REPO) + " (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"},
+    if per and extend_segments is not None:
+        # per-segment figures of the k_extend launches -> bench.py's roofline block (profiles/extend_ncu.json)
+        ic, lc = hdr.index("smsp__inst_executed.sum"), hdr.index("smsp__thread_inst_executed_per_inst_executed.ratio")
+        ext = [d for d in data if short(d[kcol]) == "k_extend"]
+        inst = [float(d[ic].replace(",", "")) for d in ext]
+        lanes = [float(d[lc].replace(",", "")) for d in ext]
+        segs = list(extend_segments)[: len(ext)]
+        tpath = os.path.join(REPO, "profiles", "extend_ncu.json")
+        json.dump({"launches": "k_extend launches of one C2 frame (the launches bench.py times)",
+                   "source": os.path.relpath(out_path, REPO) + " (ncu --set full)",
+                   "segments_per_launch": segs, "warp_inst_per_launch": inst, "lanes_per_inst_per_launch": lanes,
+                   "dram_bytes_per_launch_each": per,
+                   "warp_inst_per_segment": sum(inst) / sum(segs),
+                   "lanes_per_inst": sum(i * l for i, l in zip(inst, lanes)) / sum(inst),
+                   "dram_bytes_per_launch": sum(per) / len(per), "dram_bytes_per_segment": sum(per) / sum(segs)},
                   open(tpath, "w"), indent=1)
         print("wrote", tpath)
 
@@ -130,4 +148,8 @@ def full(rep_path, out_path, command):
 if __name__ == "__main__":
     mode, src, dst = sys.argv[1:4]
     cmd = sys.argv[4] if len(sys.argv) > 4 else ""
-    {"launches": launches, "full": full}[mode](src, dst, cmd)
+    if mode == "launches":
+        launches(src, dst, cmd)
+    else:  # full <rep> <out.md> "<command>" ["<what was captured>"]: a C2 capture (no description) also refreshes extend_ncu.json
+        what = sys.argv[5] if len(sys.argv) > 5 else None
+        full(src, dst, cmd, what, None if what else C2_EXTEND_SEGMENTS)

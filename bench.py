@@ -137,10 +137,10 @@ def reference_render(name, p0, p1, width, spp, depth, seed, aspect=None):
 
     r = ol.ref()
     h = r.ref_scene_build(name.encode(), SCENE_SEED, p0, p1)
+    if aspect:
+        r.ref_scene_set_aspect(h, aspect)
     cfg = abi.rt_camera_config()
     r.ref_scene_camera_config(h, width, spp, depth, cfg)
-    if aspect:
-        cfg.aspect_ratio = aspect
     cam = abi.rt_camera()
     r.ref_camera_init(cfg, cam)
     n = cam.image_width * cam.image_height

@@ -719,6 +719,10 @@ void ref_scene_camera_config(void *h, int width, int spp, int depth, rt_camera_c
   set3(out->background, c.background);
 }
 
+// The reference's CLI forces one aspect ratio on every scene (BASELINE config 3 renders the Cornell box at 16:9,
+// its scene function sets 1.0): override the scene camera's aspect ratio for the renders that follow.
+void ref_scene_set_aspect(void *h, double aspect_ratio) { static_cast<RefScene *>(h)->cam.aspect_ratio = aspect_ratio; }
+
 // Camera::initialize through the reference (for pinning rt_camera_init).
 void ref_camera_init(const rt_camera_config *cfg, rt_camera *out) {
   CameraConfig c;

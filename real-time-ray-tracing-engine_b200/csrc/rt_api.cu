@@ -631,7 +631,7 @@ int rt_film_resolve_rgb8_device(rt_film *film, double scale, void *device_rgb8) 
   RT_CUDA(cudaSetDevice(film->ctx->device));
   // compact order out (rank 0 of 1): the staged 16-byte-store kernel of rt_frame.cu
   launch_present_rgb8(film->ctx, film->ctx->stream, film->accum, film->n_owned, film->map.width, film->map.tile_rows, 0, 1,
-                      scale, (uint8_t *)device_rgb8, nullptr, nullptr, 0);
+                      scale, (uint8_t *)device_rgb8, nullptr, nullptr, 0, nullptr, nullptr);
   film->ctx->counters.kernel_launches += 1;
   RT_CUDA(cudaGetLastError());
   return RT_OK;

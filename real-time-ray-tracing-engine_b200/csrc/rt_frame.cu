@@ -6,12 +6,15 @@
 // 519-554, and this library's earlier resolve -> NCCL gather -> scatter sequence).
 //
 // Protocol per use of a frame (ticket t = 1, 2, ... counted by every handle on its own):
-//   every rank : rt_film_present   wait until the owner consumed ticket t-1, store the tiles, flags[rank] = t
-//   owner      : rt_frame_wait     stream-ordered wait until all flags >= t
+//   remote rank: rt_film_present   ONE kernel: waits until the owner consumed ticket t-1 (first thread of every
+//                                  block polls the owner's word), stores the tiles, the last block sets flags[rank] = t
+//   owner      : rt_film_present   one kernel, ordered after the frame's previous download by a CUDA event
+//                rt_frame_wait     one tiny kernel: the stream waits until all ranks' flags are >= t
 //                rt_frame_download (copy to host memory on the frame's copy stream, then consumed = t)
 //             or rt_frame_release  (consumed = t without a copy)
-// Waits are bounded spin kernels (RT_FRAME_TIMEOUT_CYCLES): a rank that never shows up sets the frame's error
-// word instead of hanging the GPU.
+//   A frame with one rank needs none of the flags: present is a single launch, wait and release launch nothing.
+// Waits are bounded (RT_FRAME_TIMEOUT_CYCLES): a rank that never shows up sets the frame's error word instead of
+// hanging the GPU.
 #include "rt_internal.h"
 
 #include <algorithm>
@@ -33,7 +36,8 @@ struct rt_frame {
   unsigned int *blocks_done = nullptr; // on ctx's device: block counter of the present kernel
   uint32_t ticket = 0;
   cudaStream_t copy_stream = nullptr;  // owner: downloads run here, next to the next frame's render
-  cudaEvent_t ready = nullptr;
+  cudaEvent_t ready = nullptr, copied = nullptr;
+  bool download_pending = false; // owner: the copy stream may still be reading the frame
 };
 
 static size_t frame_image_bytes(int width, int height) {
@@ -65,6 +69,23 @@ __global__ void k_frame_wait(const uint32_t *words, int n_words, uint32_t ticket
   }
 }
 
+// First thread of a block polls until *word has reached `value`; the block continues together.
+__device__ __forceinline__ void block_wait_for(const uint32_t *word, uint32_t value, uint32_t *error) {
+  if (word) {
+    if (threadIdx.x == 0) {
+      long long t0 = clock64();
+      while ((int32_t)(ld_acquire_sys(word) - value) < 0) {
+        if (clock64() - t0 > RT_FRAME_TIMEOUT_CYCLES) {
+          atomicExch(error, 1u);
+          break;
+        }
+        __nanosleep(128);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void k_frame_signal(uint32_t *word, uint32_t value) {
   __threadfence_system();
   st_release_sys(word, value);
@@ -83,8 +104,10 @@ __device__ __forceinline__ size_t frame_offset(size_t b, size_t tile_bytes, int 
 #define RT_PRESENT_PIXELS 1024
 __global__ void __launch_bounds__(RT_PRESENT_THREADS)
     k_present_rgb8(const float4 *__restrict__ film, long long n_owned, double scale, uint8_t *__restrict__ frame,
-                   size_t tile_bytes, int rank, int n_ranks, unsigned int *blocks_done, uint32_t *flag, uint32_t ticket) {
+                   size_t tile_bytes, int rank, int n_ranks, unsigned int *blocks_done, uint32_t *flag, uint32_t ticket,
+                   const uint32_t *consumed, uint32_t *error) {
   __shared__ __align__(16) uint8_t stage[RT_PRESENT_PIXELS * 3];
+  block_wait_for(consumed, ticket - 1, error);
   const long long n_chunks = (n_owned + RT_PRESENT_PIXELS - 1) / RT_PRESENT_PIXELS;
   const size_t total_bytes = (size_t)n_owned * 3;
   for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
@@ -125,7 +148,9 @@ __global__ void __launch_bounds__(RT_PRESENT_THREADS)
 // Any geometry: one pixel per thread, three byte stores.
 __global__ void k_present_rgb8_any(const float4 *__restrict__ film, long long n_owned, double scale,
                                    uint8_t *__restrict__ frame, int width, int tile_rows, int rank, int n_ranks,
-                                   unsigned int *blocks_done, uint32_t *flag, uint32_t ticket) {
+                                   unsigned int *blocks_done, uint32_t *flag, uint32_t ticket, const uint32_t *consumed,
+                                   uint32_t *error) {
+  block_wait_for(consumed, ticket - 1, error);
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n_owned; k += stride) {
     long long local_row = k / width;
@@ -154,10 +179,10 @@ __global__ void k_present_rgb8_any(const float4 *__restrict__ film, long long n_
 
 // Owned pixels of a film (compact tile order) -> RGB8.  (rank, n_ranks) = the film's own: every tile lands in its
 // rows of a row-major frame; (0, 1): the output keeps the compact order (rt_film_resolve_rgb8_device).
-// flag == nullptr: no arrival flag.
+// flag == nullptr: no arrival flag.  consumed != nullptr: every block first waits until *consumed >= ticket - 1.
 void launch_present_rgb8(const rt_context *ctx, cudaStream_t stream, const float4 *accum, int64_t n_owned, int width,
                          int tile_rows, int rank, int n_ranks, double scale, uint8_t *frame, unsigned int *blocks_done,
-                         uint32_t *flag, uint32_t ticket) {
+                         uint32_t *flag, uint32_t ticket, const uint32_t *consumed, uint32_t *error) {
   const size_t tile_bytes = (size_t)tile_rows * width * 3;
   if (n_owned == 0) {
     if (flag)
@@ -170,11 +195,11 @@ void launch_present_rgb8(const rt_context *ctx, cudaStream_t stream, const float
     int blocks = (int)std::min<long long>(chunks, (long long)ctx->sm_count * 8);
     k_present_rgb8<<<blocks, RT_PRESENT_THREADS, 0, stream>>>(accum, n_owned, scale, frame,
                                                               n_ranks == 1 ? (size_t)n_owned * 3 : tile_bytes, rank, n_ranks,
-                                                              blocks_done, flag, ticket);
+                                                              blocks_done, flag, ticket, consumed, error);
   } else {
     int blocks = (int)std::min<long long>((n_owned + 255) / 256, (long long)ctx->sm_count * 8);
     k_present_rgb8_any<<<blocks, 256, 0, stream>>>(accum, n_owned, scale, frame, width, tile_rows, rank, n_ranks, blocks_done,
-                                                   flag, ticket);
+                                                   flag, ticket, consumed, error);
   }
 }
 
@@ -190,6 +215,7 @@ int frame_finish_handle(rt_frame *f) {
   if (f->owner) {
     RT_CUDA(cudaStreamCreateWithFlags(&f->copy_stream, cudaStreamNonBlocking));
     RT_CUDA(cudaEventCreateWithFlags(&f->ready, cudaEventDisableTiming));
+    RT_CUDA(cudaEventCreateWithFlags(&f->copied, cudaEventDisableTiming));
   }
   RT_CUDA(cudaStreamSynchronize(f->ctx->stream));
   return RT_OK;
@@ -318,6 +344,8 @@ void rt_frame_destroy(rt_frame *frame) {
   }
   if (frame->ready)
     cudaEventDestroy(frame->ready);
+  if (frame->copied)
+    cudaEventDestroy(frame->copied);
   cudaFree(frame->blocks_done);
   if (frame->ipc)
     cudaIpcCloseMemHandle(frame->base);
@@ -338,13 +366,21 @@ int rt_film_present(rt_film *film, double scale, rt_frame *frame) {
   rt_context *ctx = film->ctx;
   RT_CUDA(cudaSetDevice(ctx->device));
   const uint32_t ticket = ++frame->ticket;
-  // the owner must have consumed the frame's previous content before its rows are overwritten
-  if (ticket > 1) {
-    k_frame_wait<<<1, 32, 0, ctx->stream>>>(frame->flags + RT_FRAME_CONSUMED, 1, ticket - 1, frame->flags + RT_FRAME_ERROR);
-    ctx->counters.kernel_launches += 1;
+  const bool alone = frame->n_ranks == 1;
+  const uint32_t *consumed = nullptr;
+  if (frame->owner) {
+    // the frame's previous content may still be on its way to host memory: order behind that copy (no kernel)
+    if (frame->download_pending) {
+      RT_CUDA(cudaStreamWaitEvent(ctx->stream, frame->copied, 0));
+      frame->download_pending = false;
+    }
+  } else if (ticket > 1) {
+    consumed = frame->flags + RT_FRAME_CONSUMED; // polled by the present kernel itself
   }
+  uint32_t *flag = frame->flags + film->map.rank; // raised by the kernel's last block
   launch_present_rgb8(ctx, ctx->stream, film->accum, film->n_owned, film->map.width, film->map.tile_rows, film->map.rank,
-                      film->map.n_ranks, scale, frame->rgb8, frame->blocks_done, frame->flags + film->map.rank, ticket);
+                      film->map.n_ranks, scale, frame->rgb8, frame->blocks_done, alone ? nullptr : flag, ticket, consumed,
+                      frame->flags + RT_FRAME_ERROR);
   ctx->counters.kernel_launches += 1;
   RT_CUDA(cudaGetLastError());
   return RT_OK;
@@ -355,9 +391,11 @@ int rt_frame_wait(rt_frame *frame) {
     return frame_invalid("rt_frame_wait: needs the owner's frame");
   rt_context *ctx = frame->ctx;
   RT_CUDA(cudaSetDevice(ctx->device));
-  k_frame_wait<<<1, 64, 0, ctx->stream>>>(frame->flags, frame->n_ranks, frame->ticket, frame->flags + RT_FRAME_ERROR);
-  ctx->counters.kernel_launches += 1;
-  RT_CUDA(cudaGetLastError());
+  if (frame->n_ranks > 1) {
+    k_frame_wait<<<1, 64, 0, ctx->stream>>>(frame->flags, frame->n_ranks, frame->ticket, frame->flags + RT_FRAME_ERROR);
+    ctx->counters.kernel_launches += 1;
+    RT_CUDA(cudaGetLastError());
+  }
   return RT_OK;
 }
 
@@ -366,9 +404,11 @@ int rt_frame_release(rt_frame *frame) {
     return frame_invalid("rt_frame_release: needs the owner's frame");
   rt_context *ctx = frame->ctx;
   RT_CUDA(cudaSetDevice(ctx->device));
-  k_frame_signal<<<1, 1, 0, ctx->stream>>>(frame->flags + RT_FRAME_CONSUMED, frame->ticket);
-  ctx->counters.kernel_launches += 1;
-  RT_CUDA(cudaGetLastError());
+  if (frame->n_ranks > 1) {
+    k_frame_signal<<<1, 1, 0, ctx->stream>>>(frame->flags + RT_FRAME_CONSUMED, frame->ticket);
+    ctx->counters.kernel_launches += 1;
+    RT_CUDA(cudaGetLastError());
+  }
   return RT_OK;
 }
 
@@ -381,9 +421,13 @@ int rt_frame_download(rt_frame *frame, uint8_t *host_rgb8) {
   RT_CUDA(cudaStreamWaitEvent(frame->copy_stream, frame->ready, 0));
   RT_CUDA(cudaMemcpyAsync(host_rgb8, frame->rgb8, (size_t)frame->width * frame->height * 3, cudaMemcpyDeviceToHost,
                           frame->copy_stream));
-  k_frame_signal<<<1, 1, 0, frame->copy_stream>>>(frame->flags + RT_FRAME_CONSUMED, frame->ticket);
-  ctx->counters.kernel_launches += 1;
-  RT_CUDA(cudaGetLastError());
+  if (frame->n_ranks > 1) {
+    k_frame_signal<<<1, 1, 0, frame->copy_stream>>>(frame->flags + RT_FRAME_CONSUMED, frame->ticket);
+    ctx->counters.kernel_launches += 1;
+    RT_CUDA(cudaGetLastError());
+  }
+  RT_CUDA(cudaEventRecord(frame->copied, frame->copy_stream));
+  frame->download_pending = true;
   return RT_OK;
 }
 

@@ -195,7 +195,7 @@ void launch_scatter_gathered(cudaStream_t s, int width, int height, int n_ranks,
 // displayed frames (rt_frame.cu)
 void launch_present_rgb8(const rt_context *ctx, cudaStream_t stream, const float4 *accum, int64_t n_owned, int width,
                          int tile_rows, int rank, int n_ranks, double scale, uint8_t *frame, unsigned int *blocks_done,
-                         uint32_t *flag, uint32_t ticket);
+                         uint32_t *flag, uint32_t ticket, const uint32_t *consumed, uint32_t *error);
 
 // parity audit (rt_exact.cu)
 void launch_audit_trace(const rt_context *ctx, const ExactScene &sc, const PassParams &pp, WaveBuffers &w, int bounce,

@@ -79,6 +79,7 @@ def ref():
         lib.ref_scene_desc.restype = P(abi.rt_scene_desc)
         lib.ref_scene_desc.argtypes = [C.c_void_p]
         lib.ref_scene_camera_config.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, P(abi.rt_camera_config)]
+        lib.ref_scene_set_aspect.argtypes = [C.c_void_p, C.c_double]
         lib.ref_camera_init.argtypes = [P(abi.rt_camera_config), P(abi.rt_camera)]
         lib.ref_primary_rays.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, P(abi.rt_ray)]
         lib.ref_trace.argtypes = [C.c_void_p, P(abi.rt_ray), C.c_int64, C.c_int, P(abi.rt_hit)]

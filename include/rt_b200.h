@@ -252,19 +252,26 @@ int rt_context_synchronize(rt_context *ctx);
 /* The context's cudaStream_t as an integer (so callers can record CUDA events on it). */
 uint64_t rt_context_stream(rt_context *ctx);
 
-/* Upload the scene, bake instance transforms, build the LBVH on the device and collapse it into
- * 4-wide nodes.  The description may be freed after the call returns. */
+/* Upload the scene, bake instance transforms, build the binary tree (on the device: Morton sort + PLOC; small
+ * scenes also try a host SAH tree and keep the better one) and collapse it into 4-wide nodes on the device.  The
+ * description may be freed after the call returns. */
 int rt_scene_create(rt_context *ctx, const rt_scene_desc *desc, rt_scene **out);
 void rt_scene_destroy(rt_scene *scene);
 
+enum { RT_BUILDER_NONE = 0,  /* 0 or 1 primitive */
+       RT_BUILDER_SAH = 1,   /* binary SAH tree built on the host (64 .. 65,536 primitives) */
+       RT_BUILDER_PLOC = 2,  /* device: Morton sort + parallel locally-ordered clustering */
+       RT_BUILDER_LBVH = 3   /* device: Morton sort + Karras radix tree */ };
 typedef struct rt_scene_info {
   int64_t n_prims;       /* BVH leaves: visible spheres + quads + media */
   int64_t n_nodes;       /* 4-wide nodes */
   int64_t node_bytes;
   int64_t prim_bytes;
-  double build_ms;       /* device time of the LBVH build + collapse */
+  double build_ms;       /* device time of the tree build + collapse (+ the host SAH build where one ran) */
   double bounds_min[3];
   double bounds_max[3];
+  int32_t builder;       /* RT_BUILDER_*: the tree that was kept */
+  int32_t pad_;
 } rt_scene_info;
 int rt_scene_get_info(rt_scene *scene, rt_scene_info *out);
 

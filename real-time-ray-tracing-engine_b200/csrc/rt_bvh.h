@@ -1,5 +1,6 @@
-// rt_bvh.h — per-thread bodies of the GPU LBVH build (Morton codes -> radix sort -> Karras hierarchy
-// -> bottom-up refit -> collapse to 4-wide SoA nodes).  Replaces the reference's host-side recursive
+// rt_bvh.h — per-thread bodies of the GPU BVH build (Morton codes -> radix sort -> binary tree over the sorted
+// primitives: Karras hierarchy + bottom-up refit [LBVH], or locally-ordered clustering [PLOC] -> collapse to
+// 4-wide SoA nodes).  Replaces the reference's host-side recursive
 // SAH build and its pointer / 64-byte FlatNode tree (optimization/BVHNode.cpp:21-123,322-383).
 //
 // Stages (one kernel each in rt_kernels.cu, thread i runs body(i)):
@@ -129,6 +130,76 @@ RT_HD float box_area(const BuildBox &b) {
 
 RT_HD BuildBox child_box(const BinTree &t, const BuildBox *leaf_boxes, int ref) {
   return ref >= 0 ? t.box[ref] : leaf_boxes[~ref];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// PLOC (parallel locally-ordered clustering; Meister & Bittner 2018): an agglomerative build over the
+// Morton-sorted primitives.  The clusters of the current level keep the Morton order; every cluster looks at
+// its `radius` neighbours on either side and picks the one whose merged box has the smallest surface area;
+// clusters that picked each other merge into a new binary node, the others survive to the next round; the
+// array is compacted and the rounds repeat until one cluster is left (~2 log2 n rounds).  Same input and
+// output as the Karras hierarchy + refit pair (sorted leaf boxes in, BinTree out, root = node 0) at a
+// surface-area cost close to a top-down SAH build, which is what traversal cost follows.
+// ---------------------------------------------------------------------------------------------------
+#define RT_PLOC_RADIUS 16
+
+struct PlocCluster {
+  BuildBox box;
+  int ref; // binary-tree reference: internal node index, or ~(sorted leaf index)
+  int pad_;
+};
+
+// Nearest neighbour of cluster i among clusters [i - radius, i + radius] by merged surface area (ties: the
+// lower index, so that the choice does not depend on the evaluation order).
+RT_HD int ploc_nearest_body(const PlocCluster *clusters, int count, int i) {
+  const BuildBox me = clusters[i].box;
+  int lo = i - RT_PLOC_RADIUS < 0 ? 0 : i - RT_PLOC_RADIUS;
+  int hi = i + RT_PLOC_RADIUS > count - 1 ? count - 1 : i + RT_PLOC_RADIUS;
+  int best = -1;
+  float best_area = RT_INF_F;
+  for (int j = lo; j <= hi; j++) {
+    if (j == i)
+      continue;
+    float a = box_area(box_union(me, clusters[j].box));
+    if (a < best_area) {
+      best_area = a;
+      best = j;
+    }
+  }
+  return best;
+}
+
+// What cluster i does this round: 1 = merges with nearest[i] and creates the node (the lower index of a mutual
+// pair), -1 = is absorbed by its partner, 0 = survives unchanged.
+RT_HD int ploc_role(const int *nearest, int i) {
+  int j = nearest[i];
+  if (j < 0 || nearest[j] != i)
+    return 0;
+  return i < j ? 1 : -1;
+}
+
+// Writes cluster i's successor into next[slot] (slot = number of surviving / merging clusters before i) and, for
+// a merging cluster, the new binary node `node` (= first_node - number of merging clusters before i: nodes are
+// handed out downwards from n - 2, so the last merge of the build creates node 0, the root).
+RT_HD void ploc_merge_body(const PlocCluster *clusters, const int *nearest, int i, int role, int slot, int node,
+                           PlocCluster *next, BinTree t) {
+  if (role < 0)
+    return;
+  PlocCluster c = clusters[i];
+  if (role > 0) {
+    const PlocCluster &o = clusters[nearest[i]];
+    const int n_internal = t.n - 1;
+    t.left[node] = c.ref;
+    t.right[node] = o.ref;
+    c.box = box_union(c.box, o.box);
+    t.box[node] = c.box;
+    t.parent[c.ref >= 0 ? c.ref : n_internal + ~c.ref] = node;
+    t.parent[o.ref >= 0 ? o.ref : n_internal + ~o.ref] = node;
+    if (node == 0)
+      t.parent[0] = -1;
+    c.ref = node;
+  }
+  next[slot] = c;
 }
 
 // Collapse work item: binary node `bin` becomes wide node `wide`.

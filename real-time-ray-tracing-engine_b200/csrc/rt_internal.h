@@ -170,6 +170,9 @@ void launch_morton(cudaStream_t s, const BuildBox *boxes, int n, const float *sc
                    uint64_t *codes, uint32_t *index);
 int sort_pairs(cudaStream_t s, uint64_t *keys_in, uint64_t *keys_out, uint32_t *vals_in, uint32_t *vals_out, int n);
 void launch_gather_boxes(cudaStream_t s, const BuildBox *in, const uint32_t *index, BuildBox *out, int n);
+int ploc_build(cudaStream_t s, const BuildBox *leaf_boxes, int n, BinTree t, PlocCluster *clusters[2], int *nearest,
+               unsigned long long *packed, int *rounds_out);
+int tree_area(cudaStream_t s, const BuildBox *box, int n_internal, double *d_sum, double *out);
 void launch_hierarchy(cudaStream_t s, const uint64_t *codes, BinTree t);
 void launch_refit(cudaStream_t s, BinTree t, const BuildBox *leaf_boxes);
 void launch_collapse(cudaStream_t s, BinTree t, const BuildBox *leaf_boxes, float4 *nodes, const CollapseItem *items,

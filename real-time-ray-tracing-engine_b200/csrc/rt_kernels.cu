@@ -16,6 +16,7 @@
 #include "rt_internal.h"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <cstdlib>
 #include <string>
@@ -862,6 +863,52 @@ __global__ void k_collapse(BinTree t, const BuildBox *__restrict__ leaf_boxes, f
   collapse_write(t, leaf_boxes, nodes, it.wide, child, n_child, wide_ref, it.up);
 }
 
+// ---- PLOC rounds (rt_bvh.h) ----
+__global__ void k_ploc_init(const BuildBox *__restrict__ leaf_boxes, int n, PlocCluster *__restrict__ clusters) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n)
+    clusters[j] = PlocCluster{leaf_boxes[j], ~j, 0};
+}
+
+__global__ void k_ploc_nearest(const PlocCluster *__restrict__ clusters, int count, int *__restrict__ nearest) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count)
+    nearest[i] = ploc_nearest_body(clusters, count, i);
+}
+
+// high word: this cluster creates a node; low word: this cluster has a successor.  One inclusive scan of the
+// packed words numbers both the new nodes and the slots of the next round.
+__global__ void k_ploc_roles(const int *__restrict__ nearest, int count, unsigned long long *__restrict__ packed) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) {
+    int role = ploc_role(nearest, i);
+    packed[i] = ((unsigned long long)(role > 0) << 32) | (unsigned long long)(role >= 0);
+  }
+}
+
+__global__ void k_ploc_merge(const PlocCluster *__restrict__ clusters, const int *__restrict__ nearest,
+                             const unsigned long long *__restrict__ scanned, int count, int first_node,
+                             PlocCluster *__restrict__ next, BinTree t) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count)
+    return;
+  int role = ploc_role(nearest, i);
+  unsigned long long incl = scanned[i];
+  int merges_before = (int)(incl >> 32) - (role > 0), slot = (int)(incl & 0xffffffffu) - (role >= 0);
+  ploc_merge_body(clusters, nearest, i, role, slot, first_node - merges_before, next, t);
+}
+
+// Sum of the surface areas of the binary tree's internal nodes (the tree-dependent part of its SAH cost).
+__global__ void k_tree_area(const BuildBox *__restrict__ box, int n_internal, double *__restrict__ sum) {
+  double local = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_internal; i += gridDim.x * blockDim.x)
+    local += (double)box_area(box[i]);
+  for (int o = 16; o > 0; o >>= 1)
+    local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0 && local != 0.0)
+    atomicAdd(sum, local);
+}
+
 // ---- refit of the BVH4 after primitive updates (rt_scene_update_spheres) ----
 __global__ void k_leaf_links(const float4 *__restrict__ nodes, int n_nodes, int *__restrict__ leaf_up) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -952,6 +999,64 @@ int sort_pairs(cudaStream_t s, uint64_t *keys_in, uint64_t *keys_out, uint32_t *
   if (e2 != cudaSuccess)
     return rt_cuda_fail(e2, "cudaStreamSynchronize (sort)");
   return RT_OK;
+}
+
+// All PLOC rounds: sorted leaf boxes -> BinTree (left / right / parent / box, root = node 0).  clusters[2] and
+// nearest / packed are caller-provided scratch of n entries.  The host reads one 8-byte total per round.
+int ploc_build(cudaStream_t s, const BuildBox *leaf_boxes, int n, BinTree t, PlocCluster *clusters[2], int *nearest,
+               unsigned long long *packed, int *rounds_out) {
+  size_t scan_bytes = 0;
+  cudaError_t e = cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, packed, packed, n, s);
+  if (e != cudaSuccess)
+    return rt_cuda_fail(e, "cub::DeviceScan::InclusiveSum (size query)");
+  void *scan_tmp = nullptr;
+  if ((e = cudaMalloc(&scan_tmp, scan_bytes ? scan_bytes : 16)) != cudaSuccess)
+    return rt_cuda_fail(e, "cudaMalloc (scan scratch)");
+  k_ploc_init<<<ceil_div(n, 256), 256, 0, s>>>(leaf_boxes, n, clusters[0]);
+  int count = n, next_node = n - 2, cur = 0, rounds = 0, st = RT_OK;
+  while (count > 1) {
+    int blocks = ceil_div(count, 256);
+    k_ploc_nearest<<<blocks, 256, 0, s>>>(clusters[cur], count, nearest);
+    k_ploc_roles<<<blocks, 256, 0, s>>>(nearest, count, packed);
+    e = cub::DeviceScan::InclusiveSum(scan_tmp, scan_bytes, packed, packed, count, s);
+    if (e != cudaSuccess) {
+      st = rt_cuda_fail(e, "cub::DeviceScan::InclusiveSum");
+      break;
+    }
+    k_ploc_merge<<<blocks, 256, 0, s>>>(clusters[cur], nearest, packed, count, next_node, clusters[cur ^ 1], t);
+    unsigned long long total = 0;
+    if ((e = cudaMemcpyAsync(&total, packed + (count - 1), sizeof total, cudaMemcpyDeviceToHost, s)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(s)) != cudaSuccess) {
+      st = rt_cuda_fail(e, "PLOC round");
+      break;
+    }
+    int merges = (int)(total >> 32), survivors = (int)(total & 0xffffffffu);
+    if (merges <= 0 || survivors != count - merges) { // cannot happen: the globally closest pair is always mutual
+      rt_set_error("PLOC round made no progress");
+      st = RT_ERR_CUDA;
+      break;
+    }
+    next_node -= merges;
+    count = survivors;
+    cur ^= 1;
+    rounds++;
+  }
+  cudaFree(scan_tmp);
+  if (rounds_out)
+    *rounds_out = rounds;
+  return st;
+}
+
+int tree_area(cudaStream_t s, const BuildBox *box, int n_internal, double *d_sum, double *out) {
+  cudaError_t e = cudaMemsetAsync(d_sum, 0, sizeof(double), s);
+  if (e == cudaSuccess) {
+    int blocks = ceil_div(n_internal, 256);
+    k_tree_area<<<blocks < 1024 ? blocks : 1024, 256, 0, s>>>(box, n_internal, d_sum);
+    e = cudaMemcpyAsync(out, d_sum, sizeof(double), cudaMemcpyDeviceToHost, s);
+  }
+  if (e == cudaSuccess)
+    e = cudaStreamSynchronize(s);
+  return e == cudaSuccess ? RT_OK : rt_cuda_fail(e, "tree_area");
 }
 
 void launch_gather_boxes(cudaStream_t s, const BuildBox *in, const uint32_t *index, BuildBox *out, int n) {

@@ -21,14 +21,23 @@
 
 namespace rtsah {
 
-// RT_BVH=lbvh / RT_BVH=sah force one builder (A/B runs and the tests of both paths).
+// RT_BVH=lbvh / ploc / sah force one builder (A/B runs and the tests of every path).
 inline bool use_sah(int n) {
   const char *e = std::getenv("RT_BVH");
-  if (e && !std::strcmp(e, "lbvh"))
+  if (e && (!std::strcmp(e, "lbvh") || !std::strcmp(e, "ploc")))
     return false;
   if (e && !std::strcmp(e, "sah"))
     return n >= 2;
   return n >= RT_SAH_MIN_PRIMS && n <= RT_SAH_MAX_PRIMS;
+}
+// Device builds (everything the host SAH tree does not take): PLOC by default, the plain Karras LBVH on request.
+inline bool use_ploc(int n) {
+  const char *e = std::getenv("RT_BVH");
+  if (e && !std::strcmp(e, "lbvh"))
+    return false;
+  if (e && !std::strcmp(e, "ploc"))
+    return n >= 2;
+  return n >= RT_SAH_MIN_PRIMS; // a handful of primitives: two levels either way, the radix tree stays
 }
 
 struct HostTree {

@@ -7,6 +7,8 @@
 // 4-wide collapse, rt_bvh.h).
 #include "rt_internal.h"
 
+#include <cstdio>
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -47,10 +49,22 @@ struct Scratch { // frees build scratch on every exit path
 } // namespace
 
 int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
+  // RT_BUILD_TIMING=1: wall-clock phases of the call on stderr (where scene creation time goes)
+  static const bool timing = std::getenv("RT_BUILD_TIMING") != nullptr;
+  auto wall0 = std::chrono::steady_clock::now();
+  auto phase = [&](const char *what) {
+    if (timing) {
+      cudaStreamSynchronize(ctx->stream);
+      auto now = std::chrono::steady_clock::now();
+      std::fprintf(stderr, "[rt_scene_build] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - wall0).count());
+      wall0 = now;
+    }
+  };
   Flat f;
   int st = flatten(desc, f);
   if (st != RT_OK)
     return st;
+  phase("flatten (host, FP64 bake)");
   const int n = (int)f.boxes.size();
   sc->ctx = ctx;
   sc->n_leaf = n;
@@ -73,6 +87,7 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
                       0.5 * (boxes[i].lo[2] + boxes[i].hi[2])});
   }
 
+  phase("leaf boxes (host)");
   const int n_wide_cap = std::max(n, 1);
   RT_CUDA(cudaMalloc((void **)&sc->nodes, (size_t)n_wide_cap * RT_NODE_F4 * sizeof(float4)));
   RT_CUDA(cudaMalloc((void **)&sc->prims, (size_t)std::max(n, 1) * RT_PRIM_F4 * sizeof(float4)));
@@ -145,15 +160,24 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
     RT_CUDA(cudaMemcpyAsync(d_bounds, bounds, sizeof bounds, cudaMemcpyHostToDevice, s));
     RT_CUDA(cudaMemsetAsync(t.visits, 0, sizeof(unsigned int) * (n - 1), s));
 
-    const bool sah = rtsah::use_sah(n);
-    double host_build_ms = 0.0;
-    if (sah) {
-      // small scene: binary SAH tree on the host (rt_sah.h); primitive order, children and boxes are
-      // uploaded in the layout the device hierarchy + refit stages would have produced
+    phase("uploads");
+    // Which binary tree: small scenes get the host SAH tree (rt_sah.h) AND a device PLOC tree and keep the one
+    // with the smaller surface-area sum (the SAH build wins on uniform sphere fields, PLOC on scenes with mixed
+    // primitive sizes such as the final scene: 5.8 against 6.8 node visits per segment); larger scenes are built
+    // on the device only.  RT_BVH = sah / ploc / lbvh forces one builder.
+    const bool forced = std::getenv("RT_BVH") != nullptr;
+    const bool host_sah = rtsah::use_sah(n);
+    const bool device_tree = !host_sah || !forced;
+    const bool ploc = rtsah::use_ploc(n);
+    double host_build_ms = 0.0, host_area = 0.0;
+    if (host_sah) {
       auto t0 = std::chrono::steady_clock::now();
       rtsah::HostTree ht;
       rtsah::build(boxes.data(), n, ht);
+      for (const BuildBox &b : ht.box)
+        host_area += (double)box_area(b);
       host_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      // uploaded in the layout the device stages produce (children, boxes, primitive order)
       RT_CUDA(cudaMemcpyAsync(d_index_sorted, ht.order.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, s));
       RT_CUDA(cudaMemcpyAsync(t.left, ht.left.data(), sizeof(int) * (n - 1), cudaMemcpyHostToDevice, s));
       RT_CUDA(cudaMemcpyAsync(t.right, ht.right.data(), sizeof(int) * (n - 1), cudaMemcpyHostToDevice, s));
@@ -161,19 +185,57 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
       RT_CUDA(cudaStreamSynchronize(s)); // ht goes out of scope
     }
     RT_CUDA(cudaEventRecord(ev0, s));
-    if (!sah) {
+    sc->info.builder = host_sah ? RT_BUILDER_SAH : (ploc ? RT_BUILDER_PLOC : RT_BUILDER_LBVH);
+    if (device_tree) {
+      // the device candidate: Morton order, then PLOC rounds (or the Karras hierarchy + refit)
+      BinTree dt = t;
+      uint32_t *d_order = d_index_sorted;
+      if (host_sah) { // a second set of tree arrays beside the uploaded host tree
+        RT_CUDA(scratch.alloc(&dt.left, n - 1));
+        RT_CUDA(scratch.alloc(&dt.right, n - 1));
+        RT_CUDA(scratch.alloc(&dt.parent, 2 * n - 1));
+        RT_CUDA(scratch.alloc(&dt.box, n - 1));
+        RT_CUDA(scratch.alloc(&d_order, n));
+      }
       launch_morton(s, d_boxes, n, d_bounds, d_bounds + 3, d_codes, d_index);
-      if ((st = sort_pairs(s, d_codes, d_codes_sorted, d_index, d_index_sorted, n)))
+      if ((st = sort_pairs(s, d_codes, d_codes_sorted, d_index, d_order, n)))
         return st;
+      launch_gather_boxes(s, d_boxes, d_order, d_sorted_boxes, n);
+      if (ploc) {
+        PlocCluster *clusters[2] = {nullptr, nullptr};
+        int *d_nearest = nullptr;
+        unsigned long long *d_packed = nullptr;
+        RT_CUDA(scratch.alloc(&clusters[0], n));
+        RT_CUDA(scratch.alloc(&clusters[1], n));
+        RT_CUDA(scratch.alloc(&d_nearest, n));
+        RT_CUDA(scratch.alloc(&d_packed, n));
+        int rounds = 0;
+        if ((st = ploc_build(s, d_sorted_boxes, n, dt, clusters, d_nearest, d_packed, &rounds)))
+          return st;
+      } else {
+        launch_hierarchy(s, d_codes_sorted, dt);
+        launch_refit(s, dt, d_sorted_boxes);
+      }
+      bool keep_device = true;
+      if (host_sah) {
+        double *d_sum = nullptr, device_area = 0.0;
+        RT_CUDA(scratch.alloc(&d_sum, 1));
+        if ((st = tree_area(s, dt.box, n - 1, d_sum, &device_area)))
+          return st;
+        keep_device = device_area < host_area;
+      }
+      if (keep_device) {
+        t = dt;
+        d_index_sorted = d_order;
+        sc->info.builder = ploc ? RT_BUILDER_PLOC : RT_BUILDER_LBVH;
+      }
     }
+    phase("binary tree");
+    // leaf boxes and records in the order of the tree that was kept
     launch_gather_boxes(s, d_boxes, d_index_sorted, d_sorted_boxes, n);
     launch_gather_records(s, d_prims_in, d_index_sorted, sc->prims, n, RT_PRIM_F4 * (int)sizeof(float4));
     static_assert(sizeof(PrimExact) % 16 == 0, "PrimExact must be a multiple of 16 bytes");
     launch_gather_records(s, d_ex_in, d_index_sorted, sc->ex_prims, n, (int)sizeof(PrimExact));
-    if (!sah) {
-      launch_hierarchy(s, d_codes_sorted, t);
-      launch_refit(s, t, d_sorted_boxes);
-    }
 
     // collapse, level by level; the root binary node 0 becomes wide node 0
     CollapseItem root{0, 0, -1};
@@ -198,6 +260,7 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
     sc->info.build_ms = ms + host_build_ms;
     RT_CUDA(cudaMemcpy(order.data(), d_index_sorted, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
     RT_CUDA(cudaGetLastError());
+    phase("gathers + collapse");
   }
   cudaEventDestroy(ev0);
   cudaEventDestroy(ev1);
@@ -251,6 +314,7 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
   sc->ex.chain_first = sc->ex_chain_first;
   sc->ex.chain_count = sc->ex_chain_count;
 
+  phase("leaf tables + host copies");
   sc->info.n_prims = n;
   sc->info.n_nodes = n_wide;
   sc->info.node_bytes = (int64_t)n_wide * RT_NODE_F4 * (int64_t)sizeof(float4);

@@ -197,11 +197,11 @@ int main(int argc, char **argv) {
       // copy ran beside this frame's render, is what gets shown: the host never waits for the GPU to go idle.
       const int k = f & 1;
       CHECK(present(k, scale));
-      if (f == 0)
-        CHECK(rt_frame_download_wait(frame[0])); // the first frame has no predecessor to show
-      else
-        CHECK(rt_frame_download_wait(frame[k ^ 1]));
-      rgb8 = rgb8_buf[f == 0 ? 0 : (k ^ 1)];
+      const bool have_previous = last_queued >= 0;
+      if (have_previous) {
+        CHECK(rt_frame_download_wait(frame[last_queued]));
+        rgb8 = rgb8_buf[last_queued];
+      }
       last_queued = k;
       shown++;
       fps_frames++;
@@ -215,7 +215,7 @@ int main(int argc, char **argv) {
         else if (adaptive && !converged && fps < 15.0 && strata_per_frame > 1)
           strata_per_frame /= 2;
       }
-      if (window) {
+      if (window && have_previous) {
         char line[160]; // draw_fps (:308-348) as the window title
         std::snprintf(line, sizeof line, "Dynamic Camera - %.1f fps, %d/%d samples%s", fps, std::min(taken, total_strata),
                       total_strata, converged ? " - converged" : "");
@@ -227,12 +227,14 @@ int main(int argc, char **argv) {
         std::fprintf(stderr, "[INFO] frame %d: %.3f ms (%.1f FPS)\n", f, f1 - f0, 1000.0 / (f1 - f0));
       }
     }
-    if (window)
-      rth_presenter_close(window);
-    if (last_queued >= 0) { // the last frame queued is the one written out
+    if (last_queued >= 0) { // the last frame queued: shown (one frame behind, like all the others) and written out
       CHECK(rt_frame_download_wait(frame[last_queued]));
       rgb8 = rgb8_buf[last_queued];
+      if (window)
+        rth_presenter_present(window, rgb8, "Dynamic Camera");
     }
+    if (window)
+      rth_presenter_close(window);
     mkdir("output", 0755);
     std::string path = std::string("output/") + opt.output;
     rth_write_ppm_p3(path.c_str(), W, H, rgb8);

@@ -20,6 +20,7 @@ RT_SHAPE_SPHERE, RT_SHAPE_QUAD = range(2)
 RT_PRIM_BOUNDARY = 1
 RT_PERLIN_POINTS = 256
 RT_TRACE_EXACT_F64, RT_TRACE_FAST_F32 = range(2)
+RT_BUILDER_NONE, RT_BUILDER_SAH, RT_BUILDER_PLOC, RT_BUILDER_LBVH = range(4)
 
 d3 = C.c_double * 3
 
@@ -100,7 +101,8 @@ class rt_camera(C.Structure):
 
 class rt_scene_info(C.Structure):
     _fields_ = [("n_prims", C.c_int64), ("n_nodes", C.c_int64), ("node_bytes", C.c_int64),
-                ("prim_bytes", C.c_int64), ("build_ms", C.c_double), ("bounds_min", d3), ("bounds_max", d3)]
+                ("prim_bytes", C.c_int64), ("build_ms", C.c_double), ("bounds_min", d3), ("bounds_max", d3),
+                ("builder", C.c_int32), ("pad_", C.c_int32)]
 
 
 class rt_ray(C.Structure):

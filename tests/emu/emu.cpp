@@ -68,7 +68,13 @@ static void build_bvh(EmuScene &s) {
     std::vector<int> left(n - 1), right(n - 1), parent(2 * n - 1, -2);
     std::vector<BuildBox> box(n - 1);
     std::vector<unsigned int> visits(n - 1, 0);
-    if (rtsah::use_sah(n)) { // small scenes: host SAH tree (rt_sah.h), as rt_scene.cu does
+    // the same choice as rt_scene.cu: host SAH tree for small scenes, a device-style tree (PLOC, or the Karras
+    // LBVH on request) otherwise; without RT_BVH small scenes build both and keep the smaller surface-area sum
+    const bool forced = std::getenv("RT_BVH") != nullptr;
+    const bool host_sah = rtsah::use_sah(n);
+    const bool device_tree = !host_sah || !forced;
+    double host_area = 0.0;
+    if (host_sah) {
       rtsah::HostTree ht;
       rtsah::build(boxes.data(), n, ht);
       order = ht.order;
@@ -76,30 +82,69 @@ static void build_bvh(EmuScene &s) {
       right = ht.right;
       parent = ht.parent;
       box = ht.box;
-      for (int j = 0; j < n; j++)
-        sorted_boxes[j] = boxes[order[j]];
-    } else {
+      for (const BuildBox &b : box)
+        host_area += (double)box_area(b);
+    }
+    if (device_tree) {
+      std::vector<uint32_t> d_order(n);
+      std::iota(d_order.begin(), d_order.end(), 0u);
+      std::vector<int> d_left(n - 1), d_right(n - 1), d_parent(2 * n - 1, -2);
+      std::vector<BuildBox> d_box(n - 1), d_sorted(n);
       std::vector<uint64_t> codes(n), sorted_codes(n);
       for (int i = 0; i < n; i++)
         codes[i] = morton_body(boxes[i], bounds, bounds + 3);
-      std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return codes[a] < codes[b]; });
+      std::stable_sort(d_order.begin(), d_order.end(), [&](uint32_t a, uint32_t b) { return codes[a] < codes[b]; });
       for (int j = 0; j < n; j++) {
-        sorted_codes[j] = codes[order[j]];
-        sorted_boxes[j] = boxes[order[j]];
+        sorted_codes[j] = codes[d_order[j]];
+        d_sorted[j] = boxes[d_order[j]];
       }
-      BinTree t{left.data(), right.data(), parent.data(), box.data(), visits.data(), n};
-      for (int i = 0; i < n - 1; i++)
-        hierarchy_body(sorted_codes.data(), t, i);
-      for (int j = 0; j < n; j++) { // k_refit
-        int node = parent[(n - 1) + j];
-        while (node >= 0) {
-          if (visits[node]++ == 0)
-            break;
-          box[node] = box_union(child_box(t, sorted_boxes.data(), left[node]), child_box(t, sorted_boxes.data(), right[node]));
-          node = parent[node];
+      BinTree t{d_left.data(), d_right.data(), d_parent.data(), d_box.data(), visits.data(), n};
+      if (rtsah::use_ploc(n)) { // k_ploc_nearest / scan / k_ploc_merge, one round per iteration
+        std::vector<PlocCluster> clusters(n), next(n);
+        for (int j = 0; j < n; j++)
+          clusters[j] = PlocCluster{d_sorted[j], ~j, 0};
+        std::vector<int> nearest(n);
+        int count = n, next_node = n - 2;
+        while (count > 1) {
+          for (int i = 0; i < count; i++)
+            nearest[i] = ploc_nearest_body(clusters.data(), count, i);
+          int slot = 0, merges = 0;
+          for (int i = 0; i < count; i++) {
+            int role = ploc_role(nearest.data(), i);
+            ploc_merge_body(clusters.data(), nearest.data(), i, role, slot, next_node - merges, next.data(), t);
+            slot += role >= 0;
+            merges += role > 0;
+          }
+          next_node -= merges;
+          count = slot;
+          clusters.swap(next);
+        }
+      } else {
+        for (int i = 0; i < n - 1; i++)
+          hierarchy_body(sorted_codes.data(), t, i);
+        for (int j = 0; j < n; j++) { // k_refit
+          int node = d_parent[(n - 1) + j];
+          while (node >= 0) {
+            if (visits[node]++ == 0)
+              break;
+            d_box[node] = box_union(child_box(t, d_sorted.data(), d_left[node]), child_box(t, d_sorted.data(), d_right[node]));
+            node = d_parent[node];
+          }
         }
       }
+      double device_area = 0.0;
+      for (const BuildBox &b : d_box)
+        device_area += (double)box_area(b);
+      if (!host_sah || device_area < host_area) {
+        order = d_order;
+        left = d_left;
+        right = d_right;
+        parent = d_parent;
+        box = d_box;
+      }
     }
+    for (int j = 0; j < n; j++)
+      sorted_boxes[j] = boxes[order[j]];
     BinTree t{left.data(), right.data(), parent.data(), box.data(), visits.data(), n};
     std::vector<CollapseItem> items{{0, 0, -1}}, next;
     int wide_count = 1;
@@ -240,6 +285,21 @@ void emu_stats(uint64_t *nodes, uint64_t *leaves, int reset) {
 }
 int emu_scene_nodes(const EmuScene *s) { return s->n_wide; }
 int emu_scene_leaves(const EmuScene *s) { return s->d.n_prims; }
+
+// Surface-area cost of the BVH4: sum over the wide nodes of area(node) / area(root) - the expected number of node
+// visits of a random ray that hits the root box (the quantity rt_scene.cu compares when it has two trees).
+double emu_scene_cost(const EmuScene *s) {
+  double sum = 0.0, root = 0.0;
+  for (int i = 0; i < s->n_wide; i++) {
+    const float4 *n = s->nodes.data() + (size_t)i * RT_NODE_F4;
+    float4 rows[6] = {n[0], n[1], n[2], n[3], n[4], n[5]};
+    double a = box_area(node_bounds(rows, n[6]));
+    if (i == 0)
+      root = a;
+    sum += a;
+  }
+  return root > 0 ? sum / root : 0.0;
+}
 
 // Structural check of the BVH4: every leaf referenced exactly once, every child box inside its
 // parent's slot box.  Returns 0 when consistent, otherwise a small error code.

@@ -31,12 +31,12 @@ def n_surface_prims(desc):
     return desc.contents.n_spheres + desc.contents.n_quads
 
 
-@pytest.mark.parametrize("bvh", ["sah", "lbvh"])
+@pytest.mark.parametrize("bvh", ["sah", "lbvh", "ploc"])
 @pytest.mark.parametrize("name", ["spheres", "spheres_textured", "cornell", "final"])
 def test_exact_trace_equals_the_reference(ctx, scene_index, host_scenes, name, bvh, monkeypatch):
     """Rays and answers both come from the unmodified reference (golden fixtures): primary rays of one
     stratum and every segment of a small render.  FP64 parity mode must reproduce t, object and front face
-    bit for bit - over the host SAH tree (small scenes' default) and over the device LBVH."""
+    bit for bit - over the host SAH tree and over both device builds (PLOC, Karras LBVH)."""
     g = load_golden(name)
     meta = scene_index[name]
     hs = host_scenes(meta["builtin"], meta["p0"], meta["p1"], meta["seed"])
@@ -649,3 +649,22 @@ def test_at_size_rmse_against_the_reference_render(ctx, host_scenes, cid, name, 
     assert d["ratio"] <= 1.15, d
     assert d["block8_ratio"] <= 1.15, d
     assert abs(d["luminance_rel_diff"]) <= 0.005, d
+
+
+def test_builder_choice(ctx, host_scenes, monkeypatch):
+    """rt_scene_info.builder: the uniform sphere field keeps the host SAH tree, the final scene (mixed primitive
+    sizes) the device PLOC tree, a handful of primitives the radix tree; RT_BVH forces a builder."""
+    monkeypatch.delenv("RT_BVH", raising=False)
+    for name, p0, p1, want in [("spheres", 11, -1, abi.RT_BUILDER_SAH), ("final", 20, 1000, abi.RT_BUILDER_PLOC),
+                               ("cornell", 0, -1, abi.RT_BUILDER_LBVH), ("spheres", 150, -1, abi.RT_BUILDER_PLOC)]:
+        hs = host_scenes(name, p0, p1)
+        scene = engine.Scene(ctx, hs.desc)
+        assert scene.info().builder == want, (name, scene.info().builder)
+        scene.close()
+    hs = host_scenes("final", 5, 60)
+    for mode, want in [("sah", abi.RT_BUILDER_SAH), ("ploc", abi.RT_BUILDER_PLOC), ("lbvh", abi.RT_BUILDER_LBVH)]:
+        monkeypatch.setenv("RT_BVH", mode)
+        scene = engine.Scene(ctx, hs.desc)
+        assert scene.info().builder == want
+        scene.close()
+    assert engine.Scene(ctx, abi.rt_scene_desc()).info().builder == abi.RT_BUILDER_NONE

@@ -252,9 +252,9 @@ int rt_context_synchronize(rt_context *ctx);
 /* The context's cudaStream_t as an integer (so callers can record CUDA events on it). */
 uint64_t rt_context_stream(rt_context *ctx);
 
-/* Upload the scene, bake instance transforms, build the binary tree (on the device: Morton sort + PLOC; small
- * scenes also try a host SAH tree and keep the better one) and collapse it into 4-wide nodes on the device.  The
- * description may be freed after the call returns. */
+/* Upload the scene, bake instance transforms, build the binary tree (64 .. 65,536 primitives: SAH on the host;
+ * otherwise on the device: Morton sort + Karras radix tree, or PLOC with RT_BVH=ploc) and collapse it into 4-wide
+ * nodes on the device.  The description may be freed after the call returns. */
 int rt_scene_create(rt_context *ctx, const rt_scene_desc *desc, rt_scene **out);
 void rt_scene_destroy(rt_scene *scene);
 

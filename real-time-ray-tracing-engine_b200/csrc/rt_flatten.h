@@ -14,11 +14,32 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <thread>
 #include <vector>
 
 void rt_set_error(const std::string &msg);
 
 namespace rtflat {
+
+// body(first, last) over [0, n) on up to 16 host threads; small ranges run on the caller.  The million-primitive
+// scenes spend their creation time in per-primitive FP64 baking, which is independent per primitive.
+template <class Body> inline void parallel_for(size_t n, Body body) {
+  const size_t kMinPerThread = 16384;
+  size_t threads = std::min<size_t>(std::min<size_t>(std::thread::hardware_concurrency(), 16), n / kMinPerThread);
+  if (threads <= 1) {
+    body((size_t)0, n);
+    return;
+  }
+  std::vector<std::thread> pool;
+  size_t chunk = (n + threads - 1) / threads;
+  for (size_t t = 0; t < threads; t++) {
+    size_t a = t * chunk, b = std::min(n, a + chunk);
+    if (a < b)
+      pool.emplace_back([=, &body]() { body(a, b); });
+  }
+  for (std::thread &t : pool)
+    t.join();
+}
 
 struct D3 {
   double x, y, z;
@@ -148,16 +169,16 @@ inline void embed_sphere_material(float4 *rec, const std::vector<float4> &mats) 
   rec[2] = m0;
 }
 
-inline void push_sphere(const Baker &bk, const rt_sphere &s, int id, int material, std::vector<float4> &fast,
-                 std::vector<PrimExact> &exact, BoxD &box) {
+// rec: the 4 float4 of the render-path record, exact: the FP64 parity record, box: grown by the primitive's bounds
+inline void bake_sphere(const Baker &bk, const rt_sphere &s, int id, int material, float4 *rec, PrimExact &exact, BoxD &box) {
   D3 c0 = bk.point(s.xform, d3(s.center0));
   D3 dir = bk.vector(s.xform, d3(s.center_dir));
   double r = std::fmax(0.0, s.radius);
   int typemat = (RT_PT_SPHERE << 28) | (material < 0 ? 0 : material);
-  fast.push_back(f4(c0, (float)r));
-  fast.push_back(f4(dir, 0.f));
-  fast.push_back(make_float4(0.f, 0.f, 0.f, 0.f));
-  fast.push_back(make_float4(0.f, ibits(typemat), ibits(id), ibits(s.object)));
+  rec[0] = f4(c0, (float)r);
+  rec[1] = f4(dir, 0.f);
+  rec[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+  rec[3] = make_float4(0.f, ibits(typemat), ibits(id), ibits(s.object));
   PrimExact e{};
   std::memcpy(e.a, s.center0, sizeof e.a);
   std::memcpy(e.b, s.center_dir, sizeof e.b);
@@ -168,7 +189,7 @@ inline void push_sphere(const Baker &bk, const rt_sphere &s, int id, int materia
   e.object = s.object;
   e.closed = 0;
   e.medium = -1;
-  exact.push_back(e);
+  exact = e;
   D3 c1 = c0 + dir;
   D3 rv = {r, r, r};
   box.grow(c0 - rv);
@@ -177,8 +198,14 @@ inline void push_sphere(const Baker &bk, const rt_sphere &s, int id, int materia
   box.grow(c1 + rv);
 }
 
-inline void push_quad(const Baker &bk, const rt_quad &q, int id, int material, std::vector<float4> &fast,
-               std::vector<PrimExact> &exact, BoxD &box) {
+inline void push_sphere(const Baker &bk, const rt_sphere &s, int id, int material, std::vector<float4> &fast,
+                        std::vector<PrimExact> &exact, BoxD &box) {
+  fast.resize(fast.size() + RT_PRIM_F4);
+  exact.emplace_back();
+  bake_sphere(bk, s, id, material, &fast[fast.size() - RT_PRIM_F4], exact.back(), box);
+}
+
+inline void bake_quad(const Baker &bk, const rt_quad &q, int id, int material, float4 *rec, PrimExact &exact, BoxD &box) {
   // world-space record for the render path
   D3 Q = bk.point(q.xform, d3(q.corner));
   D3 u = bk.vector(q.xform, d3(q.u)), v = bk.vector(q.xform, d3(q.v));
@@ -188,10 +215,10 @@ inline void push_quad(const Baker &bk, const rt_quad &q, int id, int material, s
   D3 w = (1.0 / dotd(n, n)) * n;
   D3 A = crossd(v, w), B = crossd(w, u);
   int typemat = (RT_PT_QUAD << 28) | (material < 0 ? 0 : material);
-  fast.push_back(f4(normal, (float)D));
-  fast.push_back(f4(A, (float)Q.x));
-  fast.push_back(f4(B, (float)Q.y));
-  fast.push_back(make_float4((float)Q.z, ibits(typemat), ibits(id), ibits(q.object)));
+  rec[0] = f4(normal, (float)D);
+  rec[1] = f4(A, (float)Q.x);
+  rec[2] = f4(B, (float)Q.y);
+  rec[3] = make_float4((float)Q.z, ibits(typemat), ibits(id), ibits(q.object));
   // object-space record for the FP64 parity path: Plane's constructor (Plane.cpp:6-21)
   PrimExact e{};
   D3 qo = d3(q.corner), uo = d3(q.u), vo = d3(q.v);
@@ -210,11 +237,18 @@ inline void push_quad(const Baker &bk, const rt_quad &q, int id, int material, s
   e.object = q.object;
   e.closed = 1;
   e.medium = -1;
-  exact.push_back(e);
+  exact = e;
   box.grow(Q);
   box.grow(Q + u);
   box.grow(Q + v);
   box.grow(Q + u + v);
+}
+
+inline void push_quad(const Baker &bk, const rt_quad &q, int id, int material, std::vector<float4> &fast,
+                      std::vector<PrimExact> &exact, BoxD &box) {
+  fast.resize(fast.size() + RT_PRIM_F4);
+  exact.emplace_back();
+  bake_quad(bk, q, id, material, &fast[fast.size() - RT_PRIM_F4], exact.back(), box);
 }
 
 constexpr double kMaxCoordinate = 1e18; // FP32 box areas stay finite: 6 * (2e18)^2 < FLT_MAX
@@ -254,7 +288,10 @@ inline int flatten(const rt_scene_desc *d, Flat &f) {
     f.ops.push_back(e);
   }
 
-  // surfaces
+  // surfaces: indices are checked and record slots handed out in one cheap serial pass, the FP64 baking of the
+  // records (instance chain, parity record, bounds) then runs over all host threads
+  std::vector<int> sphere_slot(d->n_spheres, -1), quad_slot(d->n_quads, -1);
+  int n_surface = 0;
   for (int i = 0; i < d->n_spheres; i++) {
     const rt_sphere &s = d->spheres[i];
     if (!check_xf(s.xform))
@@ -263,9 +300,7 @@ inline int flatten(const rt_scene_desc *d, Flat &f) {
       continue;
     if (!check_mat(s.material))
       return fail_invalid("sphere material index");
-    BoxD box;
-    push_sphere(bk, s, i, s.material, f.prims, f.ex_prims, box);
-    f.boxes.push_back(box);
+    sphere_slot[i] = n_surface++;
   }
   for (int i = 0; i < d->n_quads; i++) {
     const rt_quad &q = d->quads[i];
@@ -275,10 +310,26 @@ inline int flatten(const rt_scene_desc *d, Flat &f) {
       continue;
     if (!check_mat(q.material))
       return fail_invalid("quad material index");
-    BoxD box;
-    push_quad(bk, q, d->n_spheres + i, q.material, f.prims, f.ex_prims, box);
-    f.boxes.push_back(box);
+    quad_slot[i] = n_surface++;
   }
+  f.prims.resize((size_t)n_surface * RT_PRIM_F4);
+  f.ex_prims.resize(n_surface);
+  f.boxes.resize(n_surface);
+  parallel_for((size_t)d->n_spheres, [&](size_t a, size_t b) {
+    for (size_t i = a; i < b; i++)
+      if (sphere_slot[i] >= 0) {
+        const int k = sphere_slot[i];
+        bake_sphere(bk, d->spheres[i], (int)i, d->spheres[i].material, &f.prims[(size_t)k * RT_PRIM_F4], f.ex_prims[k], f.boxes[k]);
+      }
+  });
+  parallel_for((size_t)d->n_quads, [&](size_t a, size_t b) {
+    for (size_t i = a; i < b; i++)
+      if (quad_slot[i] >= 0) {
+        const int k = quad_slot[i];
+        bake_quad(bk, d->quads[i], d->n_spheres + (int)i, d->quads[i].material, &f.prims[(size_t)k * RT_PRIM_F4], f.ex_prims[k],
+                  f.boxes[k]);
+      }
+  });
   // constant media: one leaf each, boundary records on the side
   for (int m = 0; m < d->n_media; m++) {
     const rt_medium &md = d->media[m];
@@ -385,8 +436,10 @@ inline int flatten(const rt_scene_desc *d, Flat &f) {
     f.mats.push_back(b);
   }
 
-  for (size_t r = 0; r + RT_PRIM_F4 <= f.prims.size(); r += RT_PRIM_F4)
-    embed_sphere_material(&f.prims[r], f.mats);
+  parallel_for(f.prims.size() / RT_PRIM_F4, [&](size_t a, size_t b) {
+    for (size_t r = a; r < b; r++)
+      embed_sphere_material(&f.prims[r * RT_PRIM_F4], f.mats);
+  });
 
   // Geometry the FP32 build cannot order is refused here, not rendered: a NaN / infinite coordinate, or a box
   // whose FP32 surface area overflows (|coordinate| above ~1e18), would leave the SAH sweep without a finite

@@ -30,14 +30,13 @@ inline bool use_sah(int n) {
     return n >= 2;
   return n >= RT_SAH_MIN_PRIMS && n <= RT_SAH_MAX_PRIMS;
 }
-// Device builds (everything the host SAH tree does not take): PLOC by default, the plain Karras LBVH on request.
+// Device builds: the Karras radix tree by default, PLOC (rt_bvh.h) on request (RT_BVH=ploc).  Measured on B200
+// (profiles/r02_experiments.md): PLOC cuts the node visits of the final scene from 6.8 (host SAH) to 5.8 per
+// segment and still renders 3 % slower (more of the expensive medium leaves are reached), and on the uniform
+// sphere fields it visits 7 % MORE nodes than the radix tree, whose Morton splits are spatial medians of the grid.
 inline bool use_ploc(int n) {
   const char *e = std::getenv("RT_BVH");
-  if (e && !std::strcmp(e, "lbvh"))
-    return false;
-  if (e && !std::strcmp(e, "ploc"))
-    return n >= 2;
-  return n >= RT_SAH_MIN_PRIMS; // a handful of primitives: two levels either way, the radix tree stays
+  return e && !std::strcmp(e, "ploc") && n >= 2;
 }
 
 struct HostTree {

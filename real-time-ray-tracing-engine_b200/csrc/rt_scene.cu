@@ -18,6 +18,7 @@
 #include "rt_sah.h"
 
 #include <chrono>
+#include <mutex>
 
 using namespace rtflat;
 
@@ -80,11 +81,20 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
 
   std::vector<BuildBox> boxes(n);
   BoxD all, centroids;
-  for (int i = 0; i < n; i++) {
-    boxes[i] = to_build_box(f.boxes[i]);
-    all.grow(f.boxes[i]);
-    centroids.grow(D3{0.5 * (boxes[i].lo[0] + boxes[i].hi[0]), 0.5 * (boxes[i].lo[1] + boxes[i].hi[1]),
-                      0.5 * (boxes[i].lo[2] + boxes[i].hi[2])});
+  {
+    std::mutex merge;
+    parallel_for((size_t)n, [&](size_t a, size_t b) {
+      BoxD my_all, my_centroids;
+      for (size_t i = a; i < b; i++) {
+        boxes[i] = to_build_box(f.boxes[i]);
+        my_all.grow(f.boxes[i]);
+        my_centroids.grow(D3{0.5 * (boxes[i].lo[0] + boxes[i].hi[0]), 0.5 * (boxes[i].lo[1] + boxes[i].hi[1]),
+                             0.5 * (boxes[i].lo[2] + boxes[i].hi[2])});
+      }
+      std::lock_guard<std::mutex> lock(merge);
+      all.grow(my_all);
+      centroids.grow(my_centroids);
+    });
   }
 
   phase("leaf boxes (host)");
@@ -161,14 +171,15 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
     RT_CUDA(cudaMemsetAsync(t.visits, 0, sizeof(unsigned int) * (n - 1), s));
 
     phase("uploads");
-    // Which binary tree: small scenes get the host SAH tree (rt_sah.h) AND a device PLOC tree and keep the one
-    // with the smaller surface-area sum (the SAH build wins on uniform sphere fields, PLOC on scenes with mixed
-    // primitive sizes such as the final scene: 5.8 against 6.8 node visits per segment); larger scenes are built
-    // on the device only.  RT_BVH = sah / ploc / lbvh forces one builder.
-    const bool forced = std::getenv("RT_BVH") != nullptr;
+    // Which binary tree: the host SAH tree (rt_sah.h) from 64 to 65,536 primitives, a device tree otherwise (the
+    // Karras radix tree; PLOC with RT_BVH=ploc).  RT_BVH = sah / lbvh / ploc forces one builder; RT_BVH=best
+    // builds the host SAH tree AND the PLOC tree and keeps the smaller surface-area sum (an experiment aid: the
+    // area sum picks the tree with fewer node visits, which was not the faster one on the final scene).
+    const char *bvh_env = std::getenv("RT_BVH");
+    const bool best_of = bvh_env && !std::strcmp(bvh_env, "best") && n >= RT_SAH_MIN_PRIMS && n <= RT_SAH_MAX_PRIMS;
     const bool host_sah = rtsah::use_sah(n);
-    const bool device_tree = !host_sah || !forced;
-    const bool ploc = rtsah::use_ploc(n);
+    const bool device_tree = !host_sah || best_of;
+    const bool ploc = rtsah::use_ploc(n) || best_of;
     double host_build_ms = 0.0, host_area = 0.0;
     if (host_sah) {
       auto t0 = std::chrono::steady_clock::now();
@@ -267,10 +278,12 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
 
   // per-leaf object / id tables in leaf order
   std::vector<int> leaf_object(std::max(n, 1), -1), leaf_id(std::max(n, 1), -1);
-  for (int j = 0; j < n; j++) {
-    leaf_object[j] = f.ex_prims[order[j]].object;
-    leaf_id[j] = f.ex_prims[order[j]].id;
-  }
+  parallel_for((size_t)n, [&](size_t a, size_t b) {
+    for (size_t j = a; j < b; j++) {
+      leaf_object[j] = f.ex_prims[order[j]].object;
+      leaf_id[j] = f.ex_prims[order[j]].id;
+    }
+  });
   RT_CUDA(cudaMemcpy(sc->leaf_object, leaf_object.data(), sizeof(int) * leaf_object.size(), cudaMemcpyHostToDevice));
   RT_CUDA(cudaMemcpy(sc->leaf_id, leaf_id.data(), sizeof(int) * leaf_id.size(), cudaMemcpyHostToDevice));
 

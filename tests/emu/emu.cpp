@@ -68,11 +68,12 @@ static void build_bvh(EmuScene &s) {
     std::vector<int> left(n - 1), right(n - 1), parent(2 * n - 1, -2);
     std::vector<BuildBox> box(n - 1);
     std::vector<unsigned int> visits(n - 1, 0);
-    // the same choice as rt_scene.cu: host SAH tree for small scenes, a device-style tree (PLOC, or the Karras
-    // LBVH on request) otherwise; without RT_BVH small scenes build both and keep the smaller surface-area sum
-    const bool forced = std::getenv("RT_BVH") != nullptr;
+    // the same choice as rt_scene.cu: host SAH tree for small scenes, a device-style tree (the Karras LBVH, or PLOC
+    // on request) otherwise; RT_BVH=best builds the SAH and the PLOC tree and keeps the smaller surface-area sum
+    const char *bvh_env = std::getenv("RT_BVH");
+    const bool best_of = bvh_env && !std::strcmp(bvh_env, "best") && n >= RT_SAH_MIN_PRIMS && n <= RT_SAH_MAX_PRIMS;
     const bool host_sah = rtsah::use_sah(n);
-    const bool device_tree = !host_sah || !forced;
+    const bool device_tree = !host_sah || best_of;
     double host_area = 0.0;
     if (host_sah) {
       rtsah::HostTree ht;
@@ -99,7 +100,7 @@ static void build_bvh(EmuScene &s) {
         d_sorted[j] = boxes[d_order[j]];
       }
       BinTree t{d_left.data(), d_right.data(), d_parent.data(), d_box.data(), visits.data(), n};
-      if (rtsah::use_ploc(n)) { // k_ploc_nearest / scan / k_ploc_merge, one round per iteration
+      if (rtsah::use_ploc(n) || best_of) { // k_ploc_nearest / scan / k_ploc_merge, one round per iteration
         std::vector<PlocCluster> clusters(n), next(n);
         for (int j = 0; j < n; j++)
           clusters[j] = PlocCluster{d_sorted[j], ~j, 0};

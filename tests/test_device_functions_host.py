@@ -163,9 +163,9 @@ def test_fast_division_by_invariant_integers(emu):
 
 @pytest.mark.parametrize("name,p0", [("spheres", 11), ("final", 5), ("cornell", 0)])
 def test_all_bvh_builders_answer_alike(oracle, emu, host_scenes, monkeypatch, name, p0):
-    """Host SAH tree (rt_sah.h), PLOC and the Karras LBVH (rt_bvh.h), and the automatic choice between them: all
-    consistent, and the FP64 traversal finds the same hits in each; the SAH tree must not need more node visits than
-    the LBVH on the bigger scenes, and the automatic choice must be as good as the better of SAH and PLOC."""
+    """Host SAH tree (rt_sah.h), PLOC and the Karras LBVH (rt_bvh.h), and RT_BVH=best (SAH or PLOC by surface-area sum):
+    all consistent, and the FP64 traversal finds the same hits in each; the SAH tree must not need more node visits
+    than the LBVH on the bigger scenes, and `best` must visit as few nodes as the better of SAH and PLOC."""
     emu.emu_stats.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int]
     hs = host_scenes(name, p0, 60 if name == "final" else -1)
     cfg = hs.camera_config(64, 1, 8)
@@ -173,11 +173,8 @@ def test_all_bvh_builders_answer_alike(oracle, emu, host_scenes, monkeypatch, na
     _, rays, _ = oracle_segments(oracle, osc, cfg, ol.ORA_RNG_PHILOX, ol.ORA_SAMPLER_POLAR, 7, 1)
     n = len(rays)
     hits, visits = {}, {}
-    for mode in ("lbvh", "sah", "ploc", "auto"):
-        if mode == "auto":
-            monkeypatch.delenv("RT_BVH", raising=False)
-        else:
-            monkeypatch.setenv("RT_BVH", mode)
+    for mode in ("lbvh", "sah", "ploc", "best"):
+        monkeypatch.setenv("RT_BVH", mode)
         es = emu.emu_scene_create(hs.desc)
         assert es and emu.emu_scene_check_bvh(es) == 0
         out = (abi.rt_hit * n)()
@@ -189,12 +186,12 @@ def test_all_bvh_builders_answer_alike(oracle, emu, host_scenes, monkeypatch, na
         emu.emu_trace(es, rays, n, abi.RT_TRACE_EXACT_F64, 7, out)
         hits[mode] = ol.hits_to_numpy(out)
         emu.emu_scene_destroy(es)
-    for mode in ("sah", "ploc", "auto"):
+    for mode in ("sah", "ploc", "best"):
         for k in ("t", "prim", "object", "front_face"):
             assert np.array_equal(hits["lbvh"][k], hits[mode][k]), (mode, k)
     if name != "cornell":  # 13 primitives: either tree is two levels
         assert visits["sah"] < visits["lbvh"], visits
-        assert visits["auto"] <= 1.02 * min(visits["sah"], visits["ploc"]), visits
+        assert visits["best"] <= 1.02 * min(visits["sah"], visits["ploc"]), visits
     oracle.ora_scene_destroy(osc)
 
 

@@ -652,19 +652,24 @@ def test_at_size_rmse_against_the_reference_render(ctx, host_scenes, cid, name, 
 
 
 def test_builder_choice(ctx, host_scenes, monkeypatch):
-    """rt_scene_info.builder: the uniform sphere field keeps the host SAH tree, the final scene (mixed primitive
-    sizes) the device PLOC tree, a handful of primitives the radix tree; RT_BVH forces a builder."""
+    """rt_scene_info.builder: host SAH tree from 64 to 65,536 primitives, the device radix tree otherwise; RT_BVH forces
+    a builder; RT_BVH=best keeps the smaller surface-area sum of the SAH and the PLOC tree (PLOC on the final scene)."""
     monkeypatch.delenv("RT_BVH", raising=False)
-    for name, p0, p1, want in [("spheres", 11, -1, abi.RT_BUILDER_SAH), ("final", 20, 1000, abi.RT_BUILDER_PLOC),
-                               ("cornell", 0, -1, abi.RT_BUILDER_LBVH), ("spheres", 150, -1, abi.RT_BUILDER_PLOC)]:
+    for name, p0, p1, want in [("spheres", 11, -1, abi.RT_BUILDER_SAH), ("final", 20, 1000, abi.RT_BUILDER_SAH),
+                               ("cornell", 0, -1, abi.RT_BUILDER_LBVH), ("spheres", 150, -1, abi.RT_BUILDER_LBVH)]:
         hs = host_scenes(name, p0, p1)
         scene = engine.Scene(ctx, hs.desc)
         assert scene.info().builder == want, (name, scene.info().builder)
         scene.close()
     hs = host_scenes("final", 5, 60)
-    for mode, want in [("sah", abi.RT_BUILDER_SAH), ("ploc", abi.RT_BUILDER_PLOC), ("lbvh", abi.RT_BUILDER_LBVH)]:
+    for mode, want in [("sah", abi.RT_BUILDER_SAH), ("ploc", abi.RT_BUILDER_PLOC), ("lbvh", abi.RT_BUILDER_LBVH),
+                       ("best", abi.RT_BUILDER_PLOC)]:
         monkeypatch.setenv("RT_BVH", mode)
         scene = engine.Scene(ctx, hs.desc)
-        assert scene.info().builder == want
+        assert scene.info().builder == want, mode
         scene.close()
+    monkeypatch.setenv("RT_BVH", "best")
+    scene = engine.Scene(ctx, host_scenes("spheres", 11, -1).desc)
+    assert scene.info().builder == abi.RT_BUILDER_SAH
+    scene.close()
     assert engine.Scene(ctx, abi.rt_scene_desc()).info().builder == abi.RT_BUILDER_NONE

@@ -25,6 +25,7 @@ Printed JSON (one line, rank 0):
   static_4k    strong scaling: the final scene at 3840x2160, 16 spp, depth 50 - fixed total work over the N GPUs -
                with the SHA-256 of the assembled RGB8 frame (identical for every N)
   frame_sha    SHA-256 of one assembled 1080p frame of the benchmark scene (stratum 0, fixed seed; identical for every N)
+  gpu_reference  the reference's own GPU kernels (unmodified, compiled for sm_100) on the same frame and GPU (N=1 only)
   cpu_baseline the reference's own CPU implementation (oracle/_ref, all host threads) on the same frame
 `--impl reference` times only that CPU implementation.
 """
@@ -438,6 +439,9 @@ def run_ours(args):
     # ---- BASELINE config 1 against the reference's own render (rank 0) ----
     rmse = rmse_leg(ctx) if rank == 0 else None
 
+    # ---- the reference's own GPU kernels on this GPU, same frame (informational comparator, own process) ----
+    gpu_reference = gpu_reference_leg(ms_step) if rank == 0 and world == 1 else None
+
     peaks = {}
     try:
         with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
@@ -486,6 +490,7 @@ def run_ours(args):
                 "primary_mismatch_rate": audit_sum[3] / max(1.0, audit_sum[2]),
                 "hit_miss_flips": int(audit_sum[4]), "max_rel_t_error_same_prim": audit_max_t}},
             "rmse": rmse,
+            "gpu_reference": gpu_reference,
             "frame_sha": frame_sha,
             "static_4k": static_4k,
             "cpu_baseline": dict(cpu_desc, value=cpu_value, unit="Mpath-samples/s"),
@@ -647,6 +652,29 @@ def rmse_leg(ctx):
     film.close()
     scene.close()
     hs.close()
+    return out
+
+
+def gpu_reference_leg(our_frame_ms):
+    """The reference's OWN GPU path (its .cu kernels compiled unmodified for sm_100, oracle/_ref_gpu) on the benchmark
+    frame, on this GPU, in a process of its own (tools/ref_gpu_frame.py): the reference's per-tile launch loop with
+    its per-frame full-buffer copy (DynamicCamera.cpp:458-554), the loop alone, and one whole-frame launch of its
+    kernel.  Informational: the headline ratio stays the driver's, against the CPU arm."""
+    import subprocess
+
+    try:
+        r = subprocess.run([sys.executable, os.path.join(REPO, "tools", "ref_gpu_frame.py"), SCENE, "11", str(WIDTH), str(DEPTH), "3"],
+                           capture_output=True, text=True, timeout=600)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        out = json.loads(lines[-1]) if lines else {"error": (r.stderr or "no output")[-300:]}
+    except Exception as e:  # a comparator that cannot run is reported, never fatal
+        out = {"error": repr(e)}
+    out["what"] = ("the reference's own CUDA path (FP64, recursive megakernel, XORWOW state per pixel), unmodified sources compiled "
+                   "for sm_100, one 1920x1080 1-spp depth-8 frame of the same scene on this GPU")
+    out["ours_frame_ms"] = our_frame_ms
+    for key in ("tile32_with_copy", "tile32", "whole_frame_launch"):
+        if isinstance(out.get(key), dict) and out[key].get("ms_per_frame"):
+            out[key]["ratio_over_ours"] = out[key]["ms_per_frame"] / our_frame_ms
     return out
 
 

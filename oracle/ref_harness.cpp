@@ -52,6 +52,14 @@
 
 #include "../include/rt_b200.h"
 
+#ifdef USE_CUDA // the GPU comparator build (oracle/_ref_gpu): the reference's own CUDA path
+#include "core/camera/CameraKernelWrappers.cuh"
+#include "scene/CudaSceneInitialization.cuh"
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdio>
+#endif
+
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -177,6 +185,9 @@ struct RefScene {
   int n_objects = 0;
   // render-time acceleration structure (built lazily)
   std::shared_ptr<HittableList> bvh_world;
+  // plain = true: only reference classes in the object graph (no tagging / time-fix decorators), as the
+  // reference's own scene functions build it - what its CPU -> CUDA converters understand (ref_gpu_frame)
+  bool plain = false;
 
   // ---- textures ----
   Tex solid(const Color &c) {
@@ -242,7 +253,7 @@ struct RefScene {
   }
   Mat dielectric(double ior) {
     MaterialPtr d = std::make_shared<DielectricMaterial>(ior);
-    return push_mat(std::make_shared<TimeFixMaterial>(d), RT_MAT_DIELECTRIC, -1, Color(), 0, ior);
+    return push_mat(plain ? d : std::make_shared<TimeFixMaterial>(d), RT_MAT_DIELECTRIC, -1, Color(), 0, ior);
   }
   Mat diffuse_light(const Color &c) {
     Tex t = solid(c);
@@ -339,7 +350,10 @@ struct RefScene {
 
   // ---- top-level world objects ----
   void add_object(HittablePtr obj) {
-    world.add(std::make_shared<Tagged>(std::move(obj), n_objects));
+    if (plain)
+      world.add(std::move(obj));
+    else
+      world.add(std::make_shared<Tagged>(std::move(obj), n_objects));
     ++n_objects;
   }
   void add_sphere(const Point3 &c, double r, const Mat &m) {
@@ -406,7 +420,10 @@ struct RefScene {
     set3(l.a, c);
     l.radius = r;
     light_recs.push_back(l);
-    lights.add(std::make_shared<FixedTimeSphereLight>(c, r, MaterialPtr()));
+    if (plain)
+      lights.add(std::make_shared<Sphere>(c, r, MaterialPtr()));
+    else
+      lights.add(std::make_shared<FixedTimeSphereLight>(c, r, MaterialPtr()));
   }
 
   void finalize() {
@@ -674,9 +691,13 @@ extern "C" {
 
 // name: "spheres" (p0 = grid half size, default 11), "spheres_textured" (C4 generator, p0 = half
 // size), "cornell", "cornell_smoke", "final" (p0 = boxes per side, p1 = cluster spheres).
-void *ref_scene_build(const char *name, uint64_t seed, int p0, int p1) {
+static void *scene_build(const char *name, uint64_t seed, int p0, int p1, bool plain);
+void *ref_scene_build(const char *name, uint64_t seed, int p0, int p1) { return scene_build(name, seed, p0, p1, false); }
+
+static void *scene_build(const char *name, uint64_t seed, int p0, int p1, bool plain) {
   random_engine().seed(static_cast<std::mt19937::result_type>(seed));
   RefScene *s = new RefScene();
+  s->plain = plain;
   std::string n(name);
   if (n == "spheres")
     build_spheres(*s, p0 > 0 ? p0 : 11, false);
@@ -858,6 +879,107 @@ double ref_render(void *h, int width, int spp, int depth, uint64_t seed, int use
     *segments = total_segments.load();
   return std::chrono::duration<double>(t1 - t0).count();
 }
+
+#ifdef USE_CUDA
+// ---------------------------------------------------------------------------------------------------
+// The reference's own GPU path, timed as an informational comparator (oracle/_ref_gpu/libref_gpu.so: the
+// reference's .cu and .cpp sources compiled with -DUSE_CUDA for sm_100, nothing of this repository's library).
+// One dynamic-mode frame exactly as DynamicCamera::render_gpu drives it (DynamicCamera.cpp:434-554): scene
+// converted by initialize_cuda_scene, one curand state per pixel, then per displayed frame one
+// cuda_dynamic_render_tile_wrapper launch + cudaDeviceSynchronize per tile and a full-buffer copy to the host.
+//   tile_size > 0 : the reference's loop (its default tile size is 32)
+//   tile_size = 0 : ONE launch of the same kernel over the whole frame (what the kernel itself can do)
+// Returns 0 on success.  ms_frame = wall time per frame of the launch loop (+ the device-to-host copy when
+// with_copy), mean = mean of the accumulated radiance / frames (a sanity check of the picture).
+// ---------------------------------------------------------------------------------------------------
+int ref_gpu_frame(const char *name, uint64_t seed, int p0, int p1, int width, int depth, int tile_size, int frames,
+                  int with_copy, double *ms_frame, double *mean, char *error, int error_len) {
+  auto fail = [&](const std::string &msg) {
+    if (error && error_len > 0)
+      std::snprintf(error, error_len, "%s", msg.c_str());
+    return 1;
+  };
+  RefScene *s = static_cast<RefScene *>(scene_build(name, seed, p0, p1, true));
+  if (!s)
+    return fail("unknown scene");
+  HarnessCamera cam(make_config(*s, width, 1, depth));
+  rt_camera rc{};
+  cam.export_derived(&rc);
+  const int W = cam.width(), H = cam.height();
+  // -b: the world (and the lights) wrapped in the reference's BVH (StaticCamera.cpp:140-145)
+  HittableList world = s->world, lights = s->lights;
+  if (!world.get_objects().empty())
+    world = HittableList(std::make_shared<BVHNode>(world));
+  if (!lights.get_objects().empty())
+    lights = HittableList(std::make_shared<BVHNode>(lights));
+
+  CudaColor *d_accum = nullptr;
+  curandState *d_rand = nullptr;
+  const size_t accum_bytes = size_t(W) * H * sizeof(CudaColor);
+  if (cudaMalloc(&d_accum, accum_bytes) != cudaSuccess || cudaMalloc(&d_rand, size_t(W) * H * sizeof(curandState)) != cudaSuccess)
+    return fail("cudaMalloc failed");
+  cudaMemset(d_accum, 0, accum_bytes);
+  dim3 block(16, 16), grid((W + 15) / 16, (H + 15) / 16);
+  cuda_init_rand_states_wrapper(d_rand, W, H, (unsigned long)seed, grid, block);
+  if (cudaDeviceSynchronize() != cudaSuccess)
+    return fail(std::string("init_rand_states: ") + cudaGetErrorString(cudaGetLastError()));
+  CudaSceneData scene = initialize_cuda_scene(world, lights, false);
+  if (!scene.world.get() || !scene.lights.get())
+    return fail("initialize_cuda_scene returned null");
+
+  auto v3 = [](const double *p) { return CudaVec3(p[0], p[1], p[2]); };
+  // u, v, w only feed the kernel's signature (get_ray_cuda uses the derived vectors); recomputed as Camera::initialize does
+  Vec3 cw = unit_vector(s->cam.lookfrom - s->cam.lookat), cu = unit_vector(cross_product(s->cam.vup, cw)), cv = cross_product(cw, cu);
+  auto frame = [&](int f) {
+    const int ts = tile_size > 0 ? tile_size : std::max(W, H);
+    const int ntx = (W + ts - 1) / ts, nty = (H + ts - 1) / ts;
+    for (int tile = 0; tile < ntx * nty; ++tile) {
+      int sr = (tile / ntx) * ts, sc = (tile % ntx) * ts;
+      int er = std::min(sr + ts, H), ec = std::min(sc + ts, W);
+      dim3 tb(16, 16), tg((ec - sc + 15) / 16, (er - sr + 15) / 16);
+      cuda_dynamic_render_tile_wrapper(d_accum, W, H, sr, er, sc, ec, 0, 0, 1, depth, v3(rc.center), v3(rc.pixel00_loc),
+                                       v3(rc.pixel_delta_u), v3(rc.pixel_delta_v), CudaVec3(cu.x(), cu.y(), cu.z()),
+                                       CudaVec3(cv.x(), cv.y(), cv.z()), CudaVec3(cw.x(), cw.y(), cw.z()),
+                                       v3(rc.defocus_disk_u), v3(rc.defocus_disk_v), rc.defocus_angle, v3(rc.background),
+                                       scene.world.get(), scene.lights.get(), d_rand, tg, tb);
+      cudaDeviceSynchronize();
+    }
+    (void)f;
+  };
+  std::vector<CudaColor> host(size_t(W) * H);
+  frame(-1); // warm-up
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    std::string msg = std::string("render kernel: ") + cudaGetErrorString(cudaGetLastError());
+    return fail(msg);
+  }
+  cudaMemset(d_accum, 0, accum_bytes);
+  auto t0 = std::chrono::steady_clock::now();
+  for (int f = 0; f < frames; f++) {
+    frame(f);
+    if (with_copy)
+      cudaMemcpy(host.data(), d_accum, accum_bytes, cudaMemcpyDeviceToHost);
+  }
+  cudaError_t e = cudaDeviceSynchronize();
+  auto t1 = std::chrono::steady_clock::now();
+  if (e != cudaSuccess)
+    return fail(std::string("render loop: ") + cudaGetErrorString(e));
+  cudaMemcpy(host.data(), d_accum, accum_bytes, cudaMemcpyDeviceToHost);
+  double sum = 0;
+  for (const CudaColor &c : host) {
+    double v = (c.x + c.y + c.z) / 3.0;
+    sum += std::isfinite(v) ? v : 0.0;
+  }
+  if (ms_frame)
+    *ms_frame = std::chrono::duration<double, std::milli>(t1 - t0).count() / std::max(frames, 1);
+  if (mean)
+    *mean = sum / (double(W) * H) / std::max(frames, 1);
+  cleanup_cuda_scene(scene);
+  cudaFree(d_accum);
+  cudaFree(d_rand);
+  delete s;
+  return 0;
+}
+#endif // USE_CUDA
 
 // to_byte (ColorUtility.hpp:18-23) for pinning the tonemap.
 int ref_to_byte(double v) { return int(to_byte(v)); }

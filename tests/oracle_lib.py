@@ -14,6 +14,7 @@ from rt_b200 import abi  # noqa: E402
 
 ORACLE_PATH = os.path.join(REPO, "oracle", "liboracle.so")
 REF_PATH = os.path.join(REPO, "oracle", "_ref", "libref_harness.so")
+REF_GPU_PATH = os.path.join(REPO, "oracle", "_ref_gpu", "libref_gpu.so")  # the reference's own CUDA path (comparator)
 
 ORA_RNG_MT19937, ORA_RNG_PHILOX = 0, 1
 ORA_SAMPLER_REJECTION, ORA_SAMPLER_POLAR = 0, 1
@@ -95,6 +96,20 @@ def ref():
         lib.ref_hardware_threads.restype = C.c_int
         _ref = lib
     return _ref
+
+
+def have_ref_gpu():
+    return os.path.exists(REF_GPU_PATH)
+
+
+def ref_gpu():
+    """The reference compiled with -DUSE_CUDA (oracle/Makefile `gpu`).  Load it in a process of its own: it uses the
+    default stream, process-global scene state and device recursion, and a fault in it poisons the CUDA context."""
+    lib = C.CDLL(REF_GPU_PATH)
+    lib.ref_gpu_frame.restype = C.c_int
+    lib.ref_gpu_frame.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  P(C.c_double), P(C.c_double), C.c_char_p, C.c_int]
+    return lib
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -431,9 +431,17 @@ typedef struct rt_counters {
   uint64_t tail_segments;  /* the part of `segments` traced by the tail kernel */
   uint64_t nodes_visited;  /* BVH4 node visits (4 box tests each) - counted only while rt_context_set_stats is on */
   uint64_t prim_tests;     /* leaf primitive tests                - counted only while rt_context_set_stats is on */
+  uint64_t graph_launches; /* render passes submitted as one CUDA-graph launch (rt_context_set_graph) */
+  uint64_t graph_instantiations; /* how often the executable graph had to be rebuilt instead of updated in place */
 } rt_counters;
 int rt_get_counters(rt_context *ctx, rt_counters *out);
 int rt_reset_counters(rt_context *ctx);
+/* Whole-pass graph launches (DynamicCamera.cpp:458-554 launches and synchronises per tile): while enabled, every
+ * render pass - counter reset, generate, extend / shade per bounce, tail, accumulate - reaches the driver as ONE
+ * cudaGraphLaunch.  The pass is captured from the context stream and the context's executable graph is updated in
+ * place (camera, seed and stratum are kernel arguments), so nothing is re-instantiated from frame to frame.
+ * Environment RT_GRAPH=1 turns it on at context creation.  Images are unchanged. */
+int rt_context_set_graph(rt_context *ctx, int enable);
 /* Traversal statistics: while enabled, the render passes of this context launch instrumented instantiations of
  * the extend / tail kernels that count node visits and primitive tests (a few per cent slower); the product
  * kernels carry no counting code. */

@@ -899,6 +899,10 @@ int ref_gpu_frame(const char *name, uint64_t seed, int p0, int p1, int width, in
       std::snprintf(error, error_len, "%s", msg.c_str());
     return 1;
   };
+  // The reference never raises the device stack limit; its recursive ray_color_cuda (CameraKernels.cu:106-202)
+  // overruns the 1 KB default at depth 8 on this toolchain ("illegal memory access").  The harness - not the
+  // reference sources - raises it so that the kernels can be timed at all.
+  cudaDeviceSetLimit(cudaLimitStackSize, 32768);
   RefScene *s = static_cast<RefScene *>(scene_build(name, seed, p0, p1, true));
   if (!s)
     return fail("unknown scene");
@@ -950,6 +954,8 @@ int ref_gpu_frame(const char *name, uint64_t seed, int p0, int p1, int width, in
   frame(-1); // warm-up
   if (cudaDeviceSynchronize() != cudaSuccess) {
     std::string msg = std::string("render kernel: ") + cudaGetErrorString(cudaGetLastError());
+    scene.world.release(); // the context is gone: the reference's cudaFree wrappers would exit(1) on it
+    scene.lights.release();
     return fail(msg);
   }
   cudaMemset(d_accum, 0, accum_bytes);

@@ -193,6 +193,13 @@ int render_pass(rt_scene *scene, const rt_camera *camera, rt_film *film, int fir
   if (ctx->audit && (st = ensure_audit(ctx, (size_t)pp.n_paths)) != RT_OK)
     return st;
   WaveBuffers &w = ctx->wave;
+  // The pass as ONE graph launch (RT_GRAPH=1 / rt_context_set_graph): the launch sequence below is captured from
+  // the stream every pass (capturing costs a fraction of launching) and the context's executable graph is updated
+  // in place with the new kernel arguments - camera, seed, stratum - so that the driver receives a single launch
+  // per pass.  The profiling modes (stage timing, audit) bracket individual launches and keep the direct path.
+  const bool as_graph = ctx->use_graph && !ctx->timer.enabled && !ctx->audit;
+  if (as_graph)
+    RT_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
   RT_CUDA(cudaMemsetAsync(w.counts, 0, 2 * ((size_t)max_depth + 2) * sizeof(unsigned int), ctx->stream));
   // wavefront launches while the path population is large, then one tail kernel that runs whatever is
   // left to completion (rt_kernels.cu, k_tail)
@@ -235,6 +242,31 @@ int render_pass(rt_scene *scene, const rt_camera *camera, rt_film *film, int fir
   ctx->counters.kernel_launches += (fused_generate ? 0 : 1) + (pp.film_direct ? 0 : 1) + 2 * (uint64_t)wave_bounces + (uint64_t)tail_launches;
   ctx->counters.paths += (uint64_t)pp.n_paths;
   w.last_counts = (size_t)max_depth + 1;
+  if (as_graph) {
+    cudaGraph_t graph = nullptr;
+    RT_CUDA(cudaStreamEndCapture(ctx->stream, &graph));
+    bool ready = false;
+    if (ctx->graph_exec) { // same topology as the previous pass: only the node parameters change
+      cudaGraphExecUpdateResultInfo info;
+      ready = cudaGraphExecUpdate(ctx->graph_exec, graph, &info) == cudaSuccess;
+      if (!ready) {
+        cudaGetLastError();
+        cudaGraphExecDestroy(ctx->graph_exec);
+        ctx->graph_exec = nullptr;
+      }
+    }
+    if (!ready) {
+      cudaError_t e = cudaGraphInstantiate(&ctx->graph_exec, graph, 0);
+      if (e != cudaSuccess) {
+        cudaGraphDestroy(graph);
+        return rt_cuda_fail(e, "cudaGraphInstantiate");
+      }
+      ctx->counters.graph_instantiations += 1;
+    }
+    cudaGraphDestroy(graph);
+    RT_CUDA(cudaGraphLaunch(ctx->graph_exec, ctx->stream));
+    ctx->counters.graph_launches += 1;
+  }
   RT_CUDA(cudaGetLastError());
   return RT_OK;
 }
@@ -340,6 +372,8 @@ int rt_context_create(int device, rt_context **out) {
   ctx->sm_count = prop.multiProcessorCount;
   if (const char *env = std::getenv("RT_WAVE_BOUNCES")) // tuning / A-B aid: bounces run as wavefront launches
     ctx->wave_bounces = std::max(0, std::atoi(env));
+  if (const char *env = std::getenv("RT_GRAPH"))
+    ctx->use_graph = std::atoi(env) != 0;
   if (const char *env = std::getenv("RT_FUSED_GENERATE"))
     ctx->fused_generate = std::atoi(env) != 0;
   if (const char *env = std::getenv("RT_TAIL_SPAN"))
@@ -371,6 +405,8 @@ void rt_context_destroy(rt_context *ctx) {
   cudaFree(w.audit_stats);
   cudaFree(w.audit_samples);
   cudaFree(ctx->scratch);
+  if (ctx->graph_exec)
+    cudaGraphExecDestroy(ctx->graph_exec);
   for (cudaEvent_t e : ctx->timer.pool)
     cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
@@ -803,6 +839,13 @@ int rt_get_counters(rt_context *ctx, rt_counters *out) {
   out->tail_segments = stats[3];
   out->nodes_visited = stats[1]; // counted by the instrumented kernels only (rt_context_set_stats)
   out->prim_tests = stats[2];
+  return RT_OK;
+}
+
+int rt_context_set_graph(rt_context *ctx, int enable) {
+  if (!ctx)
+    return invalid("null context");
+  ctx->use_graph = enable != 0;
   return RT_OK;
 }
 

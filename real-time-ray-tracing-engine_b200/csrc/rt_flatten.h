@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -385,8 +386,9 @@ inline int flatten(const rt_scene_desc *d, Flat &f) {
   if (f.texels.size() > ((size_t)1 << 31))
     return fail_invalid("image textures exceed 2^31 texels");
 
-  // materials with their texture folded in
-  for (int i = 0; i < d->n_materials; i++) {
+  // materials with their texture folded in (a million-sphere scene has a million of them: all host threads)
+  f.mats.resize((size_t)d->n_materials * RT_MAT_F4);
+  auto bake_material = [&](int i) -> int {
     const rt_material &m = d->materials[i];
     float4 m0 = make_float4(ibits(m.type), ibits(RT_DTEX_SOLID), 0.f, 0.f);
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
@@ -431,9 +433,27 @@ inline int flatten(const rt_scene_desc *d, Flat &f) {
     } else {
       return fail_invalid("unknown material type");
     }
-    f.mats.push_back(m0);
-    f.mats.push_back(a);
-    f.mats.push_back(b);
+    f.mats[(size_t)i * RT_MAT_F4 + 0] = m0;
+    f.mats[(size_t)i * RT_MAT_F4 + 1] = a;
+    f.mats[(size_t)i * RT_MAT_F4 + 2] = b;
+    return RT_OK;
+  };
+  {
+    int bad = -1;
+    std::mutex guard;
+    parallel_for((size_t)d->n_materials, [&](size_t lo, size_t hi) {
+      for (size_t i = lo; i < hi; i++)
+        if (bake_material((int)i) != RT_OK) { // the message a worker thread sets is its own (thread-local)
+          std::lock_guard<std::mutex> lock(guard);
+          if (bad < 0 || (int)i < bad)
+            bad = (int)i;
+        }
+    });
+    if (bad >= 0) { // re-run the first failing material on this thread for its status and message
+      int st = bake_material(bad);
+      if (st != RT_OK)
+        return st;
+    }
   }
 
   parallel_for(f.prims.size() / RT_PRIM_F4, [&](size_t a, size_t b) {

@@ -99,6 +99,8 @@ struct rt_context {
   // the camera-ray arithmetic done twice at the extend kernel's lane utilisation (+0.014 ms extend, +0.013 ms
   // shade), so the separate k_generate stays the default.
   bool fused_generate = false;
+  bool use_graph = false;           // render passes are submitted as one CUDA-graph launch (rt_context_set_graph)
+  cudaGraphExec_t graph_exec = nullptr; // updated in place pass after pass
   bool audit = false; // every extend launch is checked against the FP64 parity traversal (all-wavefront schedule)
   bool stats = false; // instrumented extend / tail kernels count node visits and primitive tests
   cudaStream_t stream = nullptr;

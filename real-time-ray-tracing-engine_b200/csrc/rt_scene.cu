@@ -291,7 +291,7 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
   sc->h_xforms.assign(desc->xforms, desc->xforms + desc->n_xforms);
   sc->h_xform_ops.assign(desc->xform_ops, desc->xform_ops + desc->n_xform_ops);
   sc->h_spheres.assign(desc->spheres, desc->spheres + desc->n_spheres);
-  sc->h_mats = f.mats;
+  sc->h_mats = std::move(f.mats); // not needed by this function any more
   {
     std::vector<int> leaf_of_record(std::max(n, 1), -1);
     for (int j = 0; j < n; j++)

@@ -78,6 +78,8 @@ int main(int argc, char **argv) {
   const int tile_rows = 8;
   for (int g = 0; g < n_gpus; g++) {
     CHECK(rt_context_create(g, &ctx[g]));
+    if (opt.camera_dynamic) // one graph launch per progressive frame instead of one launch per kernel
+      CHECK(rt_context_set_graph(ctx[g], 1));
     CHECK(rt_scene_create(ctx[g], rth_scene_desc(hs), &scene[g])); // the scene is replicated on every GPU
     CHECK(rt_film_create(ctx[g], W, H, g, n_gpus, tile_rows, nullptr, &film[g]));
   }

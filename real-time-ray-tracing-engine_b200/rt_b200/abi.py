@@ -118,7 +118,8 @@ class rt_hit(C.Structure):
 
 class rt_counters(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("segments", C.c_uint64), ("kernel_launches", C.c_uint64),
-                ("tail_segments", C.c_uint64), ("nodes_visited", C.c_uint64), ("prim_tests", C.c_uint64)]
+                ("tail_segments", C.c_uint64), ("nodes_visited", C.c_uint64), ("prim_tests", C.c_uint64),
+                ("graph_launches", C.c_uint64), ("graph_instantiations", C.c_uint64)]
 
 
 class rt_audit(C.Structure):
@@ -188,6 +189,7 @@ RT_B200_SYMBOLS = {
     "rt_host_free": (None, [C.c_void_p]),
     "rt_get_counters": (C.c_int, [C.c_void_p, P(rt_counters)]),
     "rt_reset_counters": (C.c_int, [C.c_void_p]),
+    "rt_context_set_graph": (C.c_int, [C.c_void_p, C.c_int]),
     "rt_context_set_stats": (C.c_int, [C.c_void_p, C.c_int]),
     "rt_get_queue_lengths": (C.c_int, [C.c_void_p, P(C.c_uint32), C.c_int]),
     "rt_context_set_audit": (C.c_int, [C.c_void_p, C.c_int]),

@@ -44,6 +44,10 @@ class Context:
         abi.check(self.lib, self.lib.rt_get_stage_times(self._h, ms, n), "rt_get_stage_times")
         return list(ms), list(n)
 
+    def set_graph(self, enable):
+        """Render passes as one CUDA-graph launch each (captured per pass, executable graph updated in place)."""
+        abi.check(self.lib, self.lib.rt_context_set_graph(self._h, int(enable)), "rt_context_set_graph")
+
     def set_stats(self, enable):
         """Instrumented extend / tail kernels: counters() then reports node visits and primitive tests."""
         abi.check(self.lib, self.lib.rt_context_set_stats(self._h, int(enable)), "rt_context_set_stats")

@@ -673,3 +673,37 @@ def test_builder_choice(ctx, host_scenes, monkeypatch):
     assert scene.info().builder == abi.RT_BUILDER_SAH
     scene.close()
     assert engine.Scene(ctx, abi.rt_scene_desc()).info().builder == abi.RT_BUILDER_NONE
+
+
+def test_graph_passes_render_the_same_image(host_scenes):
+    """rt_context_set_graph: every render pass is one cudaGraphLaunch of an executable graph that is updated in place
+    (new seed / stratum / camera each pass), never rebuilt while the pass shape stays the same; same bits as the
+    direct launches."""
+    hs = host_scenes("spheres", 11, -1)
+    cfg = hs.camera_config(320, 4, 8)
+    cam = engine.camera_from_config(cfg)
+    images = []
+    for graph in (False, True):
+        c = engine.Context(0)
+        c.set_graph(graph)
+        scene = engine.Scene(c, hs.desc)
+        film = engine.Film(c, cam.image_width, cam.image_height)
+        for f in range(6):  # six frames: strata and seeds change, the shape does not
+            engine.render_accumulate(scene, cam, film, f % 2, (f // 2) % 2, 2, 8, 30 + f)
+        images.append(film.read_rgb(1.0 / 6))
+        n = c.counters()
+        if graph:
+            assert n.graph_launches == 6 and n.graph_instantiations == 1, (n.graph_launches, n.graph_instantiations)
+            cfg2 = hs.camera_config(320, 4, 8)
+            cfg2.lookfrom[0] += 1.0  # a camera move is a parameter update as well
+            cam2 = engine.camera_from_config(cfg2)
+            engine.render_accumulate(scene, cam2, film, 0, 0, 2, 8, 99)
+            engine.render_static(scene, cam, film, 2, 8, 5)  # another pass shape (4 samples + accumulate): one rebuild
+            n = c.counters()
+            assert n.graph_launches == 8 and n.graph_instantiations == 2, (n.graph_launches, n.graph_instantiations)
+        else:
+            assert n.graph_launches == 0
+        film.close()
+        scene.close()
+        c.close()
+    assert np.array_equal(images[0], images[1])

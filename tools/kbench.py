@@ -31,9 +31,14 @@ def run_one(args):
     names = args[args.index("--scenes") + 1].split(",") if "--scenes" in args else ["c2", "cornell", "final", "c4"]
     stats = "--stats" in args
     ctx = engine.Context(0)
+    if "--graph" in args:
+        ctx.set_graph(True)
+        lib_suffix = "+graph"
+    else:
+        lib_suffix = ""
     stream = torch.cuda.ExternalStream(ctx.stream)
     flush = torch.empty(192 << 20, dtype=torch.uint8, device="cuda")
-    lib = os.path.basename(os.environ.get("RT_B200_LIB", "default")).replace("librt_", "").replace(".so", "")
+    lib = os.path.basename(os.environ.get("RT_B200_LIB", "default")).replace("librt_", "").replace(".so", "") + lib_suffix
     for name in names:
         scene_name, p0, p1, width, depth = SCENES[name]
         hs = host.HostScene.builtin(scene_name, 1234, p0, p1)
@@ -60,6 +65,13 @@ def run_one(args):
             frame(f)
             e1.record(stream)
         ctx.synchronize()
+        # host-blocking frames: submit, wait for the GPU, submit the next (what a viewer with no frame in flight pays)
+        import time as _time
+        t0 = _time.perf_counter()
+        for f in range(frames):
+            frame(f)
+            ctx.synchronize()
+        blocking_ms = (_time.perf_counter() - t0) / frames * 1e3
         times = sorted(e0.elapsed_time(e1) for e0, e1 in pairs)
         ms, best = sum(times) / len(times), times[0]
         c = ctx.counters()
@@ -70,7 +82,7 @@ def run_one(args):
         ctx.set_stage_timing(False)
         info = scene.info()
         out = {"lib": lib, "bvh": os.environ.get("RT_BVH", "auto") + ":" + ["none", "sah", "ploc", "lbvh"][info.builder],
-               "build_ms": round(info.build_ms, 2), "scene": name, "ms": round(ms, 4), "min_ms": round(best, 4),
+               "build_ms": round(info.build_ms, 2), "scene": name, "ms": round(ms, 4), "min_ms": round(best, 4), "blocking_ms": round(blocking_ms, 4),
                "seg_per_path": round(c.segments / max(1, c.paths), 3),
                "stages": {k: round(st[i] / 10, 4) for i, k in enumerate(["gen", "extend", "shade", "accum", "tail"])}}
         if stats:

@@ -63,6 +63,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -902,7 +903,10 @@ int ref_gpu_frame(const char *name, uint64_t seed, int p0, int p1, int width, in
   // The reference never raises the device stack limit; its recursive ray_color_cuda (CameraKernels.cu:106-202)
   // overruns the 1 KB default at depth 8 on this toolchain ("illegal memory access").  The harness - not the
   // reference sources - raises it so that the kernels can be timed at all.
-  cudaDeviceSetLimit(cudaLimitStackSize, 32768);
+  {
+    const char *e = std::getenv("REF_GPU_STACK");
+    cudaDeviceSetLimit(cudaLimitStackSize, e ? (size_t)std::atol(e) : 32768);
+  }
   RefScene *s = static_cast<RefScene *>(scene_build(name, seed, p0, p1, true));
   if (!s)
     return fail("unknown scene");
@@ -912,10 +916,12 @@ int ref_gpu_frame(const char *name, uint64_t seed, int p0, int p1, int width, in
   const int W = cam.width(), H = cam.height();
   // -b: the world (and the lights) wrapped in the reference's BVH (StaticCamera.cpp:140-145)
   HittableList world = s->world, lights = s->lights;
-  if (!world.get_objects().empty())
-    world = HittableList(std::make_shared<BVHNode>(world));
-  if (!lights.get_objects().empty())
-    lights = HittableList(std::make_shared<BVHNode>(lights));
+  if (!std::getenv("REF_GPU_NO_BVH")) { // REF_GPU_NO_BVH: the list world (no -b), to tell a traversal fault from the rest
+    if (!world.get_objects().empty())
+      world = HittableList(std::make_shared<BVHNode>(world));
+    if (!lights.get_objects().empty())
+      lights = HittableList(std::make_shared<BVHNode>(lights));
+  }
 
   CudaColor *d_accum = nullptr;
   curandState *d_rand = nullptr;

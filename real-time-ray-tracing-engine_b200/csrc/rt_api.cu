@@ -190,7 +190,7 @@ int render_pass(rt_scene *scene, const rt_camera *camera, rt_film *film, int fir
   DScene sc = scene->d;
   for (int a = 0; a < 3; a++)
     sc.bg[a] = (float)camera->background[a];
-  if (ctx->audit && (st = ensure_audit(ctx, (size_t)pp.n_paths)) != RT_OK)
+  if (ctx->audit && ((st = ensure_audit(ctx, (size_t)pp.n_paths)) != RT_OK || (st = rt_scene_ensure_exact(scene)) != RT_OK))
     return st;
   WaveBuffers &w = ctx->wave;
   // The pass as ONE graph launch (RT_GRAPH=1 / rt_context_set_graph): the launch sequence below is captured from
@@ -480,6 +480,11 @@ int rt_trace_rays(rt_scene *scene, const rt_ray *rays, int64_t n, int mode, uint
     return RT_OK;
   rt_context *ctx = scene->ctx;
   RT_CUDA(cudaSetDevice(ctx->device));
+  if (mode == RT_TRACE_EXACT_F64) {
+    int ready = rt_scene_ensure_exact(scene);
+    if (ready != RT_OK)
+      return ready;
+  }
   rt_ray *d_rays = nullptr;
   rt_hit *d_hits = nullptr;
   RT_CUDA(cudaMalloc((void **)&d_rays, (size_t)n * sizeof(rt_ray)));

@@ -99,7 +99,7 @@ struct rt_context {
   // the camera-ray arithmetic done twice at the extend kernel's lane utilisation (+0.014 ms extend, +0.013 ms
   // shade), so the separate k_generate stays the default.
   bool fused_generate = false;
-  bool use_graph = false;           // render passes are submitted as one CUDA-graph launch (rt_context_set_graph)
+  bool use_graph = true;            // render passes are submitted as one CUDA-graph launch (rt_context_set_graph, RT_GRAPH=0)
   cudaGraphExec_t graph_exec = nullptr; // updated in place pass after pass
   bool audit = false; // every extend launch is checked against the FP64 parity traversal (all-wavefront schedule)
   bool stats = false; // instrumented extend / tail kernels count node visits and primitive tests
@@ -132,6 +132,7 @@ struct rt_scene {
   std::vector<rt_quad> h_quads;
   std::vector<int> sphere_leaf, quad_leaf; // -1: boundary primitive of a medium (not a leaf of its own)
   std::vector<float4> h_mats;
+  std::vector<PrimExact> h_ex_prims; // FP64 parity records in leaf order until their first use (rt_scene_ensure_exact)
   int *leaf_up = nullptr;            // device: per leaf, parent node * 4 + slot
   unsigned int *arrivals = nullptr;  // device: per node refit counter
 };
@@ -158,6 +159,7 @@ int rt_cuda_fail(cudaError_t e, const char *what);
 // ---- scene construction (rt_scene.cu) ----
 int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *scene);
 void rt_scene_release(rt_scene *scene);
+int rt_scene_ensure_exact(rt_scene *scene);
 int rt_scene_update_spheres_impl(rt_scene *scene, int first, int count, const rt_sphere *spheres);
 int rt_scene_update_quads_impl(rt_scene *scene, int first, int count, const rt_quad *quads);
 

@@ -101,7 +101,6 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
   const int n_wide_cap = std::max(n, 1);
   RT_CUDA(cudaMalloc((void **)&sc->nodes, (size_t)n_wide_cap * RT_NODE_F4 * sizeof(float4)));
   RT_CUDA(cudaMalloc((void **)&sc->prims, (size_t)std::max(n, 1) * RT_PRIM_F4 * sizeof(float4)));
-  RT_CUDA(cudaMalloc((void **)&sc->ex_prims, (size_t)std::max(n, 1) * sizeof(PrimExact)));
   RT_CUDA(cudaMalloc((void **)&sc->leaf_object, (size_t)std::max(n, 1) * sizeof(int)));
   RT_CUDA(cudaMalloc((void **)&sc->leaf_id, (size_t)std::max(n, 1) * sizeof(int)));
 
@@ -124,7 +123,6 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
     RT_CUDA(cudaMemcpy(sc->nodes, node.data(), sizeof(float4) * RT_NODE_F4, cudaMemcpyHostToDevice));
     if (n) {
       RT_CUDA(cudaMemcpy(sc->prims, f.prims.data(), sizeof(float4) * RT_PRIM_F4, cudaMemcpyHostToDevice));
-      RT_CUDA(cudaMemcpy(sc->ex_prims, f.ex_prims.data(), sizeof(PrimExact), cudaMemcpyHostToDevice));
       order[0] = 0;
     }
     sc->info.build_ms = 0.0;
@@ -132,7 +130,6 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
     Scratch scratch;
     BuildBox *d_boxes = nullptr, *d_sorted_boxes = nullptr;
     float4 *d_prims_in = nullptr;
-    PrimExact *d_ex_in = nullptr;
     uint64_t *d_codes = nullptr, *d_codes_sorted = nullptr;
     uint32_t *d_index = nullptr, *d_index_sorted = nullptr;
     float *d_bounds = nullptr;
@@ -142,7 +139,6 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
     RT_CUDA(scratch.alloc(&d_boxes, n));
     RT_CUDA(scratch.alloc(&d_sorted_boxes, n));
     RT_CUDA(scratch.alloc(&d_prims_in, (size_t)n * RT_PRIM_F4));
-    RT_CUDA(scratch.alloc(&d_ex_in, n));
     RT_CUDA(scratch.alloc(&d_codes, n));
     RT_CUDA(scratch.alloc(&d_codes_sorted, n));
     RT_CUDA(scratch.alloc(&d_index, n));
@@ -166,7 +162,6 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
     }
     RT_CUDA(cudaMemcpyAsync(d_boxes, boxes.data(), sizeof(BuildBox) * n, cudaMemcpyHostToDevice, s));
     RT_CUDA(cudaMemcpyAsync(d_prims_in, f.prims.data(), sizeof(float4) * RT_PRIM_F4 * n, cudaMemcpyHostToDevice, s));
-    RT_CUDA(cudaMemcpyAsync(d_ex_in, f.ex_prims.data(), sizeof(PrimExact) * n, cudaMemcpyHostToDevice, s));
     RT_CUDA(cudaMemcpyAsync(d_bounds, bounds, sizeof bounds, cudaMemcpyHostToDevice, s));
     RT_CUDA(cudaMemsetAsync(t.visits, 0, sizeof(unsigned int) * (n - 1), s));
 
@@ -245,8 +240,6 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
     // leaf boxes and records in the order of the tree that was kept
     launch_gather_boxes(s, d_boxes, d_index_sorted, d_sorted_boxes, n);
     launch_gather_records(s, d_prims_in, d_index_sorted, sc->prims, n, RT_PRIM_F4 * (int)sizeof(float4));
-    static_assert(sizeof(PrimExact) % 16 == 0, "PrimExact must be a multiple of 16 bytes");
-    launch_gather_records(s, d_ex_in, d_index_sorted, sc->ex_prims, n, (int)sizeof(PrimExact));
 
     // collapse, level by level; the root binary node 0 becomes wide node 0
     CollapseItem root{0, 0, -1};
@@ -292,6 +285,13 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
   sc->h_xform_ops.assign(desc->xform_ops, desc->xform_ops + desc->n_xform_ops);
   sc->h_spheres.assign(desc->spheres, desc->spheres + desc->n_spheres);
   sc->h_mats = std::move(f.mats); // not needed by this function any more
+  // The FP64 parity records (160 B per primitive) are only read by rt_trace_rays(RT_TRACE_EXACT_F64), the parity
+  // audit and primitive updates: they stay on the host, in leaf order, until one of those asks (rt_scene_ensure_exact).
+  sc->h_ex_prims.resize(std::max(n, 1));
+  parallel_for((size_t)n, [&](size_t a, size_t b) {
+    for (size_t j = a; j < b; j++)
+      sc->h_ex_prims[j] = f.ex_prims[order[j]];
+  });
   {
     std::vector<int> leaf_of_record(std::max(n, 1), -1);
     for (int j = 0; j < n; j++)
@@ -321,7 +321,7 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
   sc->d.n_media = desc->n_media;
   sc->d.bg[0] = sc->d.bg[1] = sc->d.bg[2] = 0.f; // set per render from the camera
   sc->ex.nodes = sc->nodes;
-  sc->ex.prims = sc->ex_prims;
+  sc->ex.prims = nullptr; // rt_scene_ensure_exact
   sc->ex.bprims = sc->ex_bprims;
   sc->ex.ops = sc->ex_ops;
   sc->ex.chain_first = sc->ex_chain_first;
@@ -339,6 +339,19 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
   return RT_OK;
 }
 
+// Uploads the FP64 parity records on first use.
+int rt_scene_ensure_exact(rt_scene *sc) {
+  if (sc->ex_prims)
+    return RT_OK;
+  const size_t n = sc->h_ex_prims.size();
+  RT_CUDA(cudaMalloc((void **)&sc->ex_prims, std::max<size_t>(n, 1) * sizeof(PrimExact)));
+  RT_CUDA(cudaMemcpyAsync(sc->ex_prims, sc->h_ex_prims.data(), n * sizeof(PrimExact), cudaMemcpyHostToDevice, sc->ctx->stream));
+  RT_CUDA(cudaStreamSynchronize(sc->ctx->stream));
+  sc->ex.prims = sc->ex_prims;
+  std::vector<PrimExact>().swap(sc->h_ex_prims); // the device copy is the master from here on
+  return RT_OK;
+}
+
 // rt_scene_update_spheres / rt_scene_update_quads: re-bakes the given primitives (instance chains, material copy,
 // FP64 parity record, box), scatters them to their leaves and refits the BVH4 bottom-up.  The tree keeps its topology.
 static int update_primitives(rt_scene *sc, int first, int count, const rt_sphere *spheres, const rt_quad *quads) {
@@ -350,6 +363,11 @@ static int update_primitives(rt_scene *sc, int first, int count, const rt_sphere
   if ((!spheres && !quads) || first < 0 || count < 0 || first > n_have - count) {
     rt_set_error(std::string(what) + ": primitive range out of bounds");
     return RT_ERR_INVALID;
+  }
+  { // the update scatters FP64 parity records next to the render records
+    int ready = rt_scene_ensure_exact(sc);
+    if (ready != RT_OK)
+      return ready;
   }
   rt_scene_desc d{};
   d.xforms = sc->h_xforms.data();

@@ -161,6 +161,27 @@ static int wave_depth(const rt_context *ctx, const rt_scene *scene) {
   return scene->n_leaf > 32768 ? 1 : (scene->n_leaf > 2048 ? 2 : 3);
 }
 
+} // namespace
+
+// A multi-sample pass on a film that owns its buffer leaves the in-order per-pixel sum of its samples to the next
+// reader of the film: rt_film_present folds it into its tone-map kernel (one launch and one pass over the film
+// less per displayed frame); every other reader, and the next render pass of the context (which reuses the
+// radiance buffer), completes it here with k_accumulate.  Same operands in the same order either way.
+int rt_film_flush(rt_film *film) {
+  if (!film || !film->pending.n_samples)
+    return RT_OK;
+  rt_context *ctx = film->ctx;
+  launch_accumulate(ctx, film->pending_pass, ctx->wave, film->accum);
+  ctx->counters.kernel_launches += 1;
+  film->pending = PendingSum();
+  if (ctx->pending_film == film)
+    ctx->pending_film = nullptr;
+  RT_CUDA(cudaGetLastError());
+  return RT_OK;
+}
+
+namespace {
+
 // One wavefront pass over `n_samples` strata starting at linear stratum `first_sample`.
 int render_pass(rt_scene *scene, const rt_camera *camera, rt_film *film, int first_sample, int n_samples,
                 int sqrt_spp, int max_depth, uint64_t seed) {
@@ -184,6 +205,11 @@ int render_pass(rt_scene *scene, const rt_camera *camera, rt_film *film, int fir
   }
   if (pp.n_paths == 0)
     return RT_OK;
+  if (ctx->pending_film) { // its radiance lives in the buffer this pass is about to overwrite
+    int flushed = rt_film_flush(ctx->pending_film);
+    if (flushed != RT_OK)
+      return flushed;
+  }
   int st = ensure_wave(ctx, (size_t)pp.n_paths, 2 * ((size_t)max_depth + 2)); // queue lengths + fetch cursors
   if (st != RT_OK)
     return st;
@@ -235,11 +261,24 @@ int render_pass(rt_scene *scene, const rt_camera *camera, rt_film *film, int fir
     launch_tail(ctx, sc, pp, w, first, std::min(max_depth, first + ctx->tail_span), buffer);
     tail_launches++;
   }
-  if (!pp.film_direct) {
+  // the in-order sum of a multi-sample pass: deferred to the film's next reader when the film owns its buffer
+  // (nobody can look at it behind the library's back) and no per-launch timing wants the launch here
+  const bool defer_sum = !pp.film_direct && film->owns_accum && !ctx->timer.enabled && ctx->defer_accumulate;
+  if (!pp.film_direct && !defer_sum) {
     StageSpan span(ctx, RT_STAGE_ACCUMULATE);
     launch_accumulate(ctx, pp, w, film->accum);
   }
-  ctx->counters.kernel_launches += (fused_generate ? 0 : 1) + (pp.film_direct ? 0 : 1) + 2 * (uint64_t)wave_bounces + (uint64_t)tail_launches;
+  if (defer_sum) {
+    film->pending.radiance = w.radiance;
+    film->pending.n_samples = pp.n_samples;
+    film->pending.n_owned = pp.n_owned;
+    film->pending.tiled = pp.paths.tiled;
+    film->pending.blocks_x = pp.paths.blocks_x;
+    film->pending.width = pp.map.width > 0 ? pp.map.width : 1;
+    film->pending_pass = pp;
+    ctx->pending_film = film;
+  }
+  ctx->counters.kernel_launches += (fused_generate ? 0 : 1) + ((pp.film_direct || defer_sum) ? 0 : 1) + 2 * (uint64_t)wave_bounces + (uint64_t)tail_launches;
   ctx->counters.paths += (uint64_t)pp.n_paths;
   w.last_counts = (size_t)max_depth + 1;
   if (as_graph) {
@@ -372,6 +411,8 @@ int rt_context_create(int device, rt_context **out) {
   ctx->sm_count = prop.multiProcessorCount;
   if (const char *env = std::getenv("RT_WAVE_BOUNCES")) // tuning / A-B aid: bounces run as wavefront launches
     ctx->wave_bounces = std::max(0, std::atoi(env));
+  if (const char *env = std::getenv("RT_DEFER_ACCUMULATE"))
+    ctx->defer_accumulate = std::atoi(env) != 0;
   if (const char *env = std::getenv("RT_GRAPH"))
     ctx->use_graph = std::atoi(env) != 0;
   if (const char *env = std::getenv("RT_FUSED_GENERATE"))
@@ -559,6 +600,8 @@ int rt_film_create(rt_context *ctx, int width, int height, int rank, int n_ranks
 void rt_film_destroy(rt_film *film) {
   if (!film)
     return;
+  if (film->ctx->pending_film == film)
+    film->ctx->pending_film = nullptr; // an unsummed pass dies with its film
   cudaSetDevice(film->ctx->device);
   cudaStreamSynchronize(film->ctx->stream);
   if (film->owns_accum)
@@ -570,6 +613,9 @@ int rt_film_clear(rt_film *film) {
   if (!film)
     return invalid("null film");
   RT_CUDA(cudaSetDevice(film->ctx->device));
+  film->pending = PendingSum(); // cleared before it was ever summed
+  if (film->ctx->pending_film == film)
+    film->ctx->pending_film = nullptr;
   if (film->n_owned > 0)
     RT_CUDA(cudaMemsetAsync(film->accum, 0, (size_t)film->n_owned * sizeof(float4), film->ctx->stream));
   film->samples = 0;
@@ -577,7 +623,13 @@ int rt_film_clear(rt_film *film) {
 }
 
 int64_t rt_film_owned_pixels(const rt_film *film) { return film ? film->n_owned : -1; }
-uint64_t rt_film_device_ptr(rt_film *film) { return film ? (uint64_t)(uintptr_t)film->accum : 0; }
+uint64_t rt_film_device_ptr(rt_film *film) {
+  if (!film)
+    return 0;
+  cudaSetDevice(film->ctx->device);
+  rt_film_flush(film); // whoever asks for the raw sums gets complete ones (stream-ordered)
+  return (uint64_t)(uintptr_t)film->accum;
+}
 int64_t rt_film_samples(const rt_film *film) { return film ? film->samples : -1; }
 
 static int check_render_args(rt_scene *scene, const rt_camera *camera, rt_film *film, int sqrt_spp, int max_depth) {
@@ -651,6 +703,8 @@ int rt_film_read_rgb(rt_film *film, double scale, float *host_rgb) {
     return RT_OK;
   rt_context *ctx = film->ctx;
   RT_CUDA(cudaSetDevice(ctx->device));
+  if (int flushed = rt_film_flush(film))
+    return flushed;
   void *scratch = nullptr;
   int st = ctx_scratch(ctx, (size_t)film->n_owned * 3 * sizeof(float), &scratch);
   if (st != RT_OK)
@@ -670,6 +724,8 @@ int rt_film_resolve_rgb8_device(rt_film *film, double scale, void *device_rgb8) 
   if (!film || !device_rgb8)
     return invalid("rt_film_resolve_rgb8_device: null argument");
   RT_CUDA(cudaSetDevice(film->ctx->device));
+  if (int flushed = rt_film_flush(film))
+    return flushed;
   // compact order out (rank 0 of 1): the staged 16-byte-store kernel of rt_frame.cu
   launch_present_rgb8(film->ctx, film->ctx->stream, film->accum, film->n_owned, film->map.width, film->map.tile_rows, 0, 1,
                       scale, (uint8_t *)device_rgb8, nullptr, nullptr, 0, nullptr, nullptr);
@@ -761,6 +817,8 @@ static int gather_p2p(rt_film **films, int n_ranks, double scale, float *host_rg
   };
   for (int r = 0; r < n_ranks && st == RT_OK; r++) {
     RT_CUDA(cudaSetDevice(films[r]->ctx->device));
+    if ((st = rt_film_flush(films[r])) != RT_OK)
+      break;
     if (as_rgb8 && films[r]->n_owned > 0) {
       e = cudaMalloc(&staged[r], (size_t)films[r]->n_owned * 3);
       if (e != cudaSuccess)

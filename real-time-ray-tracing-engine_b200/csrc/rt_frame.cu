@@ -97,15 +97,33 @@ __device__ __forceinline__ size_t frame_offset(size_t b, size_t tile_bytes, int 
   return (tile_local * (size_t)n_ranks + (size_t)rank) * tile_bytes + (b - tile_local * tile_bytes);
 }
 
+// The film value of owned pixel k.  When a multi-sample pass left its per-path radiance unsummed (PendingSum), this
+// is where k_accumulate's in-order sum happens - same operands, same order, so the same bits - and the film is
+// brought up to date on the way.
+__device__ __forceinline__ float4 film_value(float4 *__restrict__ film, long long k, const PendingSum &pending) {
+  float4 v = film[k];
+  if (pending.n_samples) {
+    const float4 *r = pending.radiance + film_index_to_path(pending, (uint32_t)k);
+    for (int s = 0; s < pending.n_samples; s++) {
+      float4 a = __ldg(r + (size_t)s * pending.n_owned);
+      v.x += a.x;
+      v.y += a.y;
+      v.z += a.z;
+    }
+    film[k] = v;
+  }
+  return v;
+}
+
 // to_byte(scale * sum) (ColorUtility.hpp:11-26, FP64 like k_resolve_rgb8) of the film's owned pixels, staged per
 // block in shared memory and stored as 16-byte pieces into the frame rows the tiles belong to.  1024 pixels per
 // block iteration.  Requires (tile_rows * width * 3) % 16 == 0 (every piece stays inside one tile).
 #define RT_PRESENT_THREADS 256
 #define RT_PRESENT_PIXELS 1024
 __global__ void __launch_bounds__(RT_PRESENT_THREADS)
-    k_present_rgb8(const float4 *__restrict__ film, long long n_owned, double scale, uint8_t *__restrict__ frame,
+    k_present_rgb8(float4 *__restrict__ film, long long n_owned, double scale, uint8_t *__restrict__ frame,
                    size_t tile_bytes, int rank, int n_ranks, unsigned int *blocks_done, uint32_t *flag, uint32_t ticket,
-                   const uint32_t *consumed, uint32_t *error) {
+                   const uint32_t *consumed, uint32_t *error, const __grid_constant__ PendingSum pending) {
   __shared__ __align__(16) uint8_t stage[RT_PRESENT_PIXELS * 3];
   block_wait_for(consumed, ticket - 1, error);
   const long long n_chunks = (n_owned + RT_PRESENT_PIXELS - 1) / RT_PRESENT_PIXELS;
@@ -116,7 +134,7 @@ __global__ void __launch_bounds__(RT_PRESENT_THREADS)
       int local = i * RT_PRESENT_THREADS + threadIdx.x;
       long long k = chunk * RT_PRESENT_PIXELS + local;
       if (k < n_owned) {
-        float4 v = film[k];
+        float4 v = film_value(film, k, pending);
         stage[local * 3 + 0] = to_byte_f64(scale * (double)v.x);
         stage[local * 3 + 1] = to_byte_f64(scale * (double)v.y);
         stage[local * 3 + 2] = to_byte_f64(scale * (double)v.z);
@@ -146,10 +164,10 @@ __global__ void __launch_bounds__(RT_PRESENT_THREADS)
 }
 
 // Any geometry: one pixel per thread, three byte stores.
-__global__ void k_present_rgb8_any(const float4 *__restrict__ film, long long n_owned, double scale,
+__global__ void k_present_rgb8_any(float4 *__restrict__ film, long long n_owned, double scale,
                                    uint8_t *__restrict__ frame, int width, int tile_rows, int rank, int n_ranks,
                                    unsigned int *blocks_done, uint32_t *flag, uint32_t ticket, const uint32_t *consumed,
-                                   uint32_t *error) {
+                                   uint32_t *error, const __grid_constant__ PendingSum pending) {
   block_wait_for(consumed, ticket - 1, error);
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n_owned; k += stride) {
@@ -157,7 +175,7 @@ __global__ void k_present_rgb8_any(const float4 *__restrict__ film, long long n_
     int col = (int)(k - local_row * width);
     long long tile_local = local_row / tile_rows;
     long long row = (tile_local * n_ranks + rank) * tile_rows + (local_row - tile_local * tile_rows);
-    float4 v = film[k];
+    float4 v = film_value(film, k, pending);
     uint8_t *out = frame + ((size_t)row * width + col) * 3;
     out[0] = to_byte_f64(scale * (double)v.x);
     out[1] = to_byte_f64(scale * (double)v.y);
@@ -182,7 +200,11 @@ __global__ void k_present_rgb8_any(const float4 *__restrict__ film, long long n_
 // flag == nullptr: no arrival flag.  consumed != nullptr: every block first waits until *consumed >= ticket - 1.
 void launch_present_rgb8(const rt_context *ctx, cudaStream_t stream, const float4 *accum, int64_t n_owned, int width,
                          int tile_rows, int rank, int n_ranks, double scale, uint8_t *frame, unsigned int *blocks_done,
-                         uint32_t *flag, uint32_t ticket, const uint32_t *consumed, uint32_t *error) {
+                         uint32_t *flag, uint32_t ticket, const uint32_t *consumed, uint32_t *error, float4 *accum_rw,
+                         const PendingSum &pending) {
+  // a pending sum is folded into the film by the kernel, which then needs the film writable
+  float4 *film = accum_rw ? accum_rw : const_cast<float4 *>(accum);
+  const PendingSum sum = accum_rw ? pending : PendingSum();
   const size_t tile_bytes = (size_t)tile_rows * width * 3;
   if (n_owned == 0) {
     if (flag)
@@ -193,13 +215,13 @@ void launch_present_rgb8(const rt_context *ctx, cudaStream_t stream, const float
   if (whole_pieces && ((uintptr_t)frame & 15) == 0) {
     long long chunks = (n_owned + RT_PRESENT_PIXELS - 1) / RT_PRESENT_PIXELS;
     int blocks = (int)std::min<long long>(chunks, (long long)ctx->sm_count * 8);
-    k_present_rgb8<<<blocks, RT_PRESENT_THREADS, 0, stream>>>(accum, n_owned, scale, frame,
+    k_present_rgb8<<<blocks, RT_PRESENT_THREADS, 0, stream>>>(film, n_owned, scale, frame,
                                                               n_ranks == 1 ? (size_t)n_owned * 3 : tile_bytes, rank, n_ranks,
-                                                              blocks_done, flag, ticket, consumed, error);
+                                                              blocks_done, flag, ticket, consumed, error, sum);
   } else {
     int blocks = (int)std::min<long long>((n_owned + 255) / 256, (long long)ctx->sm_count * 8);
-    k_present_rgb8_any<<<blocks, 256, 0, stream>>>(accum, n_owned, scale, frame, width, tile_rows, rank, n_ranks, blocks_done,
-                                                   flag, ticket, consumed, error);
+    k_present_rgb8_any<<<blocks, 256, 0, stream>>>(film, n_owned, scale, frame, width, tile_rows, rank, n_ranks, blocks_done,
+                                                   flag, ticket, consumed, error, sum);
   }
 }
 
@@ -378,9 +400,14 @@ int rt_film_present(rt_film *film, double scale, rt_frame *frame) {
     consumed = frame->flags + RT_FRAME_CONSUMED; // polled by the present kernel itself
   }
   uint32_t *flag = frame->flags + film->map.rank; // raised by the kernel's last block
+  // a multi-sample pass that deferred its in-order sum: the present kernel does it while it tone-maps
+  const PendingSum pending = film->pending;
+  film->pending = PendingSum();
+  if (ctx->pending_film == film)
+    ctx->pending_film = nullptr;
   launch_present_rgb8(ctx, ctx->stream, film->accum, film->n_owned, film->map.width, film->map.tile_rows, film->map.rank,
                       film->map.n_ranks, scale, frame->rgb8, frame->blocks_done, alone ? nullptr : flag, ticket, consumed,
-                      frame->flags + RT_FRAME_ERROR);
+                      frame->flags + RT_FRAME_ERROR, film->accum, pending);
   ctx->counters.kernel_launches += 1;
   RT_CUDA(cudaGetLastError());
   return RT_OK;

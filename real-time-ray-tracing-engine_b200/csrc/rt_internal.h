@@ -103,6 +103,8 @@ struct rt_context {
   cudaGraphExec_t graph_exec = nullptr; // updated in place pass after pass
   bool audit = false; // every extend launch is checked against the FP64 parity traversal (all-wavefront schedule)
   bool stats = false; // instrumented extend / tail kernels count node visits and primitive tests
+  bool defer_accumulate = true;    // multi-sample passes leave their in-order sum to the film's next reader (RT_DEFER_ACCUMULATE=0)
+  rt_film *pending_film = nullptr; // the film whose pending sum lives in wave.radiance (at most one per context)
   cudaStream_t stream = nullptr;
   WaveBuffers wave;
   rt_counters counters{};
@@ -132,10 +134,28 @@ struct rt_scene {
   std::vector<rt_quad> h_quads;
   std::vector<int> sphere_leaf, quad_leaf; // -1: boundary primitive of a medium (not a leaf of its own)
   std::vector<float4> h_mats;
-  std::vector<PrimExact> h_ex_prims; // FP64 parity records in leaf order until their first use (rt_scene_ensure_exact)
+  std::vector<PrimExact> h_ex_prims; // FP64 parity records (description order) until their first use (rt_scene_ensure_exact)
+  std::vector<uint32_t> h_order;     // leaf j holds record h_order[j]
   int *leaf_up = nullptr;            // device: per leaf, parent node * 4 + slot
   unsigned int *arrivals = nullptr;  // device: per node refit counter
 };
+
+// The per-path radiance of a multi-sample pass that has not been summed into the film yet: k_accumulate's work,
+// handed to whichever kernel reads the film next (the present kernel sums while it tone-maps).
+struct PendingSum {
+  const float4 *radiance = nullptr; // radiance[s * n_owned + path], s < n_samples
+  int n_samples = 0;                // 0: nothing pending
+  int n_owned = 0;
+  int tiled = 0, blocks_x = 1, width = 1; // PathMap: how film index k maps to the path index of its pixel
+};
+// film index (row-major over the owned scanlines) -> path index of that pixel within one sample (inverse of path_to_pixel)
+RT_HD uint32_t film_index_to_path(const PendingSum &p, uint32_t k) {
+  if (!p.tiled)
+    return k;
+  uint32_t local_row = k / (uint32_t)p.width, col = k - local_row * (uint32_t)p.width;
+  uint32_t block = (local_row >> 2) * (uint32_t)p.blocks_x + (col >> 3);
+  return (block << 5) | ((local_row & 3u) << 3) | (col & 7u);
+}
 
 struct rt_film {
   rt_context *ctx = nullptr;
@@ -144,6 +164,10 @@ struct rt_film {
   float4 *accum = nullptr;
   bool owns_accum = false;
   int64_t samples = 0;
+  // a multi-sample pass whose in-order sum into `accum` is still to be done (only films that own their buffer defer
+  // it; rt_api.cu film_flush)
+  PendingSum pending{};
+  PassParams pending_pass{};
 };
 
 // ---- error reporting (rt_api.cu) ----
@@ -202,7 +226,9 @@ void launch_scatter_gathered(cudaStream_t s, int width, int height, int n_ranks,
 // displayed frames (rt_frame.cu)
 void launch_present_rgb8(const rt_context *ctx, cudaStream_t stream, const float4 *accum, int64_t n_owned, int width,
                          int tile_rows, int rank, int n_ranks, double scale, uint8_t *frame, unsigned int *blocks_done,
-                         uint32_t *flag, uint32_t ticket, const uint32_t *consumed, uint32_t *error);
+                         uint32_t *flag, uint32_t ticket, const uint32_t *consumed, uint32_t *error,
+                         float4 *accum_rw = nullptr, const PendingSum &pending = PendingSum());
+int rt_film_flush(rt_film *film); // completes a deferred in-order sum (rt_api.cu)
 
 // parity audit (rt_exact.cu)
 void launch_audit_trace(const rt_context *ctx, const ExactScene &sc, const PassParams &pp, WaveBuffers &w, int bounce,

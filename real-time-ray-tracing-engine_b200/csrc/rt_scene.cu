@@ -286,12 +286,9 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
   sc->h_spheres.assign(desc->spheres, desc->spheres + desc->n_spheres);
   sc->h_mats = std::move(f.mats); // not needed by this function any more
   // The FP64 parity records (160 B per primitive) are only read by rt_trace_rays(RT_TRACE_EXACT_F64), the parity
-  // audit and primitive updates: they stay on the host, in leaf order, until one of those asks (rt_scene_ensure_exact).
-  sc->h_ex_prims.resize(std::max(n, 1));
-  parallel_for((size_t)n, [&](size_t a, size_t b) {
-    for (size_t j = a; j < b; j++)
-      sc->h_ex_prims[j] = f.ex_prims[order[j]];
-  });
+  // audit and primitive updates: they stay on the host until one of those asks (rt_scene_ensure_exact).
+  sc->h_ex_prims = std::move(f.ex_prims); // description order; h_order[j] = record of leaf j
+  sc->h_order = order;
   {
     std::vector<int> leaf_of_record(std::max(n, 1), -1);
     for (int j = 0; j < n; j++)
@@ -339,16 +336,35 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
   return RT_OK;
 }
 
-// Uploads the FP64 parity records on first use.
+// Uploads the FP64 parity records on first use and brings them into leaf order on the device.
 int rt_scene_ensure_exact(rt_scene *sc) {
   if (sc->ex_prims)
     return RT_OK;
-  const size_t n = sc->h_ex_prims.size();
+  const size_t n = sc->h_order.size();
+  cudaStream_t s = sc->ctx->stream;
   RT_CUDA(cudaMalloc((void **)&sc->ex_prims, std::max<size_t>(n, 1) * sizeof(PrimExact)));
-  RT_CUDA(cudaMemcpyAsync(sc->ex_prims, sc->h_ex_prims.data(), n * sizeof(PrimExact), cudaMemcpyHostToDevice, sc->ctx->stream));
-  RT_CUDA(cudaStreamSynchronize(sc->ctx->stream));
+  if (n) {
+    PrimExact *d_in = nullptr;
+    uint32_t *d_order = nullptr;
+    RT_CUDA(cudaMalloc((void **)&d_in, n * sizeof(PrimExact)));
+    cudaError_t e = cudaMalloc((void **)&d_order, n * sizeof(uint32_t));
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(d_in, sc->h_ex_prims.data(), n * sizeof(PrimExact), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(d_order, sc->h_order.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) {
+      static_assert(sizeof(PrimExact) % 16 == 0, "PrimExact must be a multiple of 16 bytes");
+      launch_gather_records(s, d_in, d_order, sc->ex_prims, (int)n, (int)sizeof(PrimExact));
+      e = cudaStreamSynchronize(s);
+    }
+    cudaFree(d_in);
+    cudaFree(d_order);
+    if (e != cudaSuccess)
+      return rt_cuda_fail(e, "rt_scene_ensure_exact");
+  }
   sc->ex.prims = sc->ex_prims;
   std::vector<PrimExact>().swap(sc->h_ex_prims); // the device copy is the master from here on
+  std::vector<uint32_t>().swap(sc->h_order);
   return RT_OK;
 }
 

@@ -707,3 +707,40 @@ def test_graph_passes_render_the_same_image(host_scenes):
         scene.close()
         c.close()
     assert np.array_equal(images[0], images[1])
+
+
+@pytest.mark.parametrize("rank,n_ranks,width", [(0, 1, 320), (1, 2, 320), (2, 3, 200)])
+def test_deferred_sample_sum_is_bit_identical(host_scenes, monkeypatch, rank, n_ranks, width):
+    """A multi-sample pass leaves the in-order per-pixel sum of its samples to the film's next reader: the present
+    kernel folds it into the tone map, every other reader runs k_accumulate first.  Film sums and frame bytes must
+    equal the immediate-accumulate schedule bit for bit, for whole films and for tile-partitioned ones."""
+    hs = host_scenes("spheres", 11, -1)
+    cam = engine.camera_from_config(hs.camera_config(width, 9, 8))
+    W, H = cam.image_width, cam.image_height
+    out = {}
+    for defer in ("1", "0"):
+        monkeypatch.setenv("RT_DEFER_ACCUMULATE", defer)
+        c = engine.Context(0)
+        scene = engine.Scene(c, hs.desc)
+        film = engine.Film(c, W, H, rank, n_ranks, 8)
+        frame = engine.Frame(c, W, H, n_ranks)
+        buf = np.zeros((W * H, 3), dtype=np.uint8)
+        engine.render_strata(scene, cam, film, 0, 3, 3, 8, 5)   # 3 strata, summed by the present kernel
+        frame.present(film, 1.0 / 3)
+        engine.render_strata(scene, cam, film, 3, 4, 3, 8, 5)   # 4 more, summed by the next pass's flush ...
+        engine.render_accumulate(scene, cam, film, 1, 2, 3, 8, 5)  # ... before this one-sample pass
+        engine.render_strata(scene, cam, film, 8, 1, 3, 8, 5)
+        sums = film.read_rgb(1.0)                               # read_rgb completes whatever is pending
+        engine.render_strata(scene, cam, film, 0, 2, 3, 8, 6)
+        frame.present(film, 1.0 / 11)
+        frame.download(buf.ctypes.data)
+        frame.download_wait()
+        out[defer] = (sums, buf.copy(), film.read_rgb(1.0), c.counters().kernel_launches)
+        assert film.samples == 11
+        frame.close()
+        film.close()
+        scene.close()
+        c.close()
+    assert np.array_equal(out["1"][0], out["0"][0]) and np.array_equal(out["1"][2], out["0"][2])
+    assert np.array_equal(out["1"][1], out["0"][1]) and out["1"][1].max() > 0
+    assert out["1"][3] < out["0"][3]  # the two presented passes saved their accumulate launches

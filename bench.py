@@ -663,7 +663,9 @@ def gpu_reference_leg(our_frame_ms):
     import subprocess
 
     try:
-        r = subprocess.run([sys.executable, os.path.join(REPO, "tools", "ref_gpu_frame.py"), SCENE, "11", str(WIDTH), str(DEPTH), "1"],
+        # whole-frame launch only: the reference's per-tile launch loop takes 44 s per 1080p frame (profiles/r02_reference_gpu.md)
+        r = subprocess.run([sys.executable, os.path.join(REPO, "tools", "ref_gpu_frame.py"), SCENE, "11", str(WIDTH), str(DEPTH), "1",
+                            "--whole-frame-only"],
                            capture_output=True, text=True, timeout=900)
         lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
         out = json.loads(lines[-1]) if lines else {"error": (r.stderr or "no output")[-300:]}

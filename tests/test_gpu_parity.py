@@ -698,9 +698,9 @@ def test_graph_passes_render_the_same_image(host_scenes):
             cfg2.lookfrom[0] += 1.0  # a camera move is a parameter update as well
             cam2 = engine.camera_from_config(cfg2)
             engine.render_accumulate(scene, cam2, film, 0, 0, 2, 8, 99)
-            engine.render_static(scene, cam, film, 2, 8, 5)  # another pass shape (4 samples + accumulate): one rebuild
-            n = c.counters()
-            assert n.graph_launches == 8 and n.graph_instantiations == 2, (n.graph_launches, n.graph_instantiations)
+            engine.render_static(scene, cam, film, 2, 8, 5)  # a 4-sample pass: same launch sequence when its sample sum
+            n = c.counters()                                 # is deferred to the film's next reader, else one rebuild
+            assert n.graph_launches == 8 and n.graph_instantiations in (1, 2), (n.graph_launches, n.graph_instantiations)
         else:
             assert n.graph_launches == 0
         film.close()

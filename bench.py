@@ -301,12 +301,17 @@ def run_ours(args):
         with torch.cuda.stream(stream):
             l2_flush.fill_(s & 0xFF)  # evict the scene and queues from L2 between timed steps
 
+    def present_on_device(frame):
+        """A frame that stays on the device (a window that displays from GPU memory): present, then rank 0 waits for
+        all ranks and marks the frame consumed in one launch."""
+        frame.present(film, 1.0 / max(1, film.samples))
+        if rank == 0:
+            frame.wait_release()
+
     def device_step(s):
         flush_only(s)
         render_step(s)
-        present(frames[0])
-        if rank == 0:
-            frames[0].release()
+        present_on_device(frames[0])
 
     def timed(n_steps):
         """Device time of n_steps steps on the context stream (ms per step, max over ranks).  Every step is
@@ -318,9 +323,7 @@ def run_ours(args):
             flush_only(s)
             e0.record(stream)
             render_step(s)
-            present(frames[0])
-            if rank == 0:
-                frames[0].release()
+            present_on_device(frames[0])
             e1.record(stream)
         barrier()
         return all_max(sum(e0.elapsed_time(e1) for e0, e1 in pairs) / n_steps)
@@ -595,8 +598,7 @@ def static_4k_leg(ctx, stream, world, rank, shared_frames, close_frames, barrier
         engine.render_static(scene, cam, film, root, DEPTH4K, SEED)
         frame.present(film, 1.0 / (root * root))
         if rank == 0:
-            frame.wait()
-            frame.release()
+            frame.wait_release()
         e1.record(stream)
         barrier()
         return all_max(e0.elapsed_time(e1))

@@ -413,6 +413,7 @@ uint64_t rt_frame_device_ptr(rt_frame *frame); /* the RGB8 image, as seen from t
 int rt_film_present(rt_film *film, double scale, rt_frame *frame);
 int rt_frame_wait(rt_frame *frame);
 int rt_frame_release(rt_frame *frame);
+int rt_frame_wait_release(rt_frame *frame); /* rt_frame_wait + rt_frame_release in one launch (a frame that stays on the device) */
 int rt_frame_download(rt_frame *frame, uint8_t *host_rgb8); /* host_rgb8: width*height*3 bytes, pinned for overlap */
 int rt_frame_download_wait(rt_frame *frame);                /* blocks until the download is in host memory */
 int rt_frame_error(rt_frame *frame);                        /* 0 = fine, 1 = a wait timed out, < 0 = CUDA error */

@@ -55,17 +55,26 @@ __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
 }
 
 // Thread r waits until word[r] has reached `ticket` (wrap-around safe), or gives up after the timeout.
-__global__ void k_frame_wait(const uint32_t *words, int n_words, uint32_t ticket, uint32_t *error) {
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n_words)
-    return;
-  long long t0 = clock64();
-  while ((int32_t)(ld_acquire_sys(words + r) - ticket) < 0) {
-    if (clock64() - t0 > RT_FRAME_TIMEOUT_CYCLES) {
-      atomicExch(error, 1u);
-      return;
+// One block.  release != nullptr: once every word has arrived, *release = ticket (the owner consumed the frame
+// without copying it anywhere: rt_frame_wait_release).
+__global__ void k_frame_wait(const uint32_t *words, int n_words, uint32_t ticket, uint32_t *error, uint32_t *release) {
+  int r = threadIdx.x;
+  if (r < n_words) {
+    long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys(words + r) - ticket) < 0) {
+      if (clock64() - t0 > RT_FRAME_TIMEOUT_CYCLES) {
+        atomicExch(error, 1u);
+        break;
+      }
+      __nanosleep(128);
     }
-    __nanosleep(128);
+  }
+  if (release) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      st_release_sys(release, ticket);
+    }
   }
 }
 
@@ -419,7 +428,21 @@ int rt_frame_wait(rt_frame *frame) {
   rt_context *ctx = frame->ctx;
   RT_CUDA(cudaSetDevice(ctx->device));
   if (frame->n_ranks > 1) {
-    k_frame_wait<<<1, 64, 0, ctx->stream>>>(frame->flags, frame->n_ranks, frame->ticket, frame->flags + RT_FRAME_ERROR);
+    k_frame_wait<<<1, 64, 0, ctx->stream>>>(frame->flags, frame->n_ranks, frame->ticket, frame->flags + RT_FRAME_ERROR, nullptr);
+    ctx->counters.kernel_launches += 1;
+    RT_CUDA(cudaGetLastError());
+  }
+  return RT_OK;
+}
+
+int rt_frame_wait_release(rt_frame *frame) {
+  if (!frame || !frame->owner)
+    return frame_invalid("rt_frame_wait_release: needs the owner's frame");
+  rt_context *ctx = frame->ctx;
+  RT_CUDA(cudaSetDevice(ctx->device));
+  if (frame->n_ranks > 1) {
+    k_frame_wait<<<1, 64, 0, ctx->stream>>>(frame->flags, frame->n_ranks, frame->ticket, frame->flags + RT_FRAME_ERROR,
+                                            frame->flags + RT_FRAME_CONSUMED);
     ctx->counters.kernel_launches += 1;
     RT_CUDA(cudaGetLastError());
   }

@@ -182,6 +182,7 @@ RT_B200_SYMBOLS = {
     "rt_film_present": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p]),
     "rt_frame_wait": (C.c_int, [C.c_void_p]),
     "rt_frame_release": (C.c_int, [C.c_void_p]),
+    "rt_frame_wait_release": (C.c_int, [C.c_void_p]),
     "rt_frame_download": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rt_frame_download_wait": (C.c_int, [C.c_void_p]),
     "rt_frame_error": (C.c_int, [C.c_void_p]),

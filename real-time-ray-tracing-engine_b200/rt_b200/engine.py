@@ -230,6 +230,9 @@ class Frame:
     def wait(self):
         abi.check(self.lib, self.lib.rt_frame_wait(self._h), "rt_frame_wait")
 
+    def wait_release(self):
+        abi.check(self.lib, self.lib.rt_frame_wait_release(self._h), "rt_frame_wait_release")
+
     def release(self):
         abi.check(self.lib, self.lib.rt_frame_release(self._h), "rt_frame_release")
 

@@ -303,6 +303,269 @@ __global__ void __launch_bounds__(RT_BLOCK, 8)
   traversal_stats<STATS>(stats, n_nodes, n_tests);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// extend, two rays per lane (RT_EXTEND_MUX=1) - an EXPERIMENT, measured slower, not the default
+// ---------------------------------------------------------------------------------------------------
+// The while-while loop above keeps a lane idle from the moment its ray reaches a leaf until every other lane of
+// the warp has reached one too (ncu: 17 of 32 lanes in the node loop on scattered rays).  Here every lane owns TWO
+// rays: the one in registers and a parked one whose traversal state (11 words) and short stack live in shared
+// memory.  A lane whose ray leaves the node phase swaps to its parked ray if that one still has nodes to visit,
+// so the node loop only runs out of work for a lane when BOTH its rays wait for the leaf phase; the leaf phase
+// then serves both.  Same node visits, same primitive tests, same answers per ray (images bit-identical,
+// tools/mux_check.py) - only their interleaving changes.
+// Measured on B200 (profiles/r02_experiments.md, ncu capture r02_mux_ncu.md): the node loop does run at 24.6 of 32
+// lanes instead of 17.2 and takes 30 % fewer iterations, exactly as intended - and the kernel is still 1.5-1.6 x
+// SLOWER (C2 extend 0.49-0.54 ms against 0.33): the swap puts shared-memory round trips and a warp-wide vote on
+// the critical path of every node iteration, issue rate falls from 2.6 to 1.3 instructions per clock (long-
+// scoreboard stalls 2.6 -> 17), i.e. the issue-bound kernel becomes latency bound, and the swap / vote
+// instructions give back a third of the saved iterations.  Kept selectable for the record; exit / refill
+// thresholds and 6 blocks per SM without spills move it by < 10 %.
+#ifndef RT_MUX_NODE_EXIT
+#define RT_MUX_NODE_EXIT 12 // leave the node phase when fewer lanes than this still have a node to visit
+#endif
+#ifndef RT_MUX_REFILL
+#define RT_MUX_REFILL 20 // refill when at least this many of the warp's 64 ray slots are empty
+#endif
+__shared__ __align__(16384) int2 rt_mux_stack_smem[2 * RT_STACK_SMEM * RT_BLOCK];
+__shared__ float4 rt_mux_park[3 * RT_BLOCK];
+struct MuxStack { // SmemStack with two regions; `which` selects the region of the ray in registers
+  static constexpr bool has_fast_push = true;
+  static constexpr int fast_depth = RT_STACK_SMEM;
+  unsigned base0, base;
+  int spill_off;
+  StackEntry spill[2 * (RT_STACK - RT_STACK_SMEM)];
+  __device__ __forceinline__ void init() {
+    base0 = (unsigned)__cvta_generic_to_shared(&rt_mux_stack_smem[threadIdx.x]);
+    asm volatile("" : "+r"(base0));
+    select(0);
+  }
+  __device__ __forceinline__ void select(int which) {
+    base = base0 + (unsigned)which * (RT_STACK_SMEM * RT_BLOCK * 8u);
+    spill_off = which * (RT_STACK - RT_STACK_SMEM);
+  }
+  __device__ __forceinline__ void set_fast_if(int i, int ref, float t, bool p) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p st.shared.v2.b32 [%0], {%1, %2};\n\t}"
+                 :
+                 : "r"(base + (unsigned)i * (RT_BLOCK * 8u)), "r"(ref), "r"(__float_as_int(t)), "r"((int)p)
+                 : "memory");
+  }
+  __device__ __forceinline__ void set(int i, int ref, float t) {
+    if (i < RT_STACK_SMEM) {
+      set_fast_if(i, ref, t, true);
+    } else {
+      spill[spill_off + i - RT_STACK_SMEM].ref = ref;
+      spill[spill_off + i - RT_STACK_SMEM].t = t;
+    }
+  }
+  __device__ __forceinline__ void get(int i, int &ref, float &t) const {
+    if (i < RT_STACK_SMEM) {
+      int tb;
+      asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];"
+                   : "=r"(ref), "=r"(tb)
+                   : "r"(base + (unsigned)i * (RT_BLOCK * 8u))
+                   : "memory");
+      t = __int_as_float(tb);
+    } else {
+      ref = spill[spill_off + i - RT_STACK_SMEM].ref;
+      t = spill[spill_off + i - RT_STACK_SMEM].t;
+    }
+  }
+};
+
+enum { RT_SLOT_EMPTY = 0, RT_SLOT_NODE = 1, RT_SLOT_LEAF = 2 };
+
+// traversal state of one ray: what moves between the registers and the parked slot
+struct MuxRay {
+  f3 inv, oi;
+  Hit best;
+  int sp, ref;
+  unsigned int q;
+};
+__device__ __forceinline__ RayTrav mux_trav(const MuxRay &r) { // the derived parts of RayTrav are recomputed, not parked
+  RayTrav t;
+  t.inv = r.inv;
+  t.oi = r.oi;
+  t.slack = 2.5e-7f * fmaxf(fabsf(r.oi.x), fmaxf(fabsf(r.oi.y), fabsf(r.oi.z)));
+  t.nx = sign_bit(r.inv.x) ? 1 : 0; // 1 / d has the sign of d (a zero component gives +-inf with the sign of the zero)
+  t.ny = sign_bit(r.inv.y) ? 3 : 2;
+  t.nz = sign_bit(r.inv.z) ? 5 : 4;
+  return t;
+}
+__device__ __forceinline__ int mux_state(int ref) { return ref == RT_DONE ? RT_SLOT_EMPTY : (ref >= 0 ? RT_SLOT_NODE : RT_SLOT_LEAF); }
+
+#ifndef RT_MUX_BLOCKS
+#define RT_MUX_BLOCKS 8
+#endif
+// registers <-> parked slot, one 16-byte row at a time so that only four temporaries are live
+#define RT_MUX_SWAP()                                                                                        \
+  do {                                                                                                       \
+    if (cur.ref == RT_DONE && cur.best.t != -1.0f) { /* a ray that ended writes its answer before it leaves */ \
+      hit[cur.q] = make_float2(cur.best.t, __int_as_float(cur.best.prim));                                   \
+      cur.best.t = -1.0f;                                                                                    \
+    }                                                                                                        \
+    float4 row = rt_mux_park[threadIdx.x];                                                                   \
+    rt_mux_park[threadIdx.x] = make_float4(cur.inv.x, cur.inv.y, cur.inv.z, cur.best.t);                     \
+    cur.inv = F3(row.x, row.y, row.z);                                                                       \
+    cur.best.t = row.w;                                                                                      \
+    row = rt_mux_park[RT_BLOCK + threadIdx.x];                                                               \
+    rt_mux_park[RT_BLOCK + threadIdx.x] = make_float4(cur.oi.x, cur.oi.y, cur.oi.z, __int_as_float(cur.best.prim)); \
+    cur.oi = F3(row.x, row.y, row.z);                                                                        \
+    cur.best.prim = __float_as_int(row.w);                                                                   \
+    row = rt_mux_park[2 * RT_BLOCK + threadIdx.x];                                                           \
+    rt_mux_park[2 * RT_BLOCK + threadIdx.x] =                                                                \
+        make_float4(__int_as_float(cur.sp), __int_as_float(cur.ref), __uint_as_float(cur.q), 0.f);           \
+    const int new_parked = mux_state(cur.ref);                                                               \
+    cur.sp = __float_as_int(row.x);                                                                          \
+    cur.ref = parked == RT_SLOT_EMPTY ? RT_DONE : __float_as_int(row.y);                                     \
+    cur.q = __float_as_uint(row.z);                                                                          \
+    if (parked == RT_SLOT_EMPTY)                                                                             \
+      cur.best.t = -1.0f;                                                                                    \
+    parked = new_parked;                                                                                     \
+    stack.base ^= stack_toggle;                                                                              \
+    stack.spill_off ^= (RT_STACK - RT_STACK_SMEM);                                                           \
+    rt = mux_trav(cur);                                                                                      \
+  } while (0)
+
+template <bool STATS>
+__global__ void __launch_bounds__(RT_BLOCK, RT_MUX_BLOCKS)
+    k_extend_mux(const __grid_constant__ DScene sc, const __grid_constant__ PassParams pp, const float4 *__restrict__ ray_a,
+                 const float4 *__restrict__ ray_b, float2 *__restrict__ hit, unsigned int *__restrict__ counts,
+                 unsigned int *__restrict__ cursor, int bounce, int has_media, unsigned long long *stats) {
+  MuxStack stack;
+  stack.init();
+  // the two stack regions are RT_STACK_SMEM * RT_BLOCK * 8 bytes apart: with the first one aligned to that size
+  // (a power of two) the region is switched by flipping one address bit
+  static_assert((RT_STACK_SMEM * RT_BLOCK * 8) == 8192, "stack region toggle assumes 8 KiB regions");
+  const unsigned stack_toggle = 8192u; // region 0 starts 16 KiB-aligned (rt_mux_stack_smem), so bit 13 selects the region
+  const unsigned int n = counts[bounce];
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    atomicAdd(&stats[0], (unsigned long long)n);
+  const unsigned int lane = threadIdx.x & 31u;
+  const unsigned int lt_mask = (1u << lane) - 1u;
+
+  MuxRay cur; // the ray in registers
+  cur.inv = cur.oi = F3(1.f, 1.f, 1.f);
+  cur.best.t = -1.f;
+  cur.best.prim = -1;
+  cur.sp = 0;
+  cur.ref = RT_DONE;
+  cur.q = 0;
+  RayTrav rt = mux_trav(cur);
+  int parked = RT_SLOT_EMPTY; // state of the parked ray
+  unsigned int n_nodes = 0, n_tests = 0;
+  bool exhausted = false;
+
+  for (;;) {
+    // ---- refill: empty slots take the next rays of the queue (registers first, then the parked slots) ----
+    if (!exhausted) {
+      unsigned int empty_cur = __ballot_sync(0xffffffffu, cur.ref == RT_DONE);
+      unsigned int empty_parked = __ballot_sync(0xffffffffu, parked == RT_SLOT_EMPTY);
+      if (__popc(empty_cur) + __popc(empty_parked) >= RT_MUX_REFILL) {
+#pragma unroll 1
+        for (int round = 0; round < 2 && !exhausted; round++) {
+          const unsigned int want = round == 0 ? empty_cur : empty_parked;
+          if (!want)
+            continue;
+          const bool mine_wanted = round == 0 ? cur.ref == RT_DONE : parked == RT_SLOT_EMPTY;
+          unsigned int base = 0;
+          int leader = __ffs(want) - 1;
+          if ((int)lane == leader)
+            base = atomicAdd(cursor, (unsigned int)__popc(want));
+          base = __shfl_sync(0xffffffffu, base, leader);
+          exhausted = base + (unsigned int)__popc(want) >= n;
+          unsigned int mine = base + (unsigned int)__popc(want & lt_mask);
+          if (mine_wanted && mine < n) {
+            float4 a = ray_a[mine], b = ray_b[mine];
+            RayTrav t = make_trav(F3(a.x, a.y, a.z), F3(b.x, b.y, b.z));
+            if (round == 0) {
+              cur.inv = t.inv;
+              cur.oi = t.oi;
+              cur.best.t = RT_INF_F;
+              cur.best.prim = -1;
+              cur.sp = 0;
+              cur.ref = 0; // root
+              cur.q = mine;
+              rt = t;
+            } else {
+              rt_mux_park[threadIdx.x] = make_float4(t.inv.x, t.inv.y, t.inv.z, RT_INF_F);
+              rt_mux_park[RT_BLOCK + threadIdx.x] = make_float4(t.oi.x, t.oi.y, t.oi.z, __int_as_float(-1));
+              rt_mux_park[2 * RT_BLOCK + threadIdx.x] = make_float4(__int_as_float(0), __int_as_float(0), __uint_as_float(mine), 0.f);
+              parked = RT_SLOT_NODE;
+            }
+          }
+        }
+      }
+    }
+    if (__all_sync(0xffffffffu, cur.ref == RT_DONE && parked == RT_SLOT_EMPTY))
+      break;
+
+    for (;;) {
+      // ---- node phase: a lane whose ray stops at a leaf (or ends) continues with its parked ray ----
+      for (;;) {
+        if (!(cur.ref >= 0 && cur.ref != RT_DONE) && parked == RT_SLOT_NODE)
+          RT_MUX_SWAP();
+        const bool work = cur.ref >= 0 && cur.ref != RT_DONE;
+        unsigned int busy = __ballot_sync(0xffffffffu, work);
+        if (__popc(busy) < RT_MUX_NODE_EXIT) {
+          // the stragglers finish their current node run (as in the plain loop) unless leaf work is waiting
+          if (busy == 0 || __any_sync(0xffffffffu, (cur.ref < 0) || parked == RT_SLOT_LEAF))
+            break;
+        }
+        if (work) {
+          if (STATS)
+            n_nodes++;
+          if (!node_visit(sc, cur.ref, rt, RT_T_MIN, cur.best.t, stack, cur.sp, cur.ref))
+            if (!stack_pop(stack, cur.sp, cur.best.t, cur.ref))
+              cur.ref = RT_DONE;
+        }
+      }
+      // ---- leaf phase: the ray in registers, then the parked one ----
+#pragma unroll 1
+      for (int pass = 0; pass < 2; pass++) {
+        if (pass == 1) {
+          if (!__any_sync(0xffffffffu, parked == RT_SLOT_LEAF))
+            break;
+          if (parked == RT_SLOT_LEAF)
+            RT_MUX_SWAP();
+        }
+        if (cur.ref < 0) {
+          float4 a = ray_a[cur.q], b = ray_b[cur.q];
+          Ray r;
+          r.o = F3(a.x, a.y, a.z);
+          r.d = F3(b.x, b.y, b.z);
+          r.time = a.w;
+          int skip = bounce == 0 ? -1 : __float_as_int(hit[cur.q].y);
+          RayKey key;
+          key.seed = pp.seed;
+          key.pixel = key.sample = 0;
+          key.bounce = (uint32_t)bounce;
+          if (has_media) {
+            int k;
+            path_to_key(pp, __float_as_int(b.w), bounce, key, k);
+          }
+          do {
+            if (STATS)
+              n_tests++;
+            leaf_test(sc, ~cur.ref, r, RT_T_MIN, cur.best, skip, key);
+            if (!stack_pop(stack, cur.sp, cur.best.t, cur.ref))
+              cur.ref = RT_DONE;
+          } while (cur.ref < 0);
+        }
+        if (cur.ref == RT_DONE && cur.best.t != -1.0f) { // a ray that ended writes its answer once and frees its slot
+          hit[cur.q] = make_float2(cur.best.t, __int_as_float(cur.best.prim));
+          cur.best.t = -1.0f;
+        }
+      }
+      unsigned int node_work = __ballot_sync(0xffffffffu, (cur.ref >= 0 && cur.ref != RT_DONE) || parked == RT_SLOT_NODE);
+      unsigned int empty = __popc(__ballot_sync(0xffffffffu, cur.ref == RT_DONE)) + __popc(__ballot_sync(0xffffffffu, parked == RT_SLOT_EMPTY));
+      if (node_work == 0 || (!exhausted && empty >= RT_MUX_REFILL))
+        break;
+    }
+  }
+  traversal_stats<STATS>(stats, n_nodes, n_tests);
+}
+#undef RT_MUX_SWAP
+
 // The straightforward variant (one ray per thread, grid stride, single if/else loop); kept for A/B
 // measurements (RT_EXTEND=simple).
 __global__ void __launch_bounds__(RT_BLOCK)
@@ -1105,10 +1368,20 @@ void launch_extend(const rt_context *ctx, const DScene &sc, const PassParams &pp
   int need = ceil_div(pp.n_paths, RT_BLOCK);
   unsigned int *cursor = w.counts + (pp.max_depth + 2) + bounce;
   const int blocks = need < sh.blocks ? need : sh.blocks;
+  static const bool mux = getenv("RT_EXTEND_MUX") && atoi(getenv("RT_EXTEND_MUX")) != 0;
+  if (mux && !gen) {
+    auto k = ctx->stats ? k_extend_mux<true> : k_extend_mux<false>;
+    k<<<blocks, RT_BLOCK, 0, ctx->stream>>>(sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b], w.counts, cursor, bounce, sc.n_media > 0,
+                                            w.stats);
+    return;
+  }
   auto kernel = gen ? (ctx->stats ? k_extend<true, true> : k_extend<false, true>)
                     : (ctx->stats ? k_extend<true, false> : k_extend<false, false>);
-  kernel<<<blocks, RT_BLOCK, 0, ctx->stream>>>(sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b], w.counts, cursor, bounce,
-                                               sc.n_media > 0, w.stats);
+  // RT_EXTEND_DYN_SMEM=<bytes>: unused dynamic shared memory per block (experiment aid: how much the kernel
+  // depends on the L1 capacity that shared memory is carved out of)
+  static const size_t dyn_smem = getenv("RT_EXTEND_DYN_SMEM") ? (size_t)atol(getenv("RT_EXTEND_DYN_SMEM")) : 0;
+  kernel<<<blocks, RT_BLOCK, dyn_smem, ctx->stream>>>(sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b], w.counts, cursor, bounce,
+                                                      sc.n_media > 0, w.stats);
 }
 
 void launch_shade(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int bounce, bool gen) {

@@ -744,3 +744,15 @@ def test_deferred_sample_sum_is_bit_identical(host_scenes, monkeypatch, rank, n_
     assert np.array_equal(out["1"][0], out["0"][0]) and np.array_equal(out["1"][2], out["0"][2])
     assert np.array_equal(out["1"][1], out["0"][1]) and out["1"][1].max() > 0
     assert out["1"][3] < out["0"][3]  # the two presented passes saved their accumulate launches
+
+
+def test_two_rays_per_lane_extend_renders_the_same_bits():
+    """RT_EXTEND_MUX=1 (the experimental extend kernel that keeps two rays per lane): same node visits and primitive
+    tests per ray in another interleaving, so the images of three scenes are bit-identical (tools/mux_check.py)."""
+    import subprocess
+    import sys
+    import os
+
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(repo, "tools", "mux_check.py")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and r.stdout.strip().endswith("IDENTICAL"), (r.stdout[-800:], r.stderr[-800:])

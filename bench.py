@@ -22,7 +22,7 @@ Printed JSON (one line, rank 0):
                render of it (oracle/_ref): RMSE, the reference-vs-reference RMSE floor, ratio, luminance
   parity       fast_vs_exact: the FP32 product traversal against the FP64 parity traversal (the reference's
                arithmetic) on EVERY segment of one 1080p frame; how often they name a different primitive
-  static_4k    strong scaling: the final scene at 3840x2160, 16 spp, depth 50 - fixed total work over the N GPUs -
+  static_4k    strong scaling: the final scene at 3840x2160, 64 spp, depth 50 - fixed total work over the N GPUs -
                with the SHA-256 of the assembled RGB8 frame (identical for every N)
   frame_sha    SHA-256 of one assembled 1080p frame of the benchmark scene (stratum 0, fixed seed; identical for every N)
   gpu_reference  the reference's own GPU kernels (unmodified, compiled for sm_100) on the same frame and GPU (N=1 only)
@@ -573,14 +573,14 @@ def roofline_block(peaks, seg_per_launch, launch_ms, stage_ms, roof_steps, strat
 
 def static_4k_leg(ctx, stream, world, rank, shared_frames, close_frames, barrier, all_max, all_sum):
     """Strong scaling (north_star: "near-linear 8-GPU scaling on 4K high-spp static renders"): the final scene
-    (BASELINE config 5's scene) at 3840x2160, depth 50, 16 spp instead of 4096 so that the default run stays short -
+    (BASELINE config 5's scene) at 3840x2160, depth 50, 64 spp instead of 4096 so that the default run stays short -
     FIXED total work, tiles interleaved over the N GPUs, every rank's tiles tone-mapped into rank 0's 4K frame.
     Device time of render + present (max over ranks), best of 2, and the SHA-256 of the assembled frame."""
     import torch
 
     from rt_b200 import engine, host
 
-    WIDTH4K, ROOT, DEPTH4K, SEED = 3840, 4, 50, 77
+    WIDTH4K, ROOT, DEPTH4K, SEED = 3840, 8, 50, 77
     hs = host.HostScene.builtin("final", SCENE_SEED, 20, 1000)
     scene = engine.Scene(ctx, hs.desc)
     n_prims = scene.info().n_prims

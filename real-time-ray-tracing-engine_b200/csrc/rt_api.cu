@@ -48,19 +48,19 @@ int ensure_wave(rt_context *ctx, size_t n_paths, size_t n_counts) {
       cudaFree(w.ray_a[k]);
       cudaFree(w.ray_b[k]);
       cudaFree(w.hit[k]);
-      w.ray_a[k] = w.ray_b[k] = nullptr;
+      cudaFree(w.thr[k]);
+      w.ray_a[k] = w.ray_b[k] = w.thr[k] = nullptr;
       w.hit[k] = nullptr;
     }
-    cudaFree(w.throughput);
     cudaFree(w.radiance);
-    w.throughput = w.radiance = nullptr;
+    w.radiance = nullptr;
     w.capacity_paths = 0;
     for (int k = 0; k < 2; k++) {
       RT_CUDA(cudaMalloc((void **)&w.ray_a[k], n_paths * sizeof(float4)));
       RT_CUDA(cudaMalloc((void **)&w.ray_b[k], n_paths * sizeof(float4)));
       RT_CUDA(cudaMalloc((void **)&w.hit[k], n_paths * sizeof(float2)));
+      RT_CUDA(cudaMalloc((void **)&w.thr[k], n_paths * sizeof(float4)));
     }
-    RT_CUDA(cudaMalloc((void **)&w.throughput, n_paths * sizeof(float4)));
     RT_CUDA(cudaMalloc((void **)&w.radiance, n_paths * sizeof(float4)));
     w.capacity_paths = n_paths;
   }
@@ -436,8 +436,8 @@ void rt_context_destroy(rt_context *ctx) {
     cudaFree(w.ray_a[k]);
     cudaFree(w.ray_b[k]);
     cudaFree(w.hit[k]);
+    cudaFree(w.thr[k]);
   }
-  cudaFree(w.throughput);
   cudaFree(w.radiance);
   cudaFree(w.counts);
   cudaFree(w.stats);

@@ -55,7 +55,7 @@ struct WaveBuffers {
   float4 *ray_a[2] = {nullptr, nullptr}; // origin.xyz, time
   float4 *ray_b[2] = {nullptr, nullptr}; // direction.xyz, path id (int bits)
   float2 *hit[2] = {nullptr, nullptr};   // in: (-, skip primitive)  out: (t, primitive) for the same queue slot
-  float4 *throughput = nullptr;          // per path
+  float4 *thr[2] = {nullptr, nullptr};   // path throughput of the ray in the same queue slot
   float4 *radiance = nullptr;            // per path: final contribution
   unsigned int *counts = nullptr;        // queue length per bounce (max_depth + 2 entries)
   unsigned long long *stats = nullptr;   // [0] segments of the extend launches  [1] node visits  [2] primitive tests

@@ -623,8 +623,8 @@ template <bool GEN>
 __global__ void __launch_bounds__(RT_SHADE_THREADS, RT_SHADE_BLOCKS * RT_BLOCK / RT_SHADE_THREADS)
     k_shade(const __grid_constant__ DScene sc, const __grid_constant__ PassParams pp, const float4 *__restrict__ ray_a,
             const float4 *__restrict__ ray_b, const float2 *__restrict__ hit, float4 *__restrict__ next_a,
-            float4 *__restrict__ next_b, float2 *__restrict__ next_hit, float4 *__restrict__ throughput,
-            float4 *__restrict__ radiance, unsigned int *__restrict__ counts, int bounce) {
+            float4 *__restrict__ next_b, float2 *__restrict__ next_hit, const float4 *__restrict__ thr,
+            float4 *__restrict__ next_thr, float4 *__restrict__ radiance, unsigned int *__restrict__ counts, int bounce) {
   __shared__ unsigned int s_count[RT_SHADE_WARPS], s_first[RT_SHADE_WARPS];
 #if RT_SHADE_SORT
   __shared__ unsigned int s_sort[8 * RT_SHADE_WARPS];
@@ -665,12 +665,12 @@ __global__ void __launch_bounds__(RT_SHADE_THREADS, RT_SHADE_BLOCKS * RT_BLOCK /
       RayKey key;
       int k;
       path_to_key(pp, path, bounce, key, k);
-      float4 tp = bounce == 0 ? make_float4(1.f, 1.f, 1.f, 0.f) : throughput[path];
+      // the path throughput travels with the ray, in queue order (sequential 16-byte accesses instead of a
+      // per-path array read and written at random: half-used 32-byte sectors both ways)
+      float4 tp = bounce == 0 ? make_float4(1.f, 1.f, 1.f, 0.f) : ldg4_now(thr + q);
       cont = shade_segment(sc, r, ht, F3(tp.x, tp.y, tp.z), key, last_bounce, res);
       if (!cont)
         path_ends(pp, radiance, path, k, res.radiance);
-      else
-        throughput[path] = make_float4(res.throughput.x, res.throughput.y, res.throughput.z, 0.f);
     }
 #if RT_SHADE_SORT
     // Block-local counting sort of the continuing rays by direction octant: the block's slots are handed out
@@ -717,6 +717,7 @@ __global__ void __launch_bounds__(RT_SHADE_THREADS, RT_SHADE_BLOCKS * RT_BLOCK /
       next_a[slot] = make_float4(res.next.o.x, res.next.o.y, res.next.o.z, res.next.time);
       next_b[slot] = make_float4(res.next.d.x, res.next.d.y, res.next.d.z, __int_as_float(path));
       next_hit[slot] = make_float2(0.f, __int_as_float(res.next_skip_prim));
+      next_thr[slot] = make_float4(res.throughput.x, res.throughput.y, res.throughput.z, 0.f);
     }
     __syncthreads(); // s_sort is rewritten by the next iteration
     continue;
@@ -748,6 +749,7 @@ __global__ void __launch_bounds__(RT_SHADE_THREADS, RT_SHADE_BLOCKS * RT_BLOCK /
       next_a[slot] = make_float4(res.next.o.x, res.next.o.y, res.next.o.z, res.next.time);
       next_b[slot] = make_float4(res.next.d.x, res.next.d.y, res.next.d.z, __int_as_float(path));
       next_hit[slot] = make_float2(0.f, __int_as_float(res.next_skip_prim));
+      next_thr[slot] = make_float4(res.throughput.x, res.throughput.y, res.throughput.z, 0.f);
     }
   }
 }
@@ -780,8 +782,9 @@ template <bool STATS>
 __global__ void __launch_bounds__(RT_BLOCK, RT_TAIL_BLOCKS)
     k_tail(const __grid_constant__ DScene sc, const __grid_constant__ PassParams pp, float4 *__restrict__ ray_a,
            float4 *__restrict__ ray_b, float2 *__restrict__ hit, float4 *__restrict__ next_a,
-           float4 *__restrict__ next_b, float2 *__restrict__ next_hit, float4 *__restrict__ throughput,
-           float4 *__restrict__ radiance, unsigned int *__restrict__ counts, unsigned int *__restrict__ cursor,
+           float4 *__restrict__ next_b, float2 *__restrict__ next_hit, float4 *__restrict__ thr,
+           float4 *__restrict__ next_thr, float4 *__restrict__ radiance, unsigned int *__restrict__ counts,
+           unsigned int *__restrict__ cursor,
            int first_bounce, int end_bounce, int has_media, unsigned long long *stats) {
   RT_DECLARE_STACK(stack);
   const unsigned int n = counts[first_bounce];
@@ -872,7 +875,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_TAIL_BLOCKS)
       RayKey key;
       int k;
       path_to_key(pp, path, bounce, key, k);
-      float4 tp = bounce == 0 ? make_float4(1.f, 1.f, 1.f, 0.f) : throughput[path];
+      float4 tp = bounce == 0 ? make_float4(1.f, 1.f, 1.f, 0.f) : thr[q]; // the lane's own queue slot
       ShadeResult res;
       bool cont = shade_segment_call(sc, r, best, F3(tp.x, tp.y, tp.z), key, bounce + 1 >= pp.max_depth, res);
       if (cont && bounce + 1 >= end_bounce) {
@@ -882,13 +885,13 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_TAIL_BLOCKS)
         next_a[slot] = make_float4(res.next.o.x, res.next.o.y, res.next.o.z, res.next.time);
         next_b[slot] = make_float4(res.next.d.x, res.next.d.y, res.next.d.z, __int_as_float(path));
         next_hit[slot] = make_float2(0.f, __int_as_float(res.next_skip_prim));
-        throughput[path] = make_float4(res.throughput.x, res.throughput.y, res.throughput.z, 0.f);
+        next_thr[slot] = make_float4(res.throughput.x, res.throughput.y, res.throughput.z, 0.f);
         best.t = -1.0f;
       } else if (cont) {
         ray_a[q] = make_float4(res.next.o.x, res.next.o.y, res.next.o.z, res.next.time);
         ray_b[q] = make_float4(res.next.d.x, res.next.d.y, res.next.d.z, __int_as_float(path));
         hit[q] = make_float2(0.f, __int_as_float(res.next_skip_prim));
-        throughput[path] = make_float4(res.throughput.x, res.throughput.y, res.throughput.z, 0.f);
+        thr[q] = make_float4(res.throughput.x, res.throughput.y, res.throughput.z, 0.f);
         rt = make_trav(res.next.o, res.next.d);
         best.t = RT_INF_F;
         best.prim = -1;
@@ -1390,7 +1393,7 @@ void launch_shade(const rt_context *ctx, const DScene &sc, const PassParams &pp,
   int b = bounce & 1, nb = b ^ 1;
   auto kernel = gen ? k_shade<true> : k_shade<false>;
   kernel<<<need < sh.blocks ? need : sh.blocks, RT_SHADE_THREADS, 0, ctx->stream>>>(
-      sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b], w.ray_a[nb], w.ray_b[nb], w.hit[nb], w.throughput, w.radiance, w.counts,
+      sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b], w.ray_a[nb], w.ray_b[nb], w.hit[nb], w.thr[b], w.thr[nb], w.radiance, w.counts,
       bounce);
 }
 
@@ -1403,11 +1406,11 @@ void launch_tail(const rt_context *ctx, const DScene &sc, const PassParams &pp, 
   const int blocks = need < sh.blocks ? need : sh.blocks;
   if (ctx->stats)
     k_tail<true><<<blocks, RT_BLOCK, 0, ctx->stream>>>(sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b], w.ray_a[nb], w.ray_b[nb],
-                                                       w.hit[nb], w.throughput, w.radiance, w.counts, cursor, first_bounce,
+                                                       w.hit[nb], w.thr[b], w.thr[nb], w.radiance, w.counts, cursor, first_bounce,
                                                        end_bounce, sc.n_media > 0, w.stats);
   else
     k_tail<false><<<blocks, RT_BLOCK, 0, ctx->stream>>>(sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b], w.ray_a[nb], w.ray_b[nb],
-                                                        w.hit[nb], w.throughput, w.radiance, w.counts, cursor, first_bounce,
+                                                        w.hit[nb], w.thr[b], w.thr[nb], w.radiance, w.counts, cursor, first_bounce,
                                                         end_bounce, sc.n_media > 0, w.stats);
 }
 

@@ -4,12 +4,18 @@
 set -u
 tag=${1:-run}
 out=gpurun_out
+mkdir -p $out
 python bench.py > $out/bench_n1_$tag.json 2> $out/bench_n1_$tag.err || exit 1
 python bench.py --impl reference --steps 3 --warmup 3 > $out/bench_ref_$tag.json 2> $out/bench_ref_$tag.err
-python bench.py --steps 3 --warmup 3 > $out/plain_$tag.log 2>&1 || exit 1
-ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $out/launches_$tag.csv \
-  python bench.py --steps 3 --warmup 3 > $out/ncu_launches_$tag.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"k_extend|k_shade|k_tail" -s 21 -c 7 -f -o $out/prof_$tag \
-  python bench.py --steps 3 --warmup 3 > $out/ncu_full_$tag.log 2>&1
+# the profiled runs use direct launches (RT_GRAPH=0): ncu lists kernels launched through a graph as well, but the
+# per-launch skip / count arithmetic below assumes the plain launch order
+RT_GRAPH=0 python tools/frame_once.py spheres 11 1920 8 6 > $out/plain_$tag.log 2>&1 || exit 1
+RT_GRAPH=0 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $out/launches_$tag.csv \
+  python tools/frame_once.py spheres 11 1920 8 6 > $out/ncu_launches_$tag.log 2>&1
+# frame_once: 6 frames x (generate, 3 x (extend, shade), tail) + 1 resolve; capture the 7 render launches of frame 4
+RT_GRAPH=0 ncu --set full --clock-control none --import-source on -k regex:"k_extend|k_shade|k_tail" -s 21 -c 7 -f -o $out/prof_$tag \
+  python tools/frame_once.py spheres 11 1920 8 6 > $out/ncu_full_$tag.log 2>&1
 python tools/run_configs.py c1 c2 c3 c4 c5 > $out/configs_n1_$tag.json 2> $out/configs_n1_$tag.err
+python tools/audit_configs.py c1 c2 c3 c3n c4 c5 > $out/audit_$tag.json 2> $out/audit_$tag.err
+python tools/ref_gpu_frame.py spheres 11 480 8 1 > $out/refgpu_480_$tag.json 2> $out/refgpu_480_$tag.err
 tail -c 600 $out/bench_n1_$tag.json

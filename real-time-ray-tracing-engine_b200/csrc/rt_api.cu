@@ -210,7 +210,15 @@ int render_pass(rt_scene *scene, const rt_camera *camera, rt_film *film, int fir
     if (flushed != RT_OK)
       return flushed;
   }
-  int st = ensure_wave(ctx, (size_t)pp.n_paths, 2 * ((size_t)max_depth + 2)); // queue lengths + fetch cursors
+  // Sub-passes (rt_internal.h, rt_context::split): a small pass is cut into disjoint path ranges (multiples of a
+  // block of 128 paths), each with its own queues and its own block of count / cursor words, launched on forked
+  // streams.  The profiling modes bracket or count individual launches on one stream and keep the single sequence.
+  const size_t count_words = 2 * ((size_t)max_depth + 2); // queue lengths + fetch cursors of one launch sequence
+  int n_split = 1;
+  if (ctx->split > 1 && !ctx->timer.enabled && !ctx->audit && !ctx->stats && pp.n_paths >= 65536 &&
+      (int64_t)pp.n_paths <= ctx->split_max_paths)
+    n_split = std::min(ctx->split, 4);
+  int st = ensure_wave(ctx, (size_t)pp.n_paths, count_words * (size_t)n_split);
   if (st != RT_OK)
     return st;
   DScene sc = scene->d;
@@ -226,16 +234,50 @@ int render_pass(rt_scene *scene, const rt_camera *camera, rt_film *film, int fir
   const bool as_graph = ctx->use_graph && !ctx->timer.enabled && !ctx->audit;
   if (as_graph)
     RT_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-  RT_CUDA(cudaMemsetAsync(w.counts, 0, 2 * ((size_t)max_depth + 2) * sizeof(unsigned int), ctx->stream));
+  RT_CUDA(cudaMemsetAsync(w.counts, 0, count_words * (size_t)n_split * sizeof(unsigned int), ctx->stream));
   // wavefront launches while the path population is large, then one tail kernel that runs whatever is
   // left to completion (rt_kernels.cu, k_tail)
   const int wave_bounces = std::min(max_depth, wave_depth(ctx, scene));
   // The first extend launch derives the camera rays itself and queue 0 is never written (k_extend<GEN>), unless
   // something else reads queue 0: a tail-only schedule, the parity audit, RT_FUSED_GENERATE=0 (A/B aid).
   const bool fused_generate = wave_bounces >= 1 && !ctx->audit && ctx->fused_generate;
+  // the sub-passes: parameters, queue views and streams
+  PassParams sub_pp[4];
+  WaveBuffers sub_w[4];
+  cudaStream_t sub_stream[4];
+  {
+    const int blocks_total = (pp.n_paths + 127) / 128;
+    int first_block = 0;
+    for (int h = 0; h < n_split; h++) {
+      const int end_block = (int)((int64_t)blocks_total * (h + 1) / n_split);
+      const int first = first_block * 128, end = std::min(pp.n_paths, end_block * 128);
+      sub_pp[h] = pp;
+      sub_pp[h].path_base = first;
+      sub_pp[h].n_paths = end - first;
+      sub_w[h] = w;
+      for (int k = 0; k < 2; k++) {
+        sub_w[h].ray_a[k] = w.ray_a[k] + first;
+        sub_w[h].ray_b[k] = w.ray_b[k] + first;
+        sub_w[h].hit[k] = w.hit[k] + first;
+        sub_w[h].thr[k] = w.thr[k] + first;
+      }
+      sub_w[h].counts = w.counts + count_words * (size_t)h;
+      sub_stream[h] = h == 0 ? ctx->stream : ctx->side_stream[h - 1];
+      first_block = end_block;
+    }
+  }
+  if (n_split > 1) { // fork: the side streams start behind the memset (and join the capture)
+    RT_CUDA(cudaEventRecord(ctx->fork_event, ctx->stream));
+    for (int h = 1; h < n_split; h++)
+      RT_CUDA(cudaStreamWaitEvent(sub_stream[h], ctx->fork_event, 0));
+  }
+  // launches are issued stage by stage across the sub-passes, so that without a graph the streams fill evenly
   if (!fused_generate) {
     StageSpan span(ctx, RT_STAGE_GENERATE);
-    launch_generate(ctx, pp, w);
+    for (int h = 0; h < n_split; h++) {
+      ctx->pass_stream = sub_stream[h];
+      launch_generate(ctx, sub_pp[h], sub_w[h]);
+    }
   }
   for (int bounce = 0; bounce < wave_bounces; bounce++) {
     const bool gen = fused_generate && bounce == 0;
@@ -243,7 +285,10 @@ int render_pass(rt_scene *scene, const rt_camera *camera, rt_film *film, int fir
       launch_audit_trace(ctx, scene->ex, pp, w, bounce, sc.n_media > 0);
     {
       StageSpan span(ctx, RT_STAGE_EXTEND);
-      launch_extend(ctx, sc, pp, w, bounce, gen);
+      for (int h = 0; h < n_split; h++) {
+        ctx->pass_stream = sub_stream[h];
+        launch_extend(ctx, sc, sub_pp[h], sub_w[h], bounce, gen);
+      }
     }
     if (ctx->audit) {
       launch_audit_compare(ctx, pp, w, bounce, scene->leaf_id);
@@ -251,15 +296,28 @@ int render_pass(rt_scene *scene, const rt_camera *camera, rt_film *film, int fir
     }
     {
       StageSpan span(ctx, RT_STAGE_SHADE);
-      launch_shade(ctx, sc, pp, w, bounce, gen);
+      for (int h = 0; h < n_split; h++) {
+        ctx->pass_stream = sub_stream[h];
+        launch_shade(ctx, sc, sub_pp[h], sub_w[h], bounce, gen);
+      }
     }
   }
   // each tail launch covers at most tail_span bounces and queues its survivors for the next one
   int tail_launches = 0;
   for (int first = wave_bounces, buffer = wave_bounces & 1; first < max_depth; first += ctx->tail_span, buffer ^= 1) {
     StageSpan span(ctx, RT_STAGE_TAIL);
-    launch_tail(ctx, sc, pp, w, first, std::min(max_depth, first + ctx->tail_span), buffer);
+    for (int h = 0; h < n_split; h++) {
+      ctx->pass_stream = sub_stream[h];
+      launch_tail(ctx, sc, sub_pp[h], sub_w[h], first, std::min(max_depth, first + ctx->tail_span), buffer);
+    }
     tail_launches++;
+  }
+  ctx->pass_stream = ctx->stream;
+  if (n_split > 1) { // join: whatever follows on the context stream sees the whole pass
+    for (int h = 1; h < n_split; h++) {
+      RT_CUDA(cudaEventRecord(ctx->join_event[h - 1], sub_stream[h]));
+      RT_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->join_event[h - 1], 0));
+    }
   }
   // the in-order sum of a multi-sample pass: deferred to the film's next reader when the film owns its buffer
   // (nobody can look at it behind the library's back) and no per-launch timing wants the launch here
@@ -278,9 +336,12 @@ int render_pass(rt_scene *scene, const rt_camera *camera, rt_film *film, int fir
     film->pending_pass = pp;
     ctx->pending_film = film;
   }
-  ctx->counters.kernel_launches += (fused_generate ? 0 : 1) + ((pp.film_direct || defer_sum) ? 0 : 1) + 2 * (uint64_t)wave_bounces + (uint64_t)tail_launches;
+  ctx->counters.kernel_launches += ((pp.film_direct || defer_sum) ? 0 : 1) +
+                                   (uint64_t)n_split * ((fused_generate ? 0 : 1) + 2 * (uint64_t)wave_bounces + (uint64_t)tail_launches);
   ctx->counters.paths += (uint64_t)pp.n_paths;
   w.last_counts = (size_t)max_depth + 1;
+  w.last_splits = (size_t)n_split;
+  w.last_stride = count_words;
   if (as_graph) {
     cudaGraph_t graph = nullptr;
     RT_CUDA(cudaStreamEndCapture(ctx->stream, &graph));
@@ -421,7 +482,15 @@ int rt_context_create(int device, rt_context **out) {
     ctx->tail_span = std::max(1, std::atoi(env));
   if (const char *env = std::getenv("RT_PASS_PATHS"))
     ctx->pass_paths = std::max<int64_t>(1, std::atoll(env));
+  if (const char *env = std::getenv("RT_SPLIT")) // sub-passes of a small pass (1 = one launch sequence)
+    ctx->split = std::min(4, std::max(1, std::atoi(env)));
   RT_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  ctx->pass_stream = ctx->stream;
+  for (int k = 0; k < 3; k++) {
+    RT_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream[k], cudaStreamNonBlocking));
+    RT_CUDA(cudaEventCreateWithFlags(&ctx->join_event[k], cudaEventDisableTiming));
+  }
+  RT_CUDA(cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
   *out = ctx;
   return RT_OK;
 }
@@ -450,6 +519,14 @@ void rt_context_destroy(rt_context *ctx) {
     cudaGraphExecDestroy(ctx->graph_exec);
   for (cudaEvent_t e : ctx->timer.pool)
     cudaEventDestroy(e);
+  for (int k = 0; k < 3; k++) {
+    if (ctx->side_stream[k])
+      cudaStreamDestroy(ctx->side_stream[k]);
+    if (ctx->join_event[k])
+      cudaEventDestroy(ctx->join_event[k]);
+  }
+  if (ctx->fork_event)
+    cudaEventDestroy(ctx->fork_event);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -929,7 +1006,12 @@ int rt_get_queue_lengths(rt_context *ctx, uint32_t *out, int n) {
   size_t have = std::min<size_t>((size_t)n, ctx->wave.last_counts);
   if (have && ctx->wave.counts) {
     RT_CUDA(cudaStreamSynchronize(ctx->stream));
-    RT_CUDA(cudaMemcpy(out, ctx->wave.counts, have * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> part(have);
+    for (size_t h = 0; h < ctx->wave.last_splits; h++) { // a split pass: the sub-passes' queues add up
+      RT_CUDA(cudaMemcpy(part.data(), ctx->wave.counts + h * ctx->wave.last_stride, have * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      for (size_t k = 0; k < have; k++)
+        out[k] += part[k];
+    }
   }
   return RT_OK;
 }

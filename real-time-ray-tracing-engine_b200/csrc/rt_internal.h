@@ -17,7 +17,8 @@ struct PassParams {
   DCamera cam;
   DFilmMap map;
   int n_owned;      // owned pixels
-  int n_paths;      // paths of this pass
+  int n_paths;      // paths of this pass (of this sub-pass when the pass is split, rt_api.cu render_pass)
+  int path_base;    // the launch sequence covers paths path_base ... path_base + n_paths - 1 (queue 0 slot q = path path_base + q)
   int first_sample; // linear stratum index of the pass's first sample
   int n_samples;    // samples in this pass
   int sqrt_spp;
@@ -68,6 +69,8 @@ struct WaveBuffers {
   rt_audit_sample *audit_samples = nullptr;  // first RT_AUDIT_MAX_SAMPLES mismatching segments
   size_t capacity_audit = 0;
   size_t last_counts = 0; // queue-length entries the most recent pass used
+  size_t last_splits = 1; // sub-passes of the most recent pass: each has its own block of count / cursor words ...
+  size_t last_stride = 0; // ... this many words apart
   size_t capacity_paths = 0;
   size_t capacity_counts = 0;
 };
@@ -106,6 +109,14 @@ struct rt_context {
   bool defer_accumulate = true;    // multi-sample passes leave their in-order sum to the film's next reader (RT_DEFER_ACCUMULATE=0)
   rt_film *pending_film = nullptr; // the film whose pending sum lives in wave.radiance (at most one per context)
   cudaStream_t stream = nullptr;
+  // Small passes (a 1-spp frame) are cut into `split` sub-passes over disjoint path ranges, each with its own queues,
+  // submitted on forked streams (parallel branches of the pass's CUDA graph): every persistent kernel ends with its
+  // slowest rays on a mostly idle GPU, and the other sub-pass's kernels fill those SMs (rt_api.cu render_pass).
+  int split = 1;                          // RT_SPLIT (measured: no gain at 2, slower at 3-4; profiles/r02_experiments.md)
+  int64_t split_max_paths = (int64_t)4 << 20; // larger passes amortise their kernel ends: not split
+  cudaStream_t side_stream[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t fork_event = nullptr, join_event[3] = {nullptr, nullptr, nullptr};
+  cudaStream_t pass_stream = nullptr;     // the stream the render-kernel wrappers launch on (stream or a side stream)
   WaveBuffers wave;
   rt_counters counters{};
   StageTimer timer;

@@ -126,9 +126,9 @@ __global__ void __launch_bounds__(RT_BLOCK)
                unsigned int *__restrict__ counts) {
   int stride = gridDim.x * blockDim.x;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < pp.n_paths; p += stride) {
-    Ray r = path_camera_ray(pp, p);
+    Ray r = path_camera_ray(pp, pp.path_base + p);
     ray_a[p] = make_float4(r.o.x, r.o.y, r.o.z, r.time);
-    ray_b[p] = make_float4(r.d.x, r.d.y, r.d.z, __int_as_float(p));
+    ray_b[p] = make_float4(r.d.x, r.d.y, r.d.z, __int_as_float(pp.path_base + p));
     // no per-path initialisation is written: at bounce 0 the throughput is 1 and no primitive is skipped
     // (the kernels know), and every path writes its radiance exactly once when it ends
   }
@@ -226,9 +226,9 @@ __global__ void __launch_bounds__(RT_BLOCK, 8)
           q = mine;
           float4 a, b;
           if (GEN) {
-            Ray r = path_camera_ray(pp, (int)q);
+            Ray r = path_camera_ray(pp, pp.path_base + (int)q);
             a = make_float4(r.o.x, r.o.y, r.o.z, r.time);
-            b = make_float4(r.d.x, r.d.y, r.d.z, __int_as_float((int)q));
+            b = make_float4(r.d.x, r.d.y, r.d.z, __int_as_float(pp.path_base + (int)q));
           } else {
             a = ray_a[q];
             b = ray_b[q];
@@ -647,8 +647,8 @@ __global__ void __launch_bounds__(RT_SHADE_THREADS, RT_SHADE_BLOCKS * RT_BLOCK /
       Hit ht;
       ht.t = h.x;
       if (GEN) {
-        path = q;
-        r = path_camera_ray(pp, q);
+        path = pp.path_base + q;
+        r = path_camera_ray(pp, path);
         // opaque to the optimiser from here on, like the loaded ray of the other instantiation
         asm volatile("" : "+f"(r.o.x), "+f"(r.o.y), "+f"(r.o.z), "+f"(r.d.x), "+f"(r.d.y), "+f"(r.d.z), "+f"(r.time));
         ht.prim = __float_as_int(h.y);
@@ -906,6 +906,244 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_TAIL_BLOCKS)
     }
   }
   // segments traced by this warp -> stats[3]
+  for (int o = 16; o > 0; o >>= 1)
+    segments += __shfl_xor_sync(0xffffffffu, segments, o);
+  if (lane == 0 && segments)
+    atomicAdd(&stats[3], (unsigned long long)segments);
+  traversal_stats<STATS>(stats, n_nodes, n_tests);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// tail with warp-local regrouping (k_tail_regroup)
+// ---------------------------------------------------------------------------------------------------
+// k_tail couples a lane to its path: a lane whose segment is traced waits until fewer than RT_TAIL_REFILL lanes
+// are still traversing, then shades with whoever else is waiting, then re-enters traversal (ncu: 10-11 of 32 lanes
+// per instruction, the lowest of all kernels).  Here the warp owns a small POOL of paths instead:
+//   * a lane that finishes a segment drops (slot, t, primitive, bounce) into the warp's pending list in shared
+//     memory and immediately takes another ray - first from the warp's own list of scattered rays, then from the
+//     launch's queue - so the traversal loop always runs with at least RT_REFILL busy lanes while work exists;
+//   * shading runs when 32 segments are pending: a full warp of hits, whatever their bounces, at 32 of 32 lanes;
+//     the scattered rays go back to their own queue slots and onto the warp's to-trace list;
+//   * the traversal registers of the rays in flight are parked in shared memory around the shading code, so the
+//     two register-hungry phases do not add up (64 registers, the occupancy of k_extend, instead of 96).
+// A warp holds at most 32 rays in flight + 63 pending hits + the to-trace list; it only fetches from the launch's
+// queue when its to-trace list cannot fill its idle lanes, so the three together never exceed 95 paths.
+// Same segments, same Philox keys (per-path bounce index), same film sums: images are bit-identical to k_tail's.
+#ifndef RT_TAIL2_BLOCKS
+#define RT_TAIL2_BLOCKS 8
+#endif
+#ifndef RT_TAIL2_PARTIAL
+#define RT_TAIL2_PARTIAL 16 // with nothing left to fetch: shade a partial batch once this many hits are pending ...
+#endif
+#ifndef RT_TAIL2_LOW
+#define RT_TAIL2_LOW 8 // ... or when fewer lanes than this are still traversing
+#endif
+#define RT_PEND_CAP 64
+#define RT_TRAV_CAP 96
+#define RT_WARPS_PER_BLOCK (RT_BLOCK / 32)
+__shared__ int4 rt_pend_smem[RT_WARPS_PER_BLOCK][RT_PEND_CAP];
+__shared__ int2 rt_trav_smem[RT_WARPS_PER_BLOCK][RT_TRAV_CAP];
+__shared__ float4 rt_park_smem[3][RT_BLOCK];
+
+template <bool STATS>
+__global__ void __launch_bounds__(RT_BLOCK, RT_TAIL2_BLOCKS)
+    k_tail_regroup(const __grid_constant__ DScene sc, const __grid_constant__ PassParams pp, float4 *__restrict__ ray_a,
+                   float4 *__restrict__ ray_b, float2 *__restrict__ hit, float4 *__restrict__ next_a,
+                   float4 *__restrict__ next_b, float2 *__restrict__ next_hit, float4 *__restrict__ thr,
+                   float4 *__restrict__ next_thr, float4 *__restrict__ radiance, unsigned int *__restrict__ counts,
+                   unsigned int *__restrict__ cursor, int first_bounce, int end_bounce, int has_media,
+                   unsigned long long *stats) {
+  RT_DECLARE_STACK(stack);
+  const unsigned int n = counts[first_bounce];
+  const unsigned int lane = threadIdx.x & 31u;
+  const unsigned int lt_mask = (1u << lane) - 1u;
+  int4 *pend = rt_pend_smem[threadIdx.x >> 5];
+  int2 *trav = rt_trav_smem[threadIdx.x >> 5];
+
+  RayTrav rt = make_trav(F3(0.f, 0.f, 0.f), F3(1.f, 1.f, 1.f));
+  Hit best;
+  int sp = 0, ref = RT_DONE, bounce = first_bounce;
+  unsigned int q = 0, segments = 0, n_nodes = 0, n_tests = 0;
+  int n_pend = 0, n_trav = 0; // warp-uniform
+  bool exhausted = false;     // the launch's queue has no more paths to hand out
+  best.t = -1.0f;
+  best.prim = -1;
+
+  for (;;) {
+    // ---- refill: lanes without a ray take one, the warp's own scattered rays first ----
+    unsigned int idle = __ballot_sync(0xffffffffu, ref == RT_DONE);
+    if (idle && (n_trav > 0 || !exhausted)) {
+      const int n_idle = __popc(idle), rank = __popc(idle & lt_mask);
+      const int local = n_idle < n_trav ? n_idle : n_trav;
+      const int wanted = n_idle - local;
+      unsigned int base = 0;
+      if (wanted && !exhausted) {
+        int leader = __ffs(idle) - 1;
+        if ((int)lane == leader)
+          base = atomicAdd(cursor, (unsigned int)wanted);
+        base = __shfl_sync(0xffffffffu, base, leader);
+        exhausted = base + (unsigned int)wanted >= n;
+      } else {
+        base = n; // nothing to fetch
+      }
+      if (ref == RT_DONE) {
+        bool got = false;
+        if (rank < local) {
+          int2 e = trav[n_trav - 1 - rank];
+          q = (unsigned int)e.x;
+          bounce = e.y;
+          got = true;
+        } else {
+          unsigned int mine = base + (unsigned int)(rank - local);
+          if (mine < n) {
+            q = mine;
+            bounce = first_bounce;
+            got = true;
+          }
+        }
+        if (got) {
+          float4 a = ray_a[q], b = ray_b[q];
+          rt = make_trav(F3(a.x, a.y, a.z), F3(b.x, b.y, b.z));
+          best.t = RT_INF_F;
+          best.prim = -1;
+          sp = 0;
+          ref = 0;
+          segments++;
+        }
+      }
+      n_trav -= local;
+      __syncwarp();
+    }
+    unsigned int busy = __ballot_sync(0xffffffffu, ref != RT_DONE);
+
+    // ---- shade: a full warp of pending hits, or what is left when nothing else can feed the idle lanes ----
+    const bool no_source = n_trav == 0 && exhausted;
+    if (n_pend >= 32 || (n_pend > 0 && no_source && (n_pend >= RT_TAIL2_PARTIAL || __popc(busy) < RT_TAIL2_LOW))) {
+      // park the rays in flight: nothing of the traversal state stays in registers across the shading code
+      rt_park_smem[0][threadIdx.x] = make_float4(rt.inv.x, rt.inv.y, rt.inv.z, best.t);
+      rt_park_smem[1][threadIdx.x] = make_float4(rt.oi.x, rt.oi.y, rt.oi.z, __int_as_float(best.prim));
+      rt_park_smem[2][threadIdx.x] = make_float4(__int_as_float(sp), __int_as_float(ref), __uint_as_float(q), __int_as_float(bounce));
+      const int batch = n_pend < 32 ? n_pend : 32;
+      n_pend -= batch;
+      bool cont = false, to_next = false;
+      ShadeResult res;
+      unsigned int eq = 0;
+      int ebounce = 0, path = 0;
+      if ((int)lane < batch) {
+        int4 e = pend[n_pend + (int)lane];
+        eq = (unsigned int)e.x;
+        ebounce = e.w;
+        Hit h;
+        h.t = __int_as_float(e.y);
+        h.prim = e.z;
+        float4 a = ray_a[eq], b = ray_b[eq];
+        path = __float_as_int(b.w);
+        Ray r;
+        r.o = F3(a.x, a.y, a.z);
+        r.d = F3(b.x, b.y, b.z);
+        r.time = a.w;
+        RayKey key;
+        int k;
+        path_to_key(pp, path, ebounce, key, k);
+        float4 tp = ebounce == 0 ? make_float4(1.f, 1.f, 1.f, 0.f) : thr[eq];
+        cont = shade_segment(sc, r, h, F3(tp.x, tp.y, tp.z), key, ebounce + 1 >= pp.max_depth, res);
+        if (!cont)
+          path_ends(pp, radiance, path, k, res.radiance);
+        to_next = cont && ebounce + 1 >= end_bounce;
+      }
+      // survivors of the launch's last bounce are queued for the next launch (one atomic per warp)
+      unsigned int m_next = __ballot_sync(0xffffffffu, to_next);
+      if (m_next) {
+        unsigned int first = 0;
+        int leader = __ffs(m_next) - 1;
+        if ((int)lane == leader)
+          first = atomicAdd(&counts[end_bounce], (unsigned int)__popc(m_next));
+        first = __shfl_sync(0xffffffffu, first, leader);
+        if (to_next) {
+          unsigned int slot = first + (unsigned int)__popc(m_next & lt_mask);
+          next_a[slot] = make_float4(res.next.o.x, res.next.o.y, res.next.o.z, res.next.time);
+          next_b[slot] = make_float4(res.next.d.x, res.next.d.y, res.next.d.z, __int_as_float(path));
+          next_hit[slot] = make_float2(0.f, __int_as_float(res.next_skip_prim));
+          next_thr[slot] = make_float4(res.throughput.x, res.throughput.y, res.throughput.z, 0.f);
+        }
+      }
+      // the others go back to their own queue slots and onto the warp's to-trace list
+      const bool stay = cont && !to_next;
+      unsigned int m_stay = __ballot_sync(0xffffffffu, stay);
+      if (stay) {
+        ray_a[eq] = make_float4(res.next.o.x, res.next.o.y, res.next.o.z, res.next.time);
+        ray_b[eq] = make_float4(res.next.d.x, res.next.d.y, res.next.d.z, __int_as_float(path));
+        hit[eq] = make_float2(0.f, __int_as_float(res.next_skip_prim));
+        thr[eq] = make_float4(res.throughput.x, res.throughput.y, res.throughput.z, 0.f);
+        trav[n_trav + __popc(m_stay & lt_mask)] = make_int2((int)eq, ebounce + 1);
+      }
+      n_trav += __popc(m_stay);
+      __syncwarp(); // the list entries and the rays in the queue slots are visible to the lanes that take them
+      // unpark
+      float4 p0 = rt_park_smem[0][threadIdx.x], p1 = rt_park_smem[1][threadIdx.x], p2 = rt_park_smem[2][threadIdx.x];
+      MuxRay m;
+      m.inv = F3(p0.x, p0.y, p0.z);
+      m.oi = F3(p1.x, p1.y, p1.z);
+      rt = mux_trav(m);
+      best.t = p0.w;
+      best.prim = __float_as_int(p1.w);
+      sp = __float_as_int(p2.x);
+      ref = __float_as_int(p2.y);
+      q = __float_as_uint(p2.z);
+      bounce = __float_as_int(p2.w);
+      continue; // refill from the new to-trace entries
+    }
+    if (busy == 0)
+      break; // nothing in flight, nothing pending, nothing to fetch
+
+    // ---- traverse until a lane count or a list length asks for one of the steps above ----
+    for (;;) {
+      while (ref >= 0 && ref != RT_DONE) {
+        if (STATS)
+          n_nodes++;
+        if (!node_visit(sc, ref, rt, RT_T_MIN, best.t, stack, sp, ref))
+          if (!stack_pop(stack, sp, best.t, ref))
+            ref = RT_DONE;
+      }
+      if (ref < 0) {
+        float4 a = ray_a[q], b = ray_b[q];
+        Ray r;
+        r.o = F3(a.x, a.y, a.z);
+        r.d = F3(b.x, b.y, b.z);
+        r.time = a.w;
+        int skip = bounce == 0 ? -1 : __float_as_int(hit[q].y);
+        RayKey key;
+        key.seed = pp.seed;
+        key.pixel = key.sample = 0;
+        key.bounce = (uint32_t)bounce;
+        if (has_media) {
+          int k;
+          path_to_key(pp, __float_as_int(b.w), bounce, key, k);
+        }
+        do {
+          if (STATS)
+            n_tests++;
+          leaf_test(sc, ~ref, r, RT_T_MIN, best, skip, key);
+          if (!stack_pop(stack, sp, best.t, ref))
+            ref = RT_DONE;
+        } while (ref < 0);
+      }
+      // a traced segment leaves the lane at once
+      const bool finished = ref == RT_DONE && best.t != -1.0f;
+      unsigned int m_fin = __ballot_sync(0xffffffffu, finished);
+      if (finished) {
+        pend[n_pend + __popc(m_fin & lt_mask)] = make_int4((int)q, __float_as_int(best.t), best.prim, bounce);
+        best.t = -1.0f;
+      }
+      n_pend += __popc(m_fin);
+      busy = __ballot_sync(0xffffffffu, ref != RT_DONE);
+      if (busy == 0 || n_pend >= 32)
+        break;
+      if (__popc(busy) < RT_REFILL && (n_trav > 0 || !exhausted || n_pend >= RT_TAIL2_PARTIAL || __popc(busy) < RT_TAIL2_LOW))
+        break;
+    }
+    __syncwarp();
+  }
   for (int o = 16; o > 0; o >>= 1)
     segments += __shfl_xor_sync(0xffffffffu, segments, o);
   if (lane == 0 && segments)
@@ -1353,7 +1591,7 @@ void launch_collapse(cudaStream_t s, BinTree t, const BuildBox *leaf_boxes, floa
 void launch_generate(const rt_context *ctx, const PassParams &pp, WaveBuffers &w) {
   LaunchShape sh = rt_persistent_shape(ctx, RT_BLOCK, 16);
   int need = ceil_div(pp.n_paths, RT_BLOCK);
-  k_generate<<<need < sh.blocks ? need : sh.blocks, RT_BLOCK, 0, ctx->stream>>>(pp, w.ray_a[0], w.ray_b[0], w.counts);
+  k_generate<<<need < sh.blocks ? need : sh.blocks, RT_BLOCK, 0, ctx->pass_stream>>>(pp, w.ray_a[0], w.ray_b[0], w.counts);
 }
 
 void launch_extend(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int bounce, bool gen) {
@@ -1362,7 +1600,7 @@ void launch_extend(const rt_context *ctx, const DScene &sc, const PassParams &pp
   if (simple) {
     LaunchShape sh = rt_persistent_shape(ctx, RT_BLOCK, 8);
     int need = ceil_div(pp.n_paths, RT_BLOCK);
-    k_extend_simple<<<need < sh.blocks ? need : sh.blocks, RT_BLOCK, 0, ctx->stream>>>(
+    k_extend_simple<<<need < sh.blocks ? need : sh.blocks, RT_BLOCK, 0, ctx->pass_stream>>>(
         sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b], w.counts, bounce, sc.n_media > 0, w.stats);
     return;
   }
@@ -1374,7 +1612,7 @@ void launch_extend(const rt_context *ctx, const DScene &sc, const PassParams &pp
   static const bool mux = getenv("RT_EXTEND_MUX") && atoi(getenv("RT_EXTEND_MUX")) != 0;
   if (mux && !gen) {
     auto k = ctx->stats ? k_extend_mux<true> : k_extend_mux<false>;
-    k<<<blocks, RT_BLOCK, 0, ctx->stream>>>(sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b], w.counts, cursor, bounce, sc.n_media > 0,
+    k<<<blocks, RT_BLOCK, 0, ctx->pass_stream>>>(sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b], w.counts, cursor, bounce, sc.n_media > 0,
                                             w.stats);
     return;
   }
@@ -1383,7 +1621,7 @@ void launch_extend(const rt_context *ctx, const DScene &sc, const PassParams &pp
   // RT_EXTEND_DYN_SMEM=<bytes>: unused dynamic shared memory per block (experiment aid: how much the kernel
   // depends on the L1 capacity that shared memory is carved out of)
   static const size_t dyn_smem = getenv("RT_EXTEND_DYN_SMEM") ? (size_t)atol(getenv("RT_EXTEND_DYN_SMEM")) : 0;
-  kernel<<<blocks, RT_BLOCK, dyn_smem, ctx->stream>>>(sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b], w.counts, cursor, bounce,
+  kernel<<<blocks, RT_BLOCK, dyn_smem, ctx->pass_stream>>>(sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b], w.counts, cursor, bounce,
                                                       sc.n_media > 0, w.stats);
 }
 
@@ -1392,7 +1630,7 @@ void launch_shade(const rt_context *ctx, const DScene &sc, const PassParams &pp,
   int need = ceil_div(pp.n_paths, RT_SHADE_THREADS);
   int b = bounce & 1, nb = b ^ 1;
   auto kernel = gen ? k_shade<true> : k_shade<false>;
-  kernel<<<need < sh.blocks ? need : sh.blocks, RT_SHADE_THREADS, 0, ctx->stream>>>(
+  kernel<<<need < sh.blocks ? need : sh.blocks, RT_SHADE_THREADS, 0, ctx->pass_stream>>>(
       sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b], w.ray_a[nb], w.ray_b[nb], w.hit[nb], w.thr[b], w.thr[nb], w.radiance, w.counts,
       bounce);
 }
@@ -1404,12 +1642,23 @@ void launch_tail(const rt_context *ctx, const DScene &sc, const PassParams &pp, 
   int b = buffer, nb = buffer ^ 1;
   unsigned int *cursor = w.counts + (pp.max_depth + 2) + first_bounce;
   const int blocks = need < sh.blocks ? need : sh.blocks;
+  // RT_TAIL=regroup: the warp-pool variant (k_tail_regroup: bit-identical, measured slower) for A/B measurements
+  static const bool regroup = getenv("RT_TAIL") && std::string(getenv("RT_TAIL")) == "regroup";
+  if (regroup) {
+    LaunchShape sh2 = rt_persistent_shape(ctx, RT_BLOCK, RT_TAIL2_BLOCKS);
+    const int blocks2 = need < sh2.blocks ? need : sh2.blocks;
+    auto k = ctx->stats ? k_tail_regroup<true> : k_tail_regroup<false>;
+    k<<<blocks2, RT_BLOCK, 0, ctx->pass_stream>>>(sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b], w.ray_a[nb], w.ray_b[nb], w.hit[nb],
+                                             w.thr[b], w.thr[nb], w.radiance, w.counts, cursor, first_bounce, end_bounce,
+                                             sc.n_media > 0, w.stats);
+    return;
+  }
   if (ctx->stats)
-    k_tail<true><<<blocks, RT_BLOCK, 0, ctx->stream>>>(sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b], w.ray_a[nb], w.ray_b[nb],
+    k_tail<true><<<blocks, RT_BLOCK, 0, ctx->pass_stream>>>(sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b], w.ray_a[nb], w.ray_b[nb],
                                                        w.hit[nb], w.thr[b], w.thr[nb], w.radiance, w.counts, cursor, first_bounce,
                                                        end_bounce, sc.n_media > 0, w.stats);
   else
-    k_tail<false><<<blocks, RT_BLOCK, 0, ctx->stream>>>(sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b], w.ray_a[nb], w.ray_b[nb],
+    k_tail<false><<<blocks, RT_BLOCK, 0, ctx->pass_stream>>>(sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b], w.ray_a[nb], w.ray_b[nb],
                                                         w.hit[nb], w.thr[b], w.thr[nb], w.radiance, w.counts, cursor, first_bounce,
                                                         end_bounce, sc.n_media > 0, w.stats);
 }
@@ -1417,7 +1666,7 @@ void launch_tail(const rt_context *ctx, const DScene &sc, const PassParams &pp, 
 void launch_accumulate(const rt_context *ctx, const PassParams &pp, WaveBuffers &w, float4 *film) {
   LaunchShape sh = rt_persistent_shape(ctx, 256, 8);
   int need = ceil_div(pp.n_owned, 256);
-  k_accumulate<<<need < sh.blocks ? need : sh.blocks, 256, 0, ctx->stream>>>(pp, w.radiance, film);
+  k_accumulate<<<need < sh.blocks ? need : sh.blocks, 256, 0, ctx->pass_stream>>>(pp, w.radiance, film);
 }
 
 void launch_resolve_rgb8(cudaStream_t s, const float4 *film, int64_t n, double scale, uint8_t *out) {

@@ -29,6 +29,10 @@ FULL_METRICS = [
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),
     ("l1tex__t_sector_hit_rate.pct", "L1 hit rate %"),
     ("l1tex__throughput.avg.pct_of_peak_sustained_active", "L1 throughput % of peak"),
+    ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "L1 data pipe (LSU wavefronts) % of peak, over the launch"),
+    ("smsp__issue_active.avg.per_cycle_active", "issue slot busy while the SM sub-partition is active (of 1)"),
+    ("smsp__warps_eligible.avg.per_cycle_active", "eligible warps per scheduler per active cycle"),
+    ("smsp__warps_active.avg.per_cycle_active", "resident warps per scheduler"),
     ("lts__t_sector_hit_rate.pct", "L2 hit rate %"),
     ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 throughput % of peak"),
     ("dram__bytes_read.sum", "DRAM read"),
@@ -40,6 +44,9 @@ FULL_METRICS = [
     ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "stall: wait"),
     ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "stall: math pipe throttle"),
     ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "stall: barrier"),
+    ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall: short scoreboard"),
+    ("smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio", "stall: dispatch"),
+    ("smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "stall: branch resolving"),
 ]
 
 

@@ -72,8 +72,8 @@ int ensure_wave(rt_context *ctx, size_t n_paths, size_t n_counts) {
     w.capacity_counts = n_counts;
   }
   if (!w.stats) {
-    RT_CUDA(cudaMalloc((void **)&w.stats, 4 * sizeof(unsigned long long)));
-    RT_CUDA(cudaMemsetAsync(w.stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    RT_CUDA(cudaMalloc((void **)&w.stats, 8 * sizeof(unsigned long long)));
+    RT_CUDA(cudaMemsetAsync(w.stats, 0, 8 * sizeof(unsigned long long), ctx->stream));
   }
   return RT_OK;
 }
@@ -969,7 +969,7 @@ int rt_get_counters(rt_context *ctx, rt_counters *out) {
   if (!ctx || !out)
     return invalid("rt_get_counters: null argument");
   RT_CUDA(cudaSetDevice(ctx->device));
-  unsigned long long stats[4] = {0, 0, 0, 0};
+  unsigned long long stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (ctx->wave.stats) {
     RT_CUDA(cudaStreamSynchronize(ctx->stream));
     RT_CUDA(cudaMemcpy(stats, ctx->wave.stats, sizeof stats, cudaMemcpyDeviceToHost));
@@ -979,6 +979,8 @@ int rt_get_counters(rt_context *ctx, rt_counters *out) {
   out->tail_segments = stats[3];
   out->nodes_visited = stats[1]; // counted by the instrumented kernels only (rt_context_set_stats)
   out->prim_tests = stats[2];
+  if (std::getenv("RT_DEBUG_STATS")) // development aid: the longest single traversal the instrumented kernels saw
+    std::fprintf(stderr, "[rt stats] longest traversal: %llu node visits; rays above 512 node visits: %llu\n", stats[4], stats[5]);
   return RT_OK;
 }
 
@@ -1105,7 +1107,7 @@ int rt_reset_counters(rt_context *ctx) {
   RT_CUDA(cudaSetDevice(ctx->device));
   ctx->counters = rt_counters{};
   if (ctx->wave.stats)
-    RT_CUDA(cudaMemsetAsync(ctx->wave.stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    RT_CUDA(cudaMemsetAsync(ctx->wave.stats, 0, 8 * sizeof(unsigned long long), ctx->stream));
   return RT_OK;
 }
 

@@ -517,26 +517,43 @@ struct StackEntry {
 
 // Per-ray traversal constants.  The slab distances are evaluated as plane * inv - o * inv (one FMA per
 // plane); the near / far plane of every axis is picked by the direction's sign bit, which selects the
-// node row to load, so no per-axis min/max is needed.  `slack` bounds the absolute error of that form
-// (the rounding of o * inv, 2^-24 relative, enters every distance): a box is entered when
-// tnear <= tfar * (1 + 4e-7) + slack, i.e. the test can only enter more boxes than the exact one, never
-// fewer.  A zero direction component gives inf / NaN distances, which fminf / fmaxf drop (that axis
-// then does not constrain the interval: conservative as well).
+// node row to load, so no per-axis min/max is needed.
+// Why this form never rejects a box the exact test enters (u = 2^-24; checked against rational arithmetic in
+// tests/test_device_functions_host.py): with inv = (1 + d1) / d, oi = o inv (1 + d2) and the FMA's own rounding d3,
+//     computed t(plane) = (plane - o (1 + d2)) / d * (1 + d1)(1 + d3),
+// i.e. the exact distance for an origin moved by at most u |o| on that axis, times 1 +- 2u.  Every box in a node
+// is at least two ulps (4u |plane|) larger than the geometry it bounds (to_build_box, rt_flatten.h; unions keep
+// that).  If |plane| >= |o| / 4 the padding outweighs the moved origin; otherwise |plane - o| > 3/4 |o| and the
+// moved origin is a relative error below 4/3 u of the distance.  Either way both sides are off by at most
+// (1 +- 3.34u), so widening the exit distance by 1 + 10u (1.0000006f) keeps entry <= exit whenever it holds
+// exactly.  No absolute allowance is needed - an earlier version added 2.5e-7 max|o / d| to every exit distance,
+// which let a ray with one tiny direction component (|o / d| huge on that axis) enter every box of the scene.
 struct RayTrav {
-  f3 inv, oi;
-  float slack;
+  f3 inv, oi;          // 1 / d and o / d
   unsigned nx, ny, nz; // row of the near plane: x 0/1, y 2/3, z 4/5
 };
 RT_HD bool sign_bit(float f) { return f2i(f) < 0; }
-RT_HD RayTrav make_trav(f3 o, f3 d) {
+RT_HD RayTrav trav_from(f3 inv, f3 oi) {
   RayTrav t;
-  t.inv = F3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-  t.oi = F3(o.x * t.inv.x, o.y * t.inv.y, o.z * t.inv.z);
-  t.slack = 2.5e-7f * fmaxf(fabsf(t.oi.x), fmaxf(fabsf(t.oi.y), fabsf(t.oi.z)));
-  t.nx = sign_bit(d.x) ? 1 : 0;
-  t.ny = sign_bit(d.y) ? 3 : 2;
-  t.nz = sign_bit(d.z) ? 5 : 4;
+  t.inv = inv;
+  t.oi = oi;
+  t.nx = sign_bit(inv.x) ? 1 : 0; // 1 / d has the sign of d
+  t.ny = sign_bit(inv.y) ? 3 : 2;
+  t.nz = sign_bit(inv.z) ? 5 : 4;
   return t;
+}
+// A zero (or denormal, or NaN) direction component is replaced by +-1e-20 for the box tests only: the planes of that
+// axis are then 1e20 x (plane - o) away, i.e. behind or beyond everything unless the origin lies between them - what
+// a parallel ray should see - instead of inf - inf = NaN, which constrains nothing.  unit_vector_polar returns exact
+// zeros with probability ~2^-22 per draw; such a ray used to walk the whole tree (1645 nodes + 3409 primitives on the
+// final scene: 2 ms of one lane, a third of the frames).  Primitive tests use the ray's own direction.
+RT_HD float trav_component(float d) { return copysignf(fminf(fmaxf(fabsf(d), 1e-20f), 1e20f), d); }
+// 1 / d by the single-instruction reciprocal (relative error <= 2^-23 = 2u): the per-side bound of the argument
+// above becomes 1 +- (2u + u + 4/3 u), the two sides together 1 + 8.7u - still inside the 1 + 10u widening - and a
+// ray's set-up loses three IEEE divisions.  (The clamp keeps the operand and the result normal numbers.)
+RT_HD RayTrav make_trav(f3 o, f3 d) {
+  f3 inv = F3(fast_rcp(trav_component(d.x)), fast_rcp(trav_component(d.y)), fast_rcp(trav_component(d.z)));
+  return trav_from(inv, F3(o.x * inv.x, o.y * inv.y, o.z * inv.z));
 }
 RT_HD float fma_sub(float a, float b, float c) { // a * b - c in one rounding
 #if defined(__CUDA_ARCH__)
@@ -562,14 +579,14 @@ RT_HD bool node_visit(const DScene &sc, int node, const RayTrav &rt, float tmin,
   const float nx[4] = {nrx.x, nrx.y, nrx.z, nrx.w}, fx[4] = {frx.x, frx.y, frx.z, frx.w};
   const float ny[4] = {nry.x, nry.y, nry.z, nry.w}, fy[4] = {fry.x, fry.y, fry.z, fry.w};
   const float nz[4] = {nrz.x, nrz.y, nrz.z, nrz.w}, fz[4] = {frz.x, frz.y, frz.z, frz.w};
-  const float tmax_wide = tmax * 1.0000004f + rt.slack;
+  const float tmax_wide = tmax * 1.0000006f; // 1 + 10u: see RayTrav
 #pragma unroll
   for (int c = 0; c < 4; c++) {
     float tnear = fmaxf(fmaxf(fma_sub(nx[c], rt.inv.x, rt.oi.x), fma_sub(ny[c], rt.inv.y, rt.oi.y)),
                         fmaxf(fma_sub(nz[c], rt.inv.z, rt.oi.z), fmaxf(tmin, i2f(cref[c]))));
     float tfar = fminf(fminf(fma_sub(fx[c], rt.inv.x, rt.oi.x), fma_sub(fy[c], rt.inv.y, rt.oi.y)),
                        fma_sub(fz[c], rt.inv.z, rt.oi.z));
-    tfar = fminf(tfar * 1.0000004f + rt.slack, tmax_wide);
+    tfar = fminf(tfar * 1.0000006f, tmax_wide);
     tn[c] = tnear <= tfar ? tnear : RT_INF_F;
   }
   // three comparators bring the nearest child to slot 0; the others are pushed as they lie (sorting them

@@ -8,14 +8,17 @@
 #include "rt_bvh.h"
 #include "rt_device.h"
 #include "rt_exact.h"
+#include "rt_bigvec.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <limits>
 #include <mutex>
 #include <string>
 #include <thread>
+#include <utility>
 #include <vector>
 
 void rt_set_error(const std::string &msg);
@@ -144,19 +147,21 @@ inline float ibits(int i) {
 }
 
 struct Flat {
-  std::vector<float4> prims, bprims, mats, lights, perlin_grad;
+  BigVec<float4> prims, mats; // per surface / per material: written element by element by the baking threads
+  std::vector<float4> bprims, lights, perlin_grad;
   std::vector<unsigned char> perlin_perm;
   std::vector<uint32_t> texels; // image textures, 0x00BBGGRR per texel
-  std::vector<PrimExact> ex_prims, ex_bprims;
+  BigVec<PrimExact> ex_prims;
+  std::vector<PrimExact> ex_bprims;
   std::vector<XformOpExact> ops;
   std::vector<int> chain_first, chain_count;
-  std::vector<BoxD> boxes;
+  BigVec<BoxD> boxes;
 };
 
 // Spheres carry a copy of their material: the header in [2] and, when one colour is all the material needs
 // (metal, or a solid texture), that colour in [2].w, [1].w, [3].x - shading a sphere hit then takes one dependent
 // fetch (the primitive record) instead of three (record -> header -> colour).  `rec` = the 4 float4 of a record.
-inline void embed_sphere_material(float4 *rec, const std::vector<float4> &mats) {
+template <class Mats> inline void embed_sphere_material(float4 *rec, const Mats &mats) {
   uint32_t typemat = (uint32_t)f2i(rec[3].y);
   size_t m = (size_t)(typemat & 0x0fffffffu) * RT_MAT_F4;
   if ((typemat >> 28) != RT_PT_SPHERE || m + 1 >= mats.size())
@@ -320,6 +325,7 @@ inline int flatten(const rt_scene_desc *d, Flat &f) {
     for (size_t i = a; i < b; i++)
       if (sphere_slot[i] >= 0) {
         const int k = sphere_slot[i];
+        f.boxes[k] = BoxD();
         bake_sphere(bk, d->spheres[i], (int)i, d->spheres[i].material, &f.prims[(size_t)k * RT_PRIM_F4], f.ex_prims[k], f.boxes[k]);
       }
   });
@@ -327,6 +333,7 @@ inline int flatten(const rt_scene_desc *d, Flat &f) {
     for (size_t i = a; i < b; i++)
       if (quad_slot[i] >= 0) {
         const int k = quad_slot[i];
+        f.boxes[k] = BoxD();
         bake_quad(bk, d->quads[i], d->n_spheres + (int)i, d->quads[i].material, &f.prims[(size_t)k * RT_PRIM_F4], f.ex_prims[k],
                   f.boxes[k]);
       }
@@ -464,10 +471,17 @@ inline int flatten(const rt_scene_desc *d, Flat &f) {
   // Geometry the FP32 build cannot order is refused here, not rendered: a NaN / infinite coordinate, or a box
   // whose FP32 surface area overflows (|coordinate| above ~1e18), would leave the SAH sweep without a finite
   // cost and the Morton codes without a scale.
-  for (const BoxD &b : f.boxes)
-    for (int a = 0; a < 3; a++)
-      if (!(std::fabs(b.lo[a]) <= kMaxCoordinate) || !(std::fabs(b.hi[a]) <= kMaxCoordinate))
-        return fail_invalid("primitive with a non-finite or too large coordinate (|x| must stay below 1e18)");
+  {
+    std::atomic<bool> bad_box{false};
+    parallel_for(f.boxes.size(), [&](size_t lo, size_t hi) {
+      for (size_t i = lo; i < hi; i++)
+        for (int a = 0; a < 3; a++)
+          if (!(std::fabs(f.boxes[i].lo[a]) <= kMaxCoordinate) || !(std::fabs(f.boxes[i].hi[a]) <= kMaxCoordinate))
+            bad_box.store(true, std::memory_order_relaxed);
+    });
+    if (bad_box.load())
+      return fail_invalid("primitive with a non-finite or too large coordinate (|x| must stay below 1e18)");
+  }
 
   for (int i = 0; i < d->n_perlins; i++) {
     const rt_perlin &p = d->perlins[i];

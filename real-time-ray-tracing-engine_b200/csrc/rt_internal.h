@@ -3,6 +3,7 @@
 #pragma once
 
 #include "../../include/rt_b200.h"
+#include "rt_bigvec.h"
 #include "rt_bvh.h"
 #include "rt_device.h"
 #include "rt_exact.h"
@@ -141,12 +142,12 @@ struct rt_scene {
   // baked with, the current spheres, where each sphere's leaf is, and the refit links (made at the first update)
   std::vector<rt_xform> h_xforms;
   std::vector<rt_xform_op> h_xform_ops;
-  std::vector<rt_sphere> h_spheres;
-  std::vector<rt_quad> h_quads;
+  rtflat::BigVec<rt_sphere> h_spheres;
+  rtflat::BigVec<rt_quad> h_quads;
   std::vector<int> sphere_leaf, quad_leaf; // -1: boundary primitive of a medium (not a leaf of its own)
-  std::vector<float4> h_mats;
-  std::vector<PrimExact> h_ex_prims; // FP64 parity records (description order) until their first use (rt_scene_ensure_exact)
-  std::vector<uint32_t> h_order;     // leaf j holds record h_order[j]
+  rtflat::BigVec<float4> h_mats;
+  rtflat::BigVec<PrimExact> h_ex_prims; // FP64 parity records (description order) until their first use (rt_scene_ensure_exact)
+  rtflat::BigVec<uint32_t> h_order;  // leaf j holds record h_order[j]
   int *leaf_up = nullptr;            // device: per leaf, parent node * 4 + slot
   unsigned int *arrivals = nullptr;  // device: per node refit counter
 };

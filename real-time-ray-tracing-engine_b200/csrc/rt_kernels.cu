@@ -160,6 +160,14 @@ __global__ void __launch_bounds__(RT_BLOCK)
 
 // STATS: the instrumented instantiation (rt_context_set_stats) counts node visits and primitive tests; the
 // product instantiation carries no counting code.
+// STATS only: the longest single traversal ([4]) and how many rays needed more than 512 node visits ([5])
+template <bool STATS> __device__ __forceinline__ void ray_stats(unsigned long long *stats, unsigned int ray_nodes) {
+  if (STATS) {
+    atomicMax(&stats[4], (unsigned long long)ray_nodes);
+    if (ray_nodes > 512u)
+      atomicAdd(&stats[5], 1ull);
+  }
+}
 template <bool STATS>
 __device__ __forceinline__ void traversal_stats(unsigned long long *stats, unsigned int n_nodes, unsigned int n_tests) {
   if (STATS) {
@@ -206,7 +214,7 @@ __global__ void __launch_bounds__(RT_BLOCK, 8)
   RayTrav rt = make_trav(F3(0.f, 0.f, 0.f), F3(1.f, 1.f, 1.f));
   Hit best;
   int sp = 0, ref = RT_DONE;
-  unsigned int q = 0, n_nodes = 0, n_tests = 0;
+  unsigned int q = 0, n_nodes = 0, n_tests = 0, ray_nodes = 0;
   bool exhausted = false; // the queue has no more rays to hand out
   best.t = -1.0f;         // no ray held
   best.prim = -1;
@@ -242,6 +250,7 @@ __global__ void __launch_bounds__(RT_BLOCK, 8)
           best.prim = -1;
           sp = 0;
           ref = 0; // root
+          ray_nodes = 0;
         }
       }
       exhausted = base + (unsigned int)__popc(idle) >= n;
@@ -253,8 +262,10 @@ __global__ void __launch_bounds__(RT_BLOCK, 8)
     for (;;) {
       // inner nodes only
       while (ref >= 0 && ref != RT_DONE) {
-        if (STATS)
+        if (STATS) {
           n_nodes++;
+          ray_nodes++;
+        }
         if (!node_visit(sc, ref, rt, RT_T_MIN, best.t, stack, sp, ref))
           if (!stack_pop(stack, sp, best.t, ref))
             ref = RT_DONE;
@@ -292,6 +303,7 @@ __global__ void __launch_bounds__(RT_BLOCK, 8)
       }
       bool finished = ref == RT_DONE && best.t != -1.0f;
       if (finished) { // write the result once
+        ray_stats<STATS>(stats, ray_nodes);
         hit[q] = make_float2(best.t, __int_as_float(best.prim));
         best.t = -1.0f; // marks "already written / no ray held"
       }
@@ -382,14 +394,7 @@ struct MuxRay {
   unsigned int q;
 };
 __device__ __forceinline__ RayTrav mux_trav(const MuxRay &r) { // the derived parts of RayTrav are recomputed, not parked
-  RayTrav t;
-  t.inv = r.inv;
-  t.oi = r.oi;
-  t.slack = 2.5e-7f * fmaxf(fabsf(r.oi.x), fmaxf(fabsf(r.oi.y), fabsf(r.oi.z)));
-  t.nx = sign_bit(r.inv.x) ? 1 : 0; // 1 / d has the sign of d (a zero component gives +-inf with the sign of the zero)
-  t.ny = sign_bit(r.inv.y) ? 3 : 2;
-  t.nz = sign_bit(r.inv.z) ? 5 : 4;
-  return t;
+  return trav_from(r.inv, r.oi);
 }
 __device__ __forceinline__ int mux_state(int ref) { return ref == RT_DONE ? RT_SLOT_EMPTY : (ref >= 0 ? RT_SLOT_NODE : RT_SLOT_LEAF); }
 
@@ -794,7 +799,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_TAIL_BLOCKS)
   RayTrav rt = make_trav(F3(0.f, 0.f, 0.f), F3(1.f, 1.f, 1.f));
   Hit best;
   int sp = 0, ref = RT_DONE, bounce = first_bounce;
-  unsigned int q = 0, segments = 0, n_nodes = 0, n_tests = 0;
+  unsigned int q = 0, segments = 0, n_nodes = 0, n_tests = 0, ray_nodes = 0;
   bool exhausted = false;
   best.t = -1.0f; // no segment held
   best.prim = -1;
@@ -830,8 +835,10 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_TAIL_BLOCKS)
     // ---- traverse until too few lanes are still inside the tree ----
     for (;;) {
       while (ref >= 0 && ref != RT_DONE) {
-        if (STATS)
+        if (STATS) {
           n_nodes++;
+          ray_nodes++;
+        }
         if (!node_visit(sc, ref, rt, RT_T_MIN, best.t, stack, sp, ref))
           if (!stack_pop(stack, sp, best.t, ref))
             ref = RT_DONE;
@@ -866,6 +873,8 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_TAIL_BLOCKS)
 
     // ---- shade the segments whose traversal is complete ----
     if (ref == RT_DONE && best.t != -1.0f) {
+      ray_stats<STATS>(stats, ray_nodes);
+      ray_nodes = 0;
       float4 a = ray_a[q], b = ray_b[q];
       int path = __float_as_int(b.w);
       Ray r;

@@ -19,15 +19,17 @@
 
 #include <chrono>
 #include <mutex>
+#include <thread>
 
 using namespace rtflat;
 
 namespace {
 
-template <class T> int upload(T **dst, const std::vector<T> &src, size_t min_count = 1) {
+template <class T, class Vec> int upload(T **dst, const Vec &src, size_t min_count = 1) {
   size_t n = std::max(src.size(), min_count);
   RT_CUDA(cudaMalloc((void **)dst, n * sizeof(T)));
-  RT_CUDA(cudaMemset(*dst, 0, n * sizeof(T)));
+  if (src.size() < n)
+    RT_CUDA(cudaMemset(*dst, 0, n * sizeof(T)));
   if (!src.empty())
     RT_CUDA(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
   return RT_OK;
@@ -71,15 +73,45 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
   sc->n_leaf = n;
   cudaStream_t s = ctx->stream;
 
-  // everything that does not depend on leaf order
-  if ((st = upload(&sc->bprims, f.bprims)) || (st = upload(&sc->mats, f.mats)) || (st = upload(&sc->lights, f.lights)) ||
-      (st = upload(&sc->perlin_grad, f.perlin_grad)) || (st = upload(&sc->perlin_perm, f.perlin_perm)) ||
-      (st = upload(&sc->texels, f.texels)) ||
-      (st = upload(&sc->ex_bprims, f.ex_bprims)) || (st = upload(&sc->ex_ops, f.ops)) ||
-      (st = upload(&sc->ex_chain_first, f.chain_first)) || (st = upload(&sc->ex_chain_count, f.chain_count)))
-    return st;
+  // Two helper threads work beside the build (joined on every way out of this function):
+  //  * everything that does not depend on leaf order is uploaded while the host prepares the leaf boxes (a million
+  //    materials are 48 MB of pageable memory: a synchronous copy of several milliseconds);
+  //  * the host-side copies of the description that rt_scene_update_* needs later are plain memory traffic.
+  struct Helper {
+    std::thread t;
+    ~Helper() {
+      if (t.joinable())
+        t.join();
+    }
+  };
+  int side_status = RT_OK;
+  std::string side_error;
+  Helper side_upload, side_copies;
+  side_upload.t = std::thread([&]() {
+    int s2 = RT_OK;
+    if (cudaSetDevice(ctx->device) != cudaSuccess)
+      s2 = RT_ERR_CUDA;
+    else if ((s2 = upload(&sc->bprims, f.bprims)) || (s2 = upload(&sc->mats, f.mats)) || (s2 = upload(&sc->lights, f.lights)) ||
+             (s2 = upload(&sc->perlin_grad, f.perlin_grad)) || (s2 = upload(&sc->perlin_perm, f.perlin_perm)) ||
+             (s2 = upload(&sc->texels, f.texels)) || (s2 = upload(&sc->ex_bprims, f.ex_bprims)) ||
+             (s2 = upload(&sc->ex_ops, f.ops)) || (s2 = upload(&sc->ex_chain_first, f.chain_first)) ||
+             (s2 = upload(&sc->ex_chain_count, f.chain_count))) {
+    }
+    if (s2 != RT_OK)
+      side_error = rt_last_error(); // the message is thread-local: carry it over to the caller's thread
+    side_status = s2;
+  });
+  side_copies.t = std::thread([&]() {
+    sc->h_xforms.assign(desc->xforms, desc->xforms + desc->n_xforms);
+    sc->h_xform_ops.assign(desc->xform_ops, desc->xform_ops + desc->n_xform_ops);
+    sc->h_spheres.resize(desc->n_spheres);
+    parallel_for((size_t)desc->n_spheres, [&](size_t a, size_t b) { std::copy(desc->spheres + a, desc->spheres + b, sc->h_spheres.begin() + a); });
+    sc->h_quads.resize(desc->n_quads);
+    parallel_for((size_t)desc->n_quads, [&](size_t a, size_t b) { std::copy(desc->quads + a, desc->quads + b, sc->h_quads.begin() + a); });
+  });
 
-  std::vector<BuildBox> boxes(n);
+  BigVec<BuildBox> boxes;
+  boxes.resize(n);
   BoxD all, centroids;
   {
     std::mutex merge;
@@ -108,7 +140,8 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
   RT_CUDA(cudaEventCreate(&ev0));
   RT_CUDA(cudaEventCreate(&ev1));
   int n_wide = 1;
-  std::vector<uint32_t> order(n);
+  BigVec<uint32_t> order; // written as a whole by the download of the tree's leaf order
+  order.resize(n);
 
   if (n <= 1) {
     // degenerate trees: one wide node with zero or one leaf child
@@ -270,7 +303,10 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
   cudaEventDestroy(ev1);
 
   // per-leaf object / id tables in leaf order
-  std::vector<int> leaf_object(std::max(n, 1), -1), leaf_id(std::max(n, 1), -1);
+  BigVec<int> leaf_object, leaf_id;
+  leaf_object.resize(std::max(n, 1));
+  leaf_id.resize(std::max(n, 1));
+  leaf_object[0] = leaf_id[0] = -1; // the placeholder entry of an empty scene
   parallel_for((size_t)n, [&](size_t a, size_t b) {
     for (size_t j = a; j < b; j++) {
       leaf_object[j] = f.ex_prims[order[j]].object;
@@ -280,19 +316,23 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
   RT_CUDA(cudaMemcpy(sc->leaf_object, leaf_object.data(), sizeof(int) * leaf_object.size(), cudaMemcpyHostToDevice));
   RT_CUDA(cudaMemcpy(sc->leaf_id, leaf_id.data(), sizeof(int) * leaf_id.size(), cudaMemcpyHostToDevice));
 
-  // kept on the host for rt_scene_update_spheres
-  sc->h_xforms.assign(desc->xforms, desc->xforms + desc->n_xforms);
-  sc->h_xform_ops.assign(desc->xform_ops, desc->xform_ops + desc->n_xform_ops);
-  sc->h_spheres.assign(desc->spheres, desc->spheres + desc->n_spheres);
-  sc->h_mats = std::move(f.mats); // not needed by this function any more
+  // kept on the host for rt_scene_update_spheres (the description copies: side_copies above)
+  side_upload.t.join();
+  if (side_status != RT_OK) {
+    rt_set_error(side_error);
+    return side_status;
+  }
+  sc->h_mats = std::move(f.mats); // uploaded; not needed by this function any more
   // The FP64 parity records (160 B per primitive) are only read by rt_trace_rays(RT_TRACE_EXACT_F64), the parity
   // audit and primitive updates: they stay on the host until one of those asks (rt_scene_ensure_exact).
   sc->h_ex_prims = std::move(f.ex_prims); // description order; h_order[j] = record of leaf j
-  sc->h_order = order;
   {
-    std::vector<int> leaf_of_record(std::max(n, 1), -1);
-    for (int j = 0; j < n; j++)
-      leaf_of_record[order[j]] = j;
+    BigVec<int> leaf_of_record; // a permutation: every entry below n is written
+    leaf_of_record.resize(std::max(n, 1));
+    parallel_for((size_t)n, [&](size_t a, size_t b) {
+      for (size_t j = a; j < b; j++)
+        leaf_of_record[order[j]] = (int)j;
+    });
     sc->sphere_leaf.assign(desc->n_spheres, -1);
     sc->quad_leaf.assign(desc->n_quads, -1);
     int record = 0; // surface spheres are the first records, then the surface quads, in description order (rt_flatten.h)
@@ -303,7 +343,8 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
       if (!(desc->quads[i].flags & RT_PRIM_BOUNDARY))
         sc->quad_leaf[i] = leaf_of_record[record++];
   }
-  sc->h_quads.assign(desc->quads, desc->quads + desc->n_quads);
+  sc->h_order = std::move(order);
+  side_copies.t.join();
 
   sc->d.nodes = sc->nodes;
   sc->d.prims = sc->prims;
@@ -363,8 +404,8 @@ int rt_scene_ensure_exact(rt_scene *sc) {
       return rt_cuda_fail(e, "rt_scene_ensure_exact");
   }
   sc->ex.prims = sc->ex_prims;
-  std::vector<PrimExact>().swap(sc->h_ex_prims); // the device copy is the master from here on
-  std::vector<uint32_t>().swap(sc->h_order);
+  BigVec<PrimExact>().swap(sc->h_ex_prims); // the device copy is the master from here on
+  BigVec<uint32_t>().swap(sc->h_order);
   return RT_OK;
 }
 

@@ -479,7 +479,10 @@ int emu_path_map(int width, int height, int rank, int n_ranks, int tile_rows, in
 }
 
 // The FP32 slab test of node_visit (rt_device.h) on one box: returns 1 when the box would be entered.
-int emu_box_test(const float *lo, const float *hi, const float *o, const float *d, float tmin, float tmax) {
+// bias[a] = -1 / 0 / +1 moves 1 / d of axis a by that many ulps off the host's correctly rounded quotient: the device
+// takes the reciprocal with one instruction (error <= 2^-23 relative), and the guarantee has to hold for that too.
+int emu_box_test_biased(const float *lo, const float *hi, const float *o, const float *d, float tmin, float tmax,
+                        const int *bias) {
   float4 node[RT_NODE_F4];
   const float inf = RT_INF_F;
   for (int a = 0; a < 3; a++) {
@@ -491,9 +494,19 @@ int emu_box_test(const float *lo, const float *hi, const float *o, const float *
   DScene sc{};
   sc.nodes = node;
   RayTrav rt = make_trav(F3(o[0], o[1], o[2]), F3(d[0], d[1], d[2]));
+  if (bias) {
+    float inv[3] = {rt.inv.x, rt.inv.y, rt.inv.z};
+    for (int a = 0; a < 3; a++)
+      for (int k = 0; k < (bias[a] < 0 ? -bias[a] : bias[a]); k++)
+        inv[a] = std::nextafterf(inv[a], bias[a] < 0 ? -inf : inf);
+    rt = trav_from(F3(inv[0], inv[1], inv[2]), F3(o[0] * inv[0], o[1] * inv[1], o[2] * inv[2]));
+  }
   LocalStack stack;
   int sp = 0, next = 0;
   return node_visit(sc, 0, rt, tmin, tmax, stack, sp, next) ? 1 : 0;
+}
+int emu_box_test(const float *lo, const float *hi, const float *o, const float *d, float tmin, float tmax) {
+  return emu_box_test_biased(lo, hi, o, d, tmin, tmax, nullptr);
 }
 
 // sphere_hit (rt_device.h) on one static sphere: returns 1 and *t on a hit

@@ -338,12 +338,15 @@ def test_path_numbering_is_a_bijection(emu, width, height, n_ranks, tile_rows):
 
 def test_fp32_slab_test_never_rejects_a_box_the_exact_test_enters(emu):
     """node_visit's slab test (FP32, fused multiply-adds, precomputed o/d) may enter boxes the exact test would
-    skip, never the other way round - otherwise the fast traversal could lose hits.  Checked against the slab test
-    in exact rational arithmetic on the same FP32 inputs, over magnitudes from 1e-3 to 1e6, axis-parallel and
-    grazing rays, origins inside, on and far outside the box."""
+    skip, never the other way round - otherwise the fast traversal could lose hits.  The guarantee of the pipeline:
+    every box stored in a node is the geometry's box moved two ulps outwards (to_build_box), and the FP32 test on the
+    STORED box enters whenever the slab test in exact rational arithmetic enters the geometry's box - over magnitudes
+    from 1e-3 to 1e6, axis-parallel and grazing rays, tiny direction components, origins inside, on and far outside
+    the box.  (No absolute allowance: see RayTrav in rt_device.h for the argument.)"""
     from fractions import Fraction
 
     emu.emu_box_test.argtypes = [C.POINTER(C.c_float)] * 4 + [C.c_float, C.c_float]
+    emu.emu_box_test_biased.argtypes = [C.POINTER(C.c_float)] * 4 + [C.c_float, C.c_float, C.POINTER(C.c_int)]
     rng = np.random.default_rng(17)
 
     def exact_accepts(lo, hi, o, d, tmin, tmax):
@@ -362,12 +365,12 @@ def test_fp32_slab_test_never_rejects_a_box_the_exact_test_enters(emu):
 
     rejected_but_exact = 0
     entered = exact = 0
-    for trial in range(6000):
+    for trial in range(24000):
         scale = np.float32(10.0 ** rng.uniform(-3, 6))
         centre = (rng.uniform(-1, 1, 3) * scale).astype(np.float32)
         half = (rng.uniform(1e-3, 1, 3) * scale * 10.0 ** rng.uniform(-3, 0)).astype(np.float32)
         lo, hi = (centre - half).astype(np.float32), (centre + half).astype(np.float32)
-        kind = trial % 5
+        kind = trial % 6
         if kind == 0:    # origin far away, aimed at a point of the box surface (grazing / corner hits)
             target = np.where(rng.random(3) < 0.5, lo, hi).astype(np.float32)
             o = (centre + rng.normal(size=3) * scale * 10.0 ** rng.uniform(0, 3)).astype(np.float32)
@@ -385,18 +388,35 @@ def test_fp32_slab_test_never_rejects_a_box_the_exact_test_enters(emu):
         elif kind == 3:  # tiny direction components
             o = (centre + rng.normal(size=3) * scale * 5).astype(np.float32)
             d = (rng.normal(size=3) * 10.0 ** rng.uniform(-12, 0, 3)).astype(np.float32)
+        elif kind == 4:  # skimming: aimed into the box, but on one axis the origin sits within a few ulps of a face
+            a = int(rng.integers(0, 3))  # plane and moves along that axis by next to nothing (|o / d| astronomically large)
+            o = (centre + rng.normal(size=3) * scale * 10.0 ** rng.uniform(0, 2)).astype(np.float32)
+            d = ((lo + (hi - lo) * rng.random(3)).astype(np.float64) - o.astype(np.float64)).astype(np.float32)
+            face = lo[a] if rng.random() < 0.5 else hi[a]
+            for _ in range(int(rng.integers(0, 4))):
+                face = np.nextafter(face, np.float32(rng.choice([-np.inf, np.inf])))
+            o[a] = face
+            d[a] = np.float32(rng.choice([-1.0, 1.0]) * 10.0 ** rng.uniform(-38, -3)) if rng.random() < 0.8 else np.float32(0.0)
         else:            # generic
             o = (centre + rng.normal(size=3) * scale * 5).astype(np.float32)
             d = (centre.astype(np.float64) + rng.normal(size=3) * half * 1.5 - o).astype(np.float32)
         if not np.any(d != 0):
             continue
         tmin, tmax = np.float32(0.001), np.float32(np.inf if trial % 3 else 10.0 ** rng.uniform(-2, 7))
-        fast = emu.emu_box_test(lo.ctypes.data_as(C.POINTER(C.c_float)), hi.ctypes.data_as(C.POINTER(C.c_float)),
+        lo_s, hi_s = lo.copy(), hi.copy()  # the stored box: two ulps outwards, as to_build_box makes it
+        for _ in range(2):
+            lo_s, hi_s = np.nextafter(lo_s, np.float32(-np.inf)), np.nextafter(hi_s, np.float32(np.inf))
+        fast = emu.emu_box_test(lo_s.ctypes.data_as(C.POINTER(C.c_float)), hi_s.ctypes.data_as(C.POINTER(C.c_float)),
                                 o.ctypes.data_as(C.POINTER(C.c_float)), d.ctypes.data_as(C.POINTER(C.c_float)), tmin, tmax)
+        # the device's one-instruction reciprocal may be an ulp off the correctly rounded 1 / d, either way, per axis
+        bias = (C.c_int * 3)(*[int(b) for b in rng.integers(-1, 2, 3)])
+        fast_biased = emu.emu_box_test_biased(lo_s.ctypes.data_as(C.POINTER(C.c_float)), hi_s.ctypes.data_as(C.POINTER(C.c_float)),
+                                              o.ctypes.data_as(C.POINTER(C.c_float)), d.ctypes.data_as(C.POINTER(C.c_float)),
+                                              tmin, tmax, bias)
         want = exact_accepts(lo, hi, o, d, tmin, tmax)
         entered += fast
         exact += want
-        if want and not fast:
+        if want and not (fast and fast_biased):
             rejected_but_exact += 1
     assert rejected_but_exact == 0
     assert exact > 1500 and entered >= exact  # the cases do exercise both outcomes
@@ -506,3 +526,34 @@ def test_fp32_quad_test_against_exact_arithmetic(emu):
             assert hit == 0, (trial, size, al, be)
             outside += 1
     assert inside == 1500 and outside == 1500
+
+
+def test_axis_parallel_rays_do_not_walk_the_whole_tree(emu, host_scenes):
+    """A direction with exactly zero components (unit_vector_polar returns them with probability ~2^-22 per draw) makes
+    o / d infinite on that axis.  The slab test has no absolute allowance and make_trav keeps |d| >= 1e-20 for the
+    box tests, so such a ray sees the boxes an almost-parallel ray sees - it once entered EVERY box (1645 nodes, 3409
+    primitive tests on this scene, 2 ms of one GPU lane) - and still finds the FP64 traversal's primitive."""
+    emu.emu_stats.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int]
+    hs = host_scenes("final", 20, 1000)
+    es = emu.emu_scene_create(hs.desc)
+    n_nodes = emu.emu_scene_nodes(es)
+    assert n_nodes > 1000
+    cases = [((478, 278, -600), (0, 0, 1)), ((478, 278, -600), (0, 0.6, 0.8)), ((478, 278, -600), (1e-30, 0, 1)),
+             ((478, 278, -600), (-0.0, 0.001, 1)), ((3000, 300, 200), (-1, 0.0, 0.0)), ((278, 554, 279.5), (0, -1, 0)),
+             ((278, 1000, 279.5), (0, -1, 0)), ((123.4, 2000, 77.7), (0, -1, 0)), ((0.5, 0.25, -900), (0, 0, 1))]
+    for o, d in cases:
+        ray = (abi.rt_ray * 1)()
+        for k in range(3):
+            ray[0].origin[k], ray[0].direction[k] = o[k], d[k]
+        ray[0].time, ray[0].t_min, ray[0].t_max = 0.5, 0.001, float("inf")
+        fast, exact = (abi.rt_hit * 1)(), (abi.rt_hit * 1)()
+        a, b = C.c_uint64(), C.c_uint64()
+        emu.emu_stats(C.byref(a), C.byref(b), 1)
+        emu.emu_trace(es, ray, 1, abi.RT_TRACE_FAST_F32, 1, fast)
+        emu.emu_stats(C.byref(a), C.byref(b), 1)
+        emu.emu_trace(es, ray, 1, abi.RT_TRACE_EXACT_F64, 1, exact)
+        assert a.value <= 40 and b.value <= 20, (o, d, a.value, b.value)
+        assert (fast[0].prim >= 0) == (exact[0].prim >= 0), (o, d)
+        if exact[0].prim >= 0:  # coincident faces of neighbouring floor boxes tie: the distance decides
+            assert abs(fast[0].t - exact[0].t) <= 1e-5 * exact[0].t, (o, d)
+    emu.emu_scene_destroy(es)

@@ -344,18 +344,35 @@ RT_HD float2 ldg2_now(const float2 *p) {
 // Sphere::hit (Sphere.cpp:101-143): roots (h -+ sqrt(disc)) / a on the open interval (tmin, tmax).
 // The discriminant is evaluated as a * (r^2 - |oc - (h/a) d|^2), which is the same quantity as
 // h^2 - a c without the catastrophic cancellation of c = |oc|^2 - r^2 in FP32 (radius-1000 ground).
+#ifndef RT_FAST_PRIM
+#define RT_FAST_PRIM 1
+#endif
+// 1 / x and sqrt of the primitive tests: the reciprocal instruction + one Newton step (<= 1 ulp) and the approximate
+// square root (<= 2 ulp) instead of the IEEE sequences (~10 instructions each, 1.7 times per segment).  Measured on
+// B200 (profiles/r02_experiments.md): frames 1.3-1.9 % faster, and the FP32-vs-FP64 primitive mismatch audit of every
+// BASELINE config counts the same mismatches as with the IEEE operations (RT_FAST_PRIM=0 keeps those).
+// FAST = false (the light-sampling pdf in the shading code, which calls the same tests once per light): IEEE operations.
+template <bool FAST> RT_HD float prim_rcp(float a) {
+  if (FAST) {
+    float r = fast_rcp(a);
+    return fmaf(fmaf(-a, r, 1.0f), r, r);
+  }
+  return 1.0f / a;
+}
+template <bool FAST> RT_HD float prim_sqrt(float x) { return FAST ? fast_sqrt(x) : sqrtf(x); }
+template <bool FAST = (RT_FAST_PRIM != 0)>
 RT_HD bool sphere_hit(float4 r0, float4 r1, const Ray &ray, float tmin, float tmax, float &t_out) {
   f3 center = F3(r0.x, r0.y, r0.z) + ray.time * F3(r1.x, r1.y, r1.z);
   float radius = r0.w;
   f3 oc = center - ray.o;
   float a = dot(ray.d, ray.d);
   float h = dot(ray.d, oc);
-  float inv_a = 1.0f / a;
+  float inv_a = prim_rcp<FAST>(a);
   f3 perp = oc - (h * inv_a) * ray.d;
   float disc = a * (radius * radius - dot(perp, perp));
   if (disc < 0.f)
     return false;
-  float sq = sqrtf(disc);
+  float sq = prim_sqrt<FAST>(disc);
   float root = (h - sq) * inv_a;
   if (!(tmin < root && root < tmax)) {
     root = (h + sq) * inv_a;
@@ -380,10 +397,10 @@ RT_HD bool sphere_hit_from_surface(float4 r0, float4 r1, const Ray &ray, float t
   if (!(h > 0.f))
     return false;
   float a = dot(ray.d, ray.d);
-  float inv_a = 1.0f / a;
+  float inv_a = prim_rcp<RT_FAST_PRIM != 0>(a);
   f3 perp = oc - (h * inv_a) * ray.d;
   float disc = a * (radius * radius - dot(perp, perp));
-  float root = (h + sqrtf(fmaxf(disc, 0.f))) * inv_a; // on the surface |perp| <= radius up to rounding
+  float root = (h + prim_sqrt<RT_FAST_PRIM != 0>(fmaxf(disc, 0.f))) * inv_a; // on the surface |perp| <= radius up to rounding
   if (!(tmin < root && root < tmax))
     return false;
   t_out = root;
@@ -391,6 +408,7 @@ RT_HD bool sphere_hit_from_surface(float4 r0, float4 r1, const Ray &ray, float t
 }
 
 // Plane::hit (Plane.cpp:78-112): closed interval on t and on the planar coordinates.
+template <bool FAST = (RT_FAST_PRIM != 0)>
 RT_HD bool quad_hit(float4 r0, float4 r1, float4 r2, float qz, const Ray &ray, float tmin, float tmax,
                     float &t_out) {
   f3 n = F3(r0.x, r0.y, r0.z);
@@ -398,7 +416,8 @@ RT_HD bool quad_hit(float4 r0, float4 r1, float4 r2, float qz, const Ray &ray, f
   float denom = dot(n, ray.d);
   if (fabsf(denom) < 1e-8f)
     return false;
-  float t = dot(n, q - ray.o) / denom; // (D - n.o) / denom with the subtraction done on the point
+  // (D - n.o) / denom with the subtraction done on the point
+  float t = FAST ? dot(n, q - ray.o) * prim_rcp<true>(denom) : dot(n, q - ray.o) / denom;
   if (!(tmin <= t && t <= tmax))
     return false;
   f3 hp = (ray.o - q) + t * ray.d;
@@ -480,15 +499,26 @@ RT_HD void leaf_test(const DScene &sc, int prim, const Ray &ray, float tmin, Hit
                      const RayKey &key) {
   RT_STAT_LEAF();
   const float4 *rec = sc.prims + (size_t)prim * RT_PRIM_F4;
+#ifndef RT_LEAF_EARLY_LOAD
+#define RT_LEAF_EARLY_LOAD 1
+#endif
   float4 r0 = ldg4(rec), r3 = ldg4(rec + 3);
+#if RT_LEAF_EARLY_LOAD
+  float4 r1 = ldg4(rec + 1); // spheres and quads both read it: issued with the other two instead of behind the type test
+#endif
   int type = (uint32_t)f2i(r3.y) >> 28;
   float t;
   bool ok;
   if (type == RT_PT_SPHERE) {
+#if !RT_LEAF_EARLY_LOAD
     float4 r1 = ldg4(rec + 1);
+#endif
     ok = prim == start_prim ? sphere_hit_from_surface(r0, r1, ray, tmin, hit.t, t) : sphere_hit(r0, r1, ray, tmin, hit.t, t);
   } else if (type == RT_PT_QUAD) {
-    ok = prim != start_prim && quad_hit(r0, ldg4(rec + 1), ldg4(rec + 2), r3.x, ray, tmin, hit.t, t);
+#if !RT_LEAF_EARLY_LOAD
+    float4 r1 = ldg4(rec + 1);
+#endif
+    ok = prim != start_prim && quad_hit(r0, r1, ldg4(rec + 2), r3.x, ray, tmin, hit.t, t);
   } else {
     Uniform4 u = philox_uniform4(key.seed, key.pixel, key.sample, key.bounce,
                                  (uint32_t)(RT_STREAM_MEDIUM0 + f2i(r0.w)), 0);
@@ -827,7 +857,7 @@ RT_HD float light_pdf_value(const float4 *l, f3 origin, f3 dir) {
     float4 q1 = make_float4(l4.x, l4.y, l4.z, l0.x);
     float4 q2 = make_float4(l5.x, l5.y, l5.z, l0.y);
     (void)l2;
-    if (!quad_hit(q0, q1, q2, l0.z, r, RT_T_MIN, RT_INF_F, t))
+    if (!quad_hit<false>(q0, q1, q2, l0.z, r, RT_T_MIN, RT_INF_F, t))
       return 0.f;
     float dd = dot(dir, dir);
     float distance_squared = t * t * dd;
@@ -837,7 +867,7 @@ RT_HD float light_pdf_value(const float4 *l, f3 origin, f3 dir) {
   // Sphere::pdf_value (Sphere.cpp:145-159)
   float4 s0 = make_float4(l0.x, l0.y, l0.z, l1.x);
   float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (!sphere_hit(s0, s1, r, RT_T_MIN, RT_INF_F, t))
+  if (!sphere_hit<false>(s0, s1, r, RT_T_MIN, RT_INF_F, t))
     return 0.f;
   f3 oc = F3(l0) - origin;
   float cos_theta_max = fast_sqrt(fmaxf(0.f, 1.f - l1.x * l1.x * fast_rcp(dot(oc, oc))));

@@ -659,15 +659,15 @@ def rmse_leg(ctx):
 
 def gpu_reference_leg(our_frame_ms):
     """The reference's OWN GPU path (its .cu kernels compiled unmodified for sm_100, oracle/_ref_gpu) on the benchmark
-    frame, on this GPU, in processes of its own (tools/ref_gpu_frame.py): the -b configuration first, the list world
-    if that faults; per configuration one whole-frame launch of its kernel and its per-tile launch loop
-    (DynamicCamera.cpp:458-554).  Informational: the headline ratio stays the driver's, against the CPU arm."""
+    frame, on this GPU, in a process of its own (tools/ref_gpu_frame.py): the list world (its -b configuration faults
+    on this scene, profiles/r02_reference_gpu.md, and is not launched here), one whole-frame launch of its kernel.
+    Informational: the headline ratio stays the driver's, against the CPU arm."""
     import subprocess
 
     try:
         # whole-frame launch only: the reference's per-tile launch loop takes 44 s per 1080p frame (profiles/r02_reference_gpu.md)
         r = subprocess.run([sys.executable, os.path.join(REPO, "tools", "ref_gpu_frame.py"), SCENE, "11", str(WIDTH), str(DEPTH), "1",
-                            "--whole-frame-only"],
+                            "--whole-frame-only", "--list-world-only"],  # a bench run launches no kernel known to fault
                            capture_output=True, text=True, timeout=900)
         lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
         out = json.loads(lines[-1]) if lines else {"error": (r.stderr or "no output")[-300:]}

@@ -12,9 +12,9 @@ from rt_b200 import abi, distributed, engine
 pytestmark = pytest.mark.gpu
 
 # FP32 product path vs the FP64 parity traversal of the same ray (rt_context_set_audit): fraction of segments that
-# name a different primitive.  Bounds = 2 x the largest rate measured at the BASELINE sizes (profiles/r02_audit.md).
-AUDIT_MISMATCH_BOUND = 2e-3
-AUDIT_PRIMARY_BOUND = 2e-3
+# name a different primitive.  Bounds = a few times the largest rate measured at the BASELINE sizes.
+AUDIT_MISMATCH_BOUND = 2e-5  # measured at size (profiles/r02_audit.json): 0 ... 4.8e-6 of all segments,
+AUDIT_PRIMARY_BOUND = 1e-5   # 0 ... 1.9e-6 of the primary rays; these sizes are small, so 3 / 1 mismatches are allowed
 
 SCENES = [("spheres", 11, -1, 96), ("spheres", 40, -1, 64), ("spheres_textured", 12, -1, 64), ("cornell", 0, -1, 48),
           ("cornell_smoke", 0, -1, 48), ("final", 5, 60, 64)]
@@ -586,7 +586,7 @@ def test_parity_audit_and_traversal_counters(ctx, host_scenes, name, p0, width, 
     assert a.segments == c1.segments and a.primary_segments == cam.image_width * cam.image_height
     assert c1.tail_segments == 0  # the audit runs every bounce as a wavefront launch
     assert abs(int(c1.segments) - int(c0.segments)) <= 2e-3 * c0.segments
-    assert a.prim_mismatch <= AUDIT_MISMATCH_BOUND * a.segments, (a.prim_mismatch, a.segments)
+    assert a.prim_mismatch <= max(3, AUDIT_MISMATCH_BOUND * a.segments), (a.prim_mismatch, a.segments)
     assert a.primary_mismatch <= max(1, AUDIT_PRIMARY_BOUND * a.primary_segments), (a.primary_mismatch, a.primary_segments)
     assert a.hit_miss_flips <= a.prim_mismatch
     samples = ctx.audit_samples()

@@ -91,6 +91,20 @@ def launches(csv_path, out_path, command):
         tot = sum(render.values())
         out += ["", "Shares of the render kernels in that frame: " +
                 ", ".join(f"{k} {100 * v / tot:.1f}%" for k, v in render.items()) + "."]
+    # bench.py's steps: generate, 3 x (extend, shade), tail, present - every occurrence of that launch sequence
+    pattern = ["k_generate", "k_extend", "k_shade", "k_extend", "k_shade", "k_extend", "k_shade", "k_tail", "k_present_rgb8"]
+    names = [k for k, _ in order]
+    steps = [order[i:i + len(pattern)] for i in range(len(order) - len(pattern) + 1) if names[i:i + len(pattern)] == pattern]
+    if steps:
+        med = [sorted(st[j][1] for st in steps)[len(steps) // 2] for j in range(len(pattern))]
+        tot = sum(med)
+        agg = collections.OrderedDict()
+        for k, us in zip(pattern, med):
+            agg[k] = agg.get(k, 0.0) + us
+        out += ["", f"The benchmark step (C2 frame + present) occurs {len(steps)} times in the list; median per launch (us):", "", "```",
+                " ".join(f"{k.replace('k_', '')}:{us:.0f}" for k, us in zip(pattern, med)), "```", "",
+                f"Shares of the step's {tot:.0f} us (serialised, cold caches): " +
+                ", ".join(f"{k} {100 * v / tot:.1f}%" for k, v in agg.items()) + "."]
     open(out_path, "w").write("\n".join(out) + "\n")
     print("wrote", out_path)
 

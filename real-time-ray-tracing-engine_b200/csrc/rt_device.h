@@ -561,6 +561,9 @@ struct StackEntry {
 struct RayTrav {
   f3 inv, oi;          // 1 / d and o / d
   unsigned nx, ny, nz; // row of the near plane: x 0/1, y 2/3, z 4/5
+  unsigned fxr, fyr, fzr; // row of the far plane = near row ^ 1, kept by node_visit<.., true> (k_extend: three registers
+                          // for three XORs per visit, extend -2.2 ... -3.6 %; k_tail has no registers to spare and
+                          // recomputes them - the members are dead there)
 };
 RT_HD bool sign_bit(float f) { return f2i(f) < 0; }
 RT_HD RayTrav trav_from(f3 inv, f3 oi) {
@@ -570,6 +573,9 @@ RT_HD RayTrav trav_from(f3 inv, f3 oi) {
   t.nx = sign_bit(inv.x) ? 1 : 0; // 1 / d has the sign of d
   t.ny = sign_bit(inv.y) ? 3 : 2;
   t.nz = sign_bit(inv.z) ? 5 : 4;
+  t.fxr = t.nx ^ 1u;
+  t.fyr = t.ny ^ 1u;
+  t.fzr = t.nz ^ 1u;
   return t;
 }
 // A zero (or denormal, or NaN) direction component is replaced by +-1e-20 for the box tests only: the planes of that
@@ -595,15 +601,17 @@ RT_HD float fma_sub(float a, float b, float c) { // a * b - c in one rounding
 
 // Visits inner node `node`: tests its four child boxes, returns the nearest hit child in `next` (false
 // when no child is hit) and pushes the other hit children.
-template <class Stack>
+template <class Stack, bool FAR_ROW_REGS = false>
 RT_HD bool node_visit(const DScene &sc, int node, const RayTrav &rt, float tmin, float tmax, Stack &stack, int &sp,
                       int &next) {
   RT_STAT_NODE();
   // rows are addressed with one 32-bit index each (node * 8 + row): a single wide multiply-add per load
   const unsigned n = (unsigned)node * RT_NODE_F4;
-  float4 nrx = ldg4(sc.nodes + (n + rt.nx)), frx = ldg4(sc.nodes + (n + (rt.nx ^ 1u))),
-         nry = ldg4(sc.nodes + (n + rt.ny)), fry = ldg4(sc.nodes + (n + (rt.ny ^ 1u))),
-         nrz = ldg4(sc.nodes + (n + rt.nz)), frz = ldg4(sc.nodes + (n + (rt.nz ^ 1u))), cr = ldg4(sc.nodes + (n + 6u));
+  const unsigned fxr = FAR_ROW_REGS ? rt.fxr : rt.nx ^ 1u, fyr = FAR_ROW_REGS ? rt.fyr : rt.ny ^ 1u,
+                 fzr = FAR_ROW_REGS ? rt.fzr : rt.nz ^ 1u;
+  float4 nrx = ldg4(sc.nodes + (n + rt.nx)), frx = ldg4(sc.nodes + (n + fxr)),
+         nry = ldg4(sc.nodes + (n + rt.ny)), fry = ldg4(sc.nodes + (n + fyr)),
+         nrz = ldg4(sc.nodes + (n + rt.nz)), frz = ldg4(sc.nodes + (n + fzr)), cr = ldg4(sc.nodes + (n + 6u));
   float tn[4];
   int cref[4] = {f2i(cr.x), f2i(cr.y), f2i(cr.z), f2i(cr.w)};
   const float nx[4] = {nrx.x, nrx.y, nrx.z, nrx.w}, fx[4] = {frx.x, frx.y, frx.z, frx.w};

@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(RT_BLOCK, 8)
           n_nodes++;
           ray_nodes++;
         }
-        if (!node_visit(sc, ref, rt, RT_T_MIN, best.t, stack, sp, ref))
+        if (!node_visit<SmemStack, true>(sc, ref, rt, RT_T_MIN, best.t, stack, sp, ref))
           if (!stack_pop(stack, sp, best.t, ref))
             ref = RT_DONE;
       }

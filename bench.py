@@ -311,7 +311,7 @@ def run_ours(args):
     def device_step(s):
         flush_only(s)
         render_step(s)
-        present_on_device(frames[0])
+        present_on_device(frames[s & 1])
 
     def timed(n_steps):
         """Device time of n_steps steps on the context stream (ms per step, max over ranks).  Every step is
@@ -323,8 +323,8 @@ def run_ours(args):
             flush_only(s)
             e0.record(stream)
             render_step(s)
-            present_on_device(frames[0])
-            e1.record(stream)
+            present_on_device(frames[s & 1])  # two displayed frames alternate (double buffering): a rank can present
+            e1.record(stream)                 # frame s+1 while the owner is still consuming frame s
         barrier()
         return all_max(sum(e0.elapsed_time(e1) for e0, e1 in pairs) / n_steps)
 

@@ -320,6 +320,22 @@ RT_HD float4 ldg4(const float4 *p) {
   return *p;
 #endif
 }
+// Two adjacent 16-byte rows (32-byte aligned) in one 256-bit load (sm_100: LDG.E.256).
+struct F8 {
+  float4 a, b;
+};
+RT_HD F8 ldg8(const float4 *p) {
+  F8 v;
+#if defined(__CUDA_ARCH__)
+  asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=f"(v.a.x), "=f"(v.a.y), "=f"(v.a.z), "=f"(v.a.w), "=f"(v.b.x), "=f"(v.b.y), "=f"(v.b.z), "=f"(v.b.w)
+      : "l"(p));
+#else
+  v.a = p[0];
+  v.b = p[1];
+#endif
+  return v;
+}
 // Read-only loads the compiler may not move: issued where they are written, so that independent fetches of
 // a latency-bound kernel go out together instead of being sunk below the first branch that uses one of them.
 RT_HD float4 ldg4_now(const float4 *p) {
@@ -601,17 +617,33 @@ RT_HD float fma_sub(float a, float b, float c) { // a * b - c in one rounding
 
 // Visits inner node `node`: tests its four child boxes, returns the nearest hit child in `next` (false
 // when no child is hit) and pushes the other hit children.
+#ifndef RT_LOAD256
+#define RT_LOAD256 0 // measured slower (extend +7.5 % on C2): see below and profiles/r02_experiments.md
+#endif
 template <class Stack, bool FAR_ROW_REGS = false>
 RT_HD bool node_visit(const DScene &sc, int node, const RayTrav &rt, float tmin, float tmax, Stack &stack, int &sp,
                       int &next) {
   RT_STAT_NODE();
   // rows are addressed with one 32-bit index each (node * 8 + row): a single wide multiply-add per load
   const unsigned n = (unsigned)node * RT_NODE_F4;
+#if RT_LOAD256
+  // experiment: the lo / hi rows of an axis share a 32-byte sector - one 256-bit load per axis (sm_100's LDG.E.256)
+  // and one address computation per node instead of two 128-bit loads picked by the sign, the near / far planes then
+  // selected in registers (24 FSEL).  4 L1 requests per visit instead of 7 - and 7.5 % slower: the L1 data pipe is
+  // not what holds the kernel back, the instruction count (+17 per visit) is
+  const float4 *np = sc.nodes + n;
+  F8 ax = ldg8(np), ay = ldg8(np + 2), az = ldg8(np + 4);
+  float4 cr = ldg4(np + 6);
+  const bool sx = rt.nx & 1u, sy = rt.ny & 1u, sz = rt.nz & 1u;
+  float4 nrx = sx ? ax.b : ax.a, frx = sx ? ax.a : ax.b, nry = sy ? ay.b : ay.a, fry = sy ? ay.a : ay.b,
+         nrz = sz ? az.b : az.a, frz = sz ? az.a : az.b;
+#else
   const unsigned fxr = FAR_ROW_REGS ? rt.fxr : rt.nx ^ 1u, fyr = FAR_ROW_REGS ? rt.fyr : rt.ny ^ 1u,
                  fzr = FAR_ROW_REGS ? rt.fzr : rt.nz ^ 1u;
   float4 nrx = ldg4(sc.nodes + (n + rt.nx)), frx = ldg4(sc.nodes + (n + fxr)),
          nry = ldg4(sc.nodes + (n + rt.ny)), fry = ldg4(sc.nodes + (n + fyr)),
          nrz = ldg4(sc.nodes + (n + rt.nz)), frz = ldg4(sc.nodes + (n + fzr)), cr = ldg4(sc.nodes + (n + 6u));
+#endif
   float tn[4];
   int cref[4] = {f2i(cr.x), f2i(cr.y), f2i(cr.z), f2i(cr.w)};
   const float nx[4] = {nrx.x, nrx.y, nrx.z, nrx.w}, fx[4] = {frx.x, frx.y, frx.z, frx.w};

@@ -52,6 +52,17 @@ FLOPS_PER_SEGMENT = 20.0 * NODE_TESTS_PER_SEGMENT + 30.0 * SPHERE_TESTS_PER_SEGM
 LUM = (0.2126, 0.7152, 0.0722)
 
 
+def workload_config():
+    """`config` of the JSON line: the SAME object from both arms (ours and --impl reference) and for every N, so that
+    the two lines can be compared key by key; what differs between the arms and with N is in `run`."""
+    return {"workload": "spheres scene (BASELINE config 2: 485 objects, seed 1234) 1920x1080, 1 spp per frame, depth 8, "
+                        "dynamic-mode (progressive) frames",
+            "scene": "spheres", "objects": 485, "width": WIDTH, "height": int(WIDTH / (16.0 / 9.0)), "spp_per_frame": 1,
+            "max_depth": DEPTH, "paths_per_frame": WIDTH * int(WIDTH / (16.0 / 9.0)),
+            "l2": "GPU arm: 192 MiB buffer written before every timed step (outside the step's CUDA-event pair); "
+                  "CPU reference arm: not applicable"}
+
+
 class ClockSampler(threading.Thread):
     """SM clock and throttle reasons during the timed region, through NVML (the same counters nvidia-smi's
     clocks.sm / clocks_event_reasons.* columns print, B200_PROFILING.md), sampled every 2 ms."""
@@ -195,8 +206,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mpath-samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": WIDTH * height / value / 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "spheres scene (485 objects, seed 1234) 1920x1080, 1 spp per frame, depth 8; "
-                                   "reference CPU path on the host cores"},
+            "config": workload_config(),
+            "run": {"what": "the reference's CPU path (oracle/_ref, unmodified sources) on the host cores, one full frame per step"},
             "cpu_baseline": dict(desc, value=value, unit="Mpath-samples/s"),
             "e2e": {"value": value, "unit": "Mpath-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": elapsed}
@@ -459,15 +470,14 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "Mpath-samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {
-                "workload": f"spheres scene (485 objects, seed 1234) 1920x1080, depth 8, dynamic-mode frames: "
-                            f"{strata_per_step} stratum/strata of the whole frame per step (= 1 per GPU), "
-                            f"{TILE_ROWS}-scanline tiles interleaved over {world} GPU(s), scene replicated; every step ends with "
-                            f"the displayed frame: each rank's to_byte tiles stored into rank 0's row-major RGB8 frame "
-                            f"(NVLink peer stores through CUDA IPC + arrival flags; no collective)",
+            "config": workload_config(),
+            "run": {
+                "what": f"{strata_per_step} stratum/strata of the whole frame per step (= 1 per GPU), "
+                        f"{TILE_ROWS}-scanline tiles interleaved over {world} GPU(s), scene replicated; every step ends with "
+                        f"the displayed frame: each rank's to_byte tiles stored into rank 0's row-major RGB8 frame "
+                        f"(NVLink peer stores through CUDA IPC + arrival flags; no collective); two frames alternate",
                 "paths_per_step": paths_per_step, "segments_per_path": counters.segments / max(1, counters.paths),
-                "bvh": {"primitives": info.n_prims, "nodes4": info.n_nodes, "device_build_ms": info.build_ms},
-                "l2": "192 MiB buffer written before every timed step (outside the step's CUDA-event pair)"},
+                "bvh": {"primitives": info.n_prims, "nodes4": info.n_nodes, "device_build_ms": info.build_ms}},
             "frame_ms": ms_step / strata_per_step,
             "e2e": {"value": e2e_value, "unit": "Mpath-samples/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": C.sizeof(abi.rt_camera), "d2h_bytes_per_step": npix * 3,

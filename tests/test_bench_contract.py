@@ -28,7 +28,8 @@ def test_reference_arm_runs_the_cpu_implementation():
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["e2e"]["value"] == d["value"] == d["cpu_baseline"]["value"]
-    assert "workload" in d["config"]
+    import bench
+    assert d["config"] == bench.workload_config()  # the same object our arm prints: the two lines compare key by key
 
 
 @pytest.mark.gpu
@@ -49,4 +50,6 @@ def test_our_arm_reports_every_contract_key():
     c = d["cpu_baseline"]
     assert c["value"] > 0 and c["cores"] >= 1 and c["kind"] in ("reference", "port") and c["sample"]
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
-    assert "workload" in d["config"] and "model" not in d["config"]
+    import bench
+    assert d["config"] == bench.workload_config() and "model" not in d["config"]
+    assert d["run"]["paths_per_step"] == 1920 * 1080

@@ -271,7 +271,8 @@ typedef struct rt_scene_info {
   double bounds_min[3];
   double bounds_max[3];
   int32_t builder;       /* RT_BUILDER_*: the tree that was kept */
-  int32_t pad_;
+  int32_t depth;         /* levels of the 4-wide tree; rt_scene_create keeps 3 * depth within the traversal stack (64
+                          * entries): a device tree deeper than that is rebuilt with the host SAH builder */
 } rt_scene_info;
 int rt_scene_get_info(rt_scene *scene, rt_scene_info *out);
 

@@ -21,8 +21,15 @@
 
 namespace rtsah {
 
+// Set (per thread) by rt_scene_build while it rebuilds a scene whose device tree came out deeper than the traversal
+// stack allows: the host SAH builder splits at the spatial / object median when its sweep finds nothing better, so its
+// trees stay shallow where a radix tree over clustered Morton codes does not.
+inline thread_local bool g_force_sah = false;
+
 // RT_BVH=lbvh / ploc / sah force one builder (A/B runs and the tests of every path).
 inline bool use_sah(int n) {
+  if (g_force_sah)
+    return n >= 2;
   const char *e = std::getenv("RT_BVH");
   if (e && (!std::strcmp(e, "lbvh") || !std::strcmp(e, "ploc")))
     return false;
@@ -35,6 +42,8 @@ inline bool use_sah(int n) {
 // segment and still renders 3 % slower (more of the expensive medium leaves are reached), and on the uniform
 // sphere fields it visits 7 % MORE nodes than the radix tree, whose Morton splits are spatial medians of the grid.
 inline bool use_ploc(int n) {
+  if (g_force_sah)
+    return false;
   const char *e = std::getenv("RT_BVH");
   return e && !std::strcmp(e, "ploc") && n >= 2;
 }

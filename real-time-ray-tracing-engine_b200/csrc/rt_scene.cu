@@ -19,6 +19,7 @@
 
 #include <chrono>
 #include <mutex>
+#include <string>
 #include <thread>
 
 using namespace rtflat;
@@ -51,7 +52,7 @@ struct Scratch { // frees build scratch on every exit path
 
 } // namespace
 
-int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
+static int scene_build_once(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
   // RT_BUILD_TIMING=1: wall-clock phases of the call on stderr (where scene creation time goes)
   static const bool timing = std::getenv("RT_BUILD_TIMING") != nullptr;
   auto wall0 = std::chrono::steady_clock::now();
@@ -159,6 +160,7 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
       order[0] = 0;
     }
     sc->info.build_ms = 0.0;
+    sc->info.depth = 1;
   } else {
     Scratch scratch;
     BuildBox *d_boxes = nullptr, *d_sorted_boxes = nullptr;
@@ -279,8 +281,9 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
     int counters[2] = {0, 1};
     RT_CUDA(cudaMemcpyAsync(d_items[0], &root, sizeof root, cudaMemcpyHostToDevice, s));
     RT_CUDA(cudaMemcpyAsync(d_counters, counters, sizeof counters, cudaMemcpyHostToDevice, s));
-    int n_items = 1, cur = 0;
+    int n_items = 1, cur = 0, levels = 0;
     while (n_items > 0) {
+      levels++; // one collapse launch per level of the 4-wide tree
       RT_CUDA(cudaMemsetAsync(d_counters, 0, sizeof(int), s)); // next level's queue length
       launch_collapse(s, t, d_sorted_boxes, sc->nodes, d_items[cur], n_items, d_items[cur ^ 1], d_counters,
                       d_counters + 1);
@@ -290,6 +293,7 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
       cur ^= 1;
     }
     n_wide = counters[1];
+    sc->info.depth = levels;
     RT_CUDA(cudaEventRecord(ev1, s));
     RT_CUDA(cudaEventSynchronize(ev1));
     float ms = 0.f;
@@ -375,6 +379,31 @@ int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
     sc->info.bounds_max[a] = n ? all.hi[a] : 0.0;
   }
   return RT_OK;
+}
+
+// A traversal descends at most `depth` levels of the 4-wide tree and leaves at most three siblings on its stack per
+// level, so 3 x depth <= RT_STACK entries are always enough.  Host SAH trees and radix trees over spread-out scenes are
+// far below that (10^6 spheres: 12 levels); a radix tree over Morton codes that share long prefixes (geometry
+// clustered at many scales) can exceed it, and a dropped push would silently lose geometry - such a scene is rebuilt
+// with the host SAH builder, and refused if even that tree is too deep.
+int rt_scene_build(rt_context *ctx, const rt_scene_desc *desc, rt_scene *sc) {
+  int st = scene_build_once(ctx, desc, sc);
+  if (st != RT_OK || 3 * sc->info.depth <= RT_STACK)
+    return st;
+  const int first_depth = sc->info.depth;
+  if (sc->info.builder != RT_BUILDER_SAH) {
+    cudaStreamSynchronize(ctx->stream);
+    rt_scene_release(sc);
+    *sc = rt_scene();
+    rtsah::g_force_sah = true;
+    st = scene_build_once(ctx, desc, sc);
+    rtsah::g_force_sah = false;
+    if (st != RT_OK || 3 * sc->info.depth <= RT_STACK)
+      return st;
+  }
+  rt_set_error("scene hierarchy too deep for the traversal stack (" + std::to_string(first_depth) + " levels, then " +
+               std::to_string(sc->info.depth) + " with the SAH builder; at most " + std::to_string(RT_STACK / 3) + ")");
+  return RT_ERR_UNSUPPORTED;
 }
 
 // Uploads the FP64 parity records on first use and brings them into leaf order on the device.

@@ -102,7 +102,7 @@ class rt_camera(C.Structure):
 class rt_scene_info(C.Structure):
     _fields_ = [("n_prims", C.c_int64), ("n_nodes", C.c_int64), ("node_bytes", C.c_int64),
                 ("prim_bytes", C.c_int64), ("build_ms", C.c_double), ("bounds_min", d3), ("bounds_max", d3),
-                ("builder", C.c_int32), ("pad_", C.c_int32)]
+                ("builder", C.c_int32), ("depth", C.c_int32)]
 
 
 class rt_ray(C.Structure):

@@ -756,3 +756,61 @@ def test_two_rays_per_lane_extend_renders_the_same_bits():
     repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(repo, "tools", "mux_check.py")], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and r.stdout.strip().endswith("IDENTICAL"), (r.stdout[-800:], r.stderr[-800:])
+
+
+def test_a_tree_deeper_than_the_traversal_stack_is_rebuilt(ctx, oracle, monkeypatch):
+    """A traversal leaves at most three siblings per level on its 64-entry stack, so rt_scene_create keeps
+    3 x depth <= 64.  Geometry clustered at 63 different scales (one sphere per Morton bit) plus 4,096 coincident
+    spheres makes the radix tree a chain more than 70 binary levels deep: the scene must come back built by the host
+    SAH builder (shallow), report its depth, and answer rays exactly like the oracle."""
+    monkeypatch.setenv("RT_BVH", "lbvh")
+    scale, cells = 1024.0, 1 << 21
+    centres = []
+    for j in range(63):  # sphere j: the only one whose Morton key has bit 62 - j set
+        axis, cbit = (62 - j) % 3, (62 - j) // 3
+        c = [0.0, 0.0, 0.0]
+        c[axis] = scale * (1 << cbit) / cells
+        centres.append(c)
+    centres += [[0.0, 0.0, 0.0]] * 4096
+    centres.append([scale, scale, scale])  # pins the upper corner of the centroid bounds
+    n = len(centres)
+    spheres = (abi.rt_sphere * n)()
+    for i, c in enumerate(centres):
+        spheres[i].center0[:] = c
+        spheres[i].radius = scale * 0.2 / cells
+        spheres[i].material, spheres[i].xform, spheres[i].object = 0, -1, i
+    mat = abi.rt_material(type=abi.RT_MAT_LAMBERTIAN, texture=0)
+    tex = abi.rt_texture(type=abi.RT_TEX_SOLID, even=-1, odd=-1, perlin=-1)
+    tex.color[:] = (0.5, 0.5, 0.5)
+    desc = abi.rt_scene_desc(n_spheres=n, n_materials=1, n_textures=1, n_objects=n, spheres=spheres,
+                             materials=C.pointer(mat), textures=C.pointer(tex))
+    scene = engine.Scene(ctx, desc)
+    info = scene.info()
+    assert info.n_prims == n and info.builder == abi.RT_BUILDER_SAH, info.builder  # not the radix tree that was asked for
+    assert 1 <= info.depth and 3 * info.depth <= 64, info.depth
+    monkeypatch.delenv("RT_BVH")
+    plain = engine.Scene(ctx, desc)  # the default policy (SAH at this size) for comparison
+    assert plain.info().builder == abi.RT_BUILDER_SAH and plain.info().depth == info.depth
+    plain.close()
+    # rays at every cluster scale, against the oracle's closest hits
+    rng = np.random.default_rng(5)
+    targets = np.array(centres[:63] + [centres[-1]] + centres[63:67])
+    m = len(targets) * 4
+    rays = (abi.rt_ray * m)()
+    for k in range(m):
+        t = targets[k % len(targets)]
+        o = t + rng.normal(size=3) * scale * 10.0 ** rng.uniform(-6, 0)
+        d = t - o + rng.normal(size=3) * (scale * 0.05 / cells)
+        rays[k].origin[:], rays[k].direction[:] = o.tolist(), d.tolist()
+        rays[k].t_min, rays[k].t_max = 0.001 * scale / cells, float("inf")
+    osc = oracle.ora_scene_create(C.pointer(desc))
+    want = (abi.rt_hit * m)()
+    oracle.ora_trace(osc, rays, m, 1, ol.ORA_RNG_PHILOX, 1, want)
+    a, b = ol.hits_to_numpy(want), ol.hits_to_numpy(scene.trace(rays, abi.RT_TRACE_EXACT_F64, 1))
+    assert (a["prim"] >= 0).mean() > 0.3
+    # the 4,096 coincident spheres tie exactly: compare distances, and primitives outside the tie
+    assert np.array_equal(a["t"], b["t"])
+    distinct = (a["prim"] < 63) | (a["prim"] == n - 1)
+    assert np.array_equal(a["prim"][distinct], b["prim"][distinct])
+    oracle.ora_scene_destroy(osc)
+    scene.close()

@@ -82,7 +82,7 @@ def run_one(args):
         ctx.set_stage_timing(False)
         info = scene.info()
         out = {"lib": lib, "bvh": os.environ.get("RT_BVH", "auto") + ":" + ["none", "sah", "ploc", "lbvh"][info.builder],
-               "build_ms": round(info.build_ms, 2), "scene": name, "ms": round(ms, 4), "min_ms": round(best, 4), "blocking_ms": round(blocking_ms, 4),
+               "build_ms": round(info.build_ms, 2), "depth": info.depth, "scene": name, "ms": round(ms, 4), "min_ms": round(best, 4), "blocking_ms": round(blocking_ms, 4),
                "seg_per_path": round(c.segments / max(1, c.paths), 3),
                "stages": {k: round(st[i] / 10, 4) for i, k in enumerate(["gen", "extend", "shade", "accum", "tail"])}}
         if stats:

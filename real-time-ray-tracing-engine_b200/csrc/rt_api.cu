@@ -213,7 +213,7 @@ int render_pass(rt_scene *scene, const rt_camera *camera, rt_film *film, int fir
   // Sub-passes (rt_internal.h, rt_context::split): a small pass is cut into disjoint path ranges (multiples of a
   // block of 128 paths), each with its own queues and its own block of count / cursor words, launched on forked
   // streams.  The profiling modes bracket or count individual launches on one stream and keep the single sequence.
-  const size_t count_words = 2 * ((size_t)max_depth + 2); // queue lengths + fetch cursors of one launch sequence
+  const size_t count_words = 3 * ((size_t)max_depth + 2); // queue lengths + fetch cursors of the extend / tail and of the shade launches
   int n_split = 1;
   if (ctx->split > 1 && !ctx->timer.enabled && !ctx->audit && !ctx->stats && pp.n_paths >= 65536 &&
       (int64_t)pp.n_paths <= ctx->split_max_paths)

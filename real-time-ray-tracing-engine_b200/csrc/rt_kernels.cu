@@ -618,6 +618,12 @@ __global__ void __launch_bounds__(RT_BLOCK)
 #ifndef RT_SHADE_SORT
 #define RT_SHADE_SORT 0
 #endif
+#ifndef RT_SHADE_DYNAMIC
+#define RT_SHADE_DYNAMIC 1
+#endif
+#if RT_SHADE_SORT && RT_SHADE_DYNAMIC
+#error "RT_SHADE_SORT keeps the static partition: build with -DRT_SHADE_DYNAMIC=0"
+#endif
 // Queue compaction: every warp counts its continuing paths with a ballot, the block adds the counts up in
 // shared memory and reserves the slots of all its warps with ONE atomicAdd on the next queue's length.  All
 // atomics of a launch hit the same address and the L2 serialises them (~0.85 clocks each): one per warp
@@ -629,17 +635,29 @@ __global__ void __launch_bounds__(RT_SHADE_THREADS, RT_SHADE_BLOCKS * RT_BLOCK /
     k_shade(const __grid_constant__ DScene sc, const __grid_constant__ PassParams pp, const float4 *__restrict__ ray_a,
             const float4 *__restrict__ ray_b, const float2 *__restrict__ hit, float4 *__restrict__ next_a,
             float4 *__restrict__ next_b, float2 *__restrict__ next_hit, const float4 *__restrict__ thr,
-            float4 *__restrict__ next_thr, float4 *__restrict__ radiance, unsigned int *__restrict__ counts, int bounce) {
+            float4 *__restrict__ next_thr, float4 *__restrict__ radiance, unsigned int *__restrict__ counts,
+            unsigned int *__restrict__ cursor, int bounce) {
   __shared__ unsigned int s_count[RT_SHADE_WARPS], s_first[RT_SHADE_WARPS];
+  __shared__ unsigned int s_base; // the block's next 256 queue entries (dynamic fetch: RT_SHADE_DYNAMIC)
 #if RT_SHADE_SORT
   __shared__ unsigned int s_sort[8 * RT_SHADE_WARPS];
 #endif
   const int n = (int)counts[bounce];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool last_bounce = bounce + 1 >= pp.max_depth;
+#if RT_SHADE_DYNAMIC
+  // Blocks take their 256 entries from a device-side cursor instead of a fixed stride: iterations differ in cost
+  // (misses are cheap, glass and textures are not), and with a static partition the SMs idled 15-20 % of the launch
+  // waiting for the slowest blocks.  The next fetch rides on the barrier pair the compaction needs anyway.
+  if (threadIdx.x == 0)
+    s_base = atomicAdd(cursor, (unsigned int)RT_SHADE_THREADS);
+  __syncthreads();
+  for (int block_base = (int)s_base; block_base < n;) {
+#else
   const int stride = gridDim.x * blockDim.x;
   // the same trip count for every warp of the block: the loop body has block-wide barriers
   for (int block_base = blockIdx.x * blockDim.x; block_base < n; block_base += stride) {
+#endif
     int q = block_base + (int)threadIdx.x;
     bool active = q < n;
     bool cont = false;
@@ -747,8 +765,15 @@ __global__ void __launch_bounds__(RT_SHADE_THREADS, RT_SHADE_BLOCKS * RT_BLOCK /
       first = __shfl_sync(0xffffffffu, first, 0);
       if (lane < RT_SHADE_WARPS)
         s_first[lane] = first + incl - c;
+#if RT_SHADE_DYNAMIC
+      if (lane == 0)
+        s_base = atomicAdd(cursor, (unsigned int)RT_SHADE_THREADS);
+#endif
     }
     __syncthreads();
+#if RT_SHADE_DYNAMIC
+    block_base = (int)s_base; // read by every thread before warp 0 can rewrite it behind the next iteration's first barrier
+#endif
     if (cont) {
       unsigned int slot = s_first[warp] + (unsigned int)__popc(mask & ((1u << lane) - 1u));
       next_a[slot] = make_float4(res.next.o.x, res.next.o.y, res.next.o.z, res.next.time);
@@ -1639,9 +1664,10 @@ void launch_shade(const rt_context *ctx, const DScene &sc, const PassParams &pp,
   int need = ceil_div(pp.n_paths, RT_SHADE_THREADS);
   int b = bounce & 1, nb = b ^ 1;
   auto kernel = gen ? k_shade<true> : k_shade<false>;
+  unsigned int *cursor = w.counts + 2 * (pp.max_depth + 2) + bounce; // third block of the count words: shade fetch cursors
   kernel<<<need < sh.blocks ? need : sh.blocks, RT_SHADE_THREADS, 0, ctx->pass_stream>>>(
       sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b], w.ray_a[nb], w.ray_b[nb], w.hit[nb], w.thr[b], w.thr[nb], w.radiance, w.counts,
-      bounce);
+      cursor, bounce);
 }
 
 void launch_tail(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int first_bounce,

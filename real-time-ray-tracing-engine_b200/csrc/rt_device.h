@@ -390,9 +390,9 @@ RT_HD bool sphere_hit(float4 r0, float4 r1, const Ray &ray, float tmin, float tm
     return false;
   float sq = prim_sqrt<FAST>(disc);
   float root = (h - sq) * inv_a;
-  if (!(tmin < root && root < tmax)) {
+  if (!(tmin < root && root <= tmax)) { // closed at tmax: ties are decided by leaf_test, not by the order of the tests
     root = (h + sq) * inv_a;
-    if (!(tmin < root && root < tmax))
+    if (!(tmin < root && root <= tmax))
       return false;
   }
   t_out = root;
@@ -417,7 +417,7 @@ RT_HD bool sphere_hit_from_surface(float4 r0, float4 r1, const Ray &ray, float t
   f3 perp = oc - (h * inv_a) * ray.d;
   float disc = a * (radius * radius - dot(perp, perp));
   float root = (h + prim_sqrt<RT_FAST_PRIM != 0>(fmaxf(disc, 0.f))) * inv_a; // on the surface |perp| <= radius up to rounding
-  if (!(tmin < root && root < tmax))
+  if (!(tmin < root && root <= tmax))
     return false;
   t_out = root;
   return true;
@@ -511,6 +511,27 @@ struct RayKey {
 // start_prim: the surface primitive the ray starts on (the previous segment's hit; -1 for camera rays, rays
 // scattered inside a medium and the parity hook).  A flat primitive cannot be met again, a sphere only at its
 // far root (sphere_hit_from_surface).
+// Is a hit of primitive `prim` at distance t better than the best so far?  Closer wins; at exactly the same distance
+// (coincident surfaces: the two faces neighbouring boxes share, a quad listed twice) the primitive that comes LATER in
+// the scene description wins - what the reference does for planes, whose interval is closed (Plane.cpp:88, later objects
+// replace earlier ones at equal t) - decided by the unified primitive id stored in the records.  The rule does not
+// depend on the order in which primitives are tested, so every traversal order, every tree builder and a traversal
+// shared between lanes (k_tail) name the same primitive.  Ties are rare: the ids are only fetched when one occurs.
+RT_HD bool tie_wins(const DScene &sc, int prim, int old_prim) {
+  if (old_prim < 0)
+    return true;
+  const int id_new = f2i(ldg4(sc.prims + (size_t)prim * RT_PRIM_F4 + 3).z);
+  const int id_old = f2i(ldg4(sc.prims + (size_t)old_prim * RT_PRIM_F4 + 3).z);
+  return id_new > id_old;
+}
+RT_HD bool closer_hit(const DScene &sc, float t, int prim, const Hit &hit) {
+  return t < hit.t || (t == hit.t && tie_wins(sc, prim, hit.prim));
+}
+// TIES: decide hits at exactly the same distance by closer_hit's order-independent rule (needed where a traversal is
+// shared between lanes: k_tail<.., SHARE>, and then in every kernel that traces the same scene).  Without it the last
+// primitive TESTED at that distance wins, which depends on the traversal order - as it does in the reference.  The
+// rule costs 2 % of the traversal kernels (measured), so scenes that do not need it run without.
+template <bool TIES = false>
 RT_HD void leaf_test(const DScene &sc, int prim, const Ray &ray, float tmin, Hit &hit, int start_prim,
                      const RayKey &key) {
   RT_STAT_LEAF();
@@ -540,9 +561,14 @@ RT_HD void leaf_test(const DScene &sc, int prim, const Ray &ray, float tmin, Hit
                                  (uint32_t)(RT_STREAM_MEDIUM0 + f2i(r0.w)), 0);
     ok = medium_hit(sc, r0, ray, tmin, hit.t, u.x, t);
   }
+  // the closest hit (the tests accept t <= hit.t); a tie is decided by closer_hit's order-independent rule
   if (ok) {
-    hit.t = t;
-    hit.prim = prim;
+    if (TIES && __builtin_expect(t == hit.t, 0))
+      ok = tie_wins(sc, prim, hit.prim);
+    if (ok) {
+      hit.t = t;
+      hit.prim = prim;
+    }
   }
 }
 
@@ -709,7 +735,7 @@ template <class Stack> RT_HD bool stack_pop(Stack &stack, int &sp, float tmax, i
   return false;
 }
 
-template <class Stack>
+template <class Stack, bool TIES = false>
 RT_HD void traverse(const DScene &sc, const Ray &ray, float tmin, Hit &hit, int skip_prim, const RayKey &key,
                     Stack &stack) {
   RayTrav rt = make_trav(ray.o, ray.d);
@@ -720,7 +746,7 @@ RT_HD void traverse(const DScene &sc, const Ray &ray, float tmin, Hit &hit, int 
       if (node_visit(sc, ref, rt, tmin, hit.t, stack, sp, ref))
         continue;
     } else {
-      leaf_test(sc, ~ref, ray, tmin, hit, skip_prim, key);
+      leaf_test<TIES>(sc, ~ref, ray, tmin, hit, skip_prim, key);
     }
     if (!stack_pop(stack, sp, hit.t, ref))
       return;

@@ -24,6 +24,21 @@
 #define RT_BLOCK 128
 #define RT_STACK_SMEM 8
 
+#ifndef RT_TAIL_SHARE_MIN_PRIMS
+#define RT_TAIL_SHARE_MIN_PRIMS 32768 // end-game sharing in k_tail from this many primitives on (0: always, -1: never)
+#endif
+// Scenes whose longest traversals can hold a launch up get k_tail's end-game sharing - and with it leaf_test's
+// order-independent tie rule in every kernel that traces them.  RT_TAIL_SHARE=0 / 1 forces both off / on; 2 = the tie
+// rule without the sharing (what a shared traversal must reproduce bit for bit: tools/env_check.py).
+static int rt_share_mode(const DScene &sc) {
+  static const int share_env = getenv("RT_TAIL_SHARE") ? atoi(getenv("RT_TAIL_SHARE")) : -1;
+  if (share_env >= 0)
+    return share_env;
+  return RT_TAIL_SHARE_MIN_PRIMS >= 0 && sc.n_prims >= RT_TAIL_SHARE_MIN_PRIMS ? 1 : 0;
+}
+static bool rt_scene_tie_rule(const DScene &sc) { return rt_share_mode(sc) != 0; }
+static bool rt_scene_shares_traversals(const DScene &sc) { return rt_share_mode(sc) == 1; }
+
 LaunchShape rt_persistent_shape(const rt_context *ctx, int threads, int blocks_per_sm) {
   LaunchShape s;
   s.threads = threads;
@@ -74,6 +89,15 @@ struct SmemStack {
       ref = spill[i - RT_STACK_SMEM].ref;
       t = spill[i - RT_STACK_SMEM].t;
     }
+  }
+  // entry i (< RT_STACK_SMEM) of the column `lane_offset` threads away (another lane of the same warp)
+  __device__ __forceinline__ void get_from(int lane_offset, int i, int &ref, float &t) const {
+    int tb;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];"
+                 : "=r"(ref), "=r"(tb)
+                 : "r"(base + (unsigned)(lane_offset * 8) + (unsigned)i * (RT_BLOCK * 8u))
+                 : "memory");
+    t = __int_as_float(tb);
   }
 };
 #define RT_DECLARE_STACK(stack)                                                                              \
@@ -191,7 +215,7 @@ __device__ __forceinline__ void traversal_stats(unsigned long long *stats, unsig
 #endif
 __shared__ float4 rt_ray_smem_a[RT_BLOCK], rt_ray_smem_b[RT_BLOCK];
 
-template <bool STATS, bool GEN>
+template <bool STATS, bool GEN, bool TIES>
 __global__ void __launch_bounds__(RT_BLOCK, 8)
     k_extend(const __grid_constant__ DScene sc, const __grid_constant__ PassParams pp,
              const float4 *__restrict__ ray_a, const float4 *__restrict__ ray_b, float2 *__restrict__ hit,
@@ -296,7 +320,7 @@ __global__ void __launch_bounds__(RT_BLOCK, 8)
         do {
           if (STATS)
             n_tests++;
-          leaf_test(sc, ~ref, r, RT_T_MIN, best, skip, key);
+          leaf_test<TIES>(sc, ~ref, r, RT_T_MIN, best, skip, key);
           if (!stack_pop(stack, sp, best.t, ref))
             ref = RT_DONE;
         } while (ref < 0);
@@ -808,7 +832,9 @@ __device__ __noinline__ bool shade_segment_call(const DScene &sc, const Ray &ray
 #define shade_segment_call shade_segment
 #endif
 
-template <bool STATS>
+// SHARE: end-game sharing of long traversals between the lanes of a warp (below); the launch wrapper turns it on for
+// scenes whose stragglers matter (rt_kernels.cu launch_tail), the others run the instantiation without its bookkeeping.
+template <bool STATS, bool SHARE, bool TIES>
 __global__ void __launch_bounds__(RT_BLOCK, RT_TAIL_BLOCKS)
     k_tail(const __grid_constant__ DScene sc, const __grid_constant__ PassParams pp, float4 *__restrict__ ray_a,
            float4 *__restrict__ ray_b, float2 *__restrict__ hit, float4 *__restrict__ next_a,
@@ -828,8 +854,81 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_TAIL_BLOCKS)
   bool exhausted = false;
   best.t = -1.0f; // no segment held
   best.prim = -1;
+  // End-game sharing (below): `owner` = the lane whose segment this lane is tracing (itself, or the lane it helps),
+  // `helpers` = how many lanes are still tracing subtrees of this lane's own segment.  (Dead without SHARE.)
+  int owner = (int)lane, helpers = 0;
 
   for (;;) {
+    // ---- end-game sharing: once the queue is empty, a warp's last long traversals would run on one lane each while
+    // the other lanes - and soon most of the GPU - idle (10^6 spheres: the SMs were active 72 % of the launch).  A
+    // lane without work takes one pending subtree (a stack entry) of the busiest lane and traces it with that lane's
+    // ray; results come back through shuffles and are merged with leaf_test's order-independent rule, so the answer
+    // does not depend on who traced what.
+    if (SHARE) {
+      // helpers that are done hand their result to the owner and become free lanes
+      // (a helper that has given subtrees away itself waits for those first)
+      unsigned int done_helpers = __ballot_sync(0xffffffffu, owner != (int)lane && ref == RT_DONE && helpers == 0);
+      while (done_helpers) {
+        const int h = __ffs(done_helpers) - 1;
+        done_helpers &= done_helpers - 1;
+        const int o = __shfl_sync(0xffffffffu, owner, h);
+        const float ht = __shfl_sync(0xffffffffu, best.t, h);
+        const int hp = __shfl_sync(0xffffffffu, best.prim, h);
+        if ((int)lane == o) {
+          helpers--;
+          if (hp >= 0 && hp != best.prim && closer_hit(sc, ht, hp, best)) {
+            best.t = ht;
+            best.prim = hp;
+          }
+        }
+        if ((int)lane == h) {
+          owner = (int)lane;
+          best.t = -1.0f;
+          best.prim = -1;
+        }
+      }
+      if (exhausted) {
+        const unsigned int free_lanes = __ballot_sync(0xffffffffu, ref == RT_DONE && best.t == -1.0f);
+        // the donor: the lane with the most pending subtrees, all of them in the shared-memory part of its stack
+        const int key = (ref != RT_DONE && sp >= 1 && sp <= RT_STACK_SMEM) ? ((sp << 5) | (int)lane) : -1;
+        const int top = __reduce_max_sync(0xffffffffu, key);
+        if (free_lanes && top >= 0) {
+          const int donor = top & 31, dsp = top >> 5;
+          const int n_free = __popc(free_lanes);
+          const int k = n_free < dsp ? n_free : dsp;
+          const int rank = __popc(free_lanes & lt_mask);
+          const bool take = ((free_lanes >> lane) & 1u) && rank < k;
+          __syncwarp(); // the donor's pushes are visible to the lanes that read its column
+          // the donor's ray, interval and identity
+          const float ix = __shfl_sync(0xffffffffu, rt.inv.x, donor), iy = __shfl_sync(0xffffffffu, rt.inv.y, donor),
+                      iz = __shfl_sync(0xffffffffu, rt.inv.z, donor), ox = __shfl_sync(0xffffffffu, rt.oi.x, donor),
+                      oy = __shfl_sync(0xffffffffu, rt.oi.y, donor), oz = __shfl_sync(0xffffffffu, rt.oi.z, donor);
+          const float dt = __shfl_sync(0xffffffffu, best.t, donor);
+          const int dp = __shfl_sync(0xffffffffu, best.prim, donor);
+          const unsigned int dq = __shfl_sync(0xffffffffu, q, donor);
+          const int db = __shfl_sync(0xffffffffu, bounce, donor);
+          if (take) {
+            rt = trav_from(F3(ix, iy, iz), F3(ox, oy, oz));
+            best.t = dt;
+            best.prim = dp;
+            q = dq;
+            bounce = db;
+            owner = donor;
+            sp = 0;
+            // entry dsp - 1 - rank of the donor's column (columns are 8 bytes apart, rows 1 KB)
+            int eref;
+            float et;
+            stack.get_from(donor - (int)lane, dsp - 1 - rank, eref, et);
+            ref = et <= best.t ? eref : RT_DONE;
+          }
+          __syncwarp(); // ... and read before the donor pushes over them
+          if ((int)lane == donor) {
+            sp -= k;
+            helpers += k;
+          }
+        }
+      }
+    }
     // ---- fetch: lanes without a path take the next ones of the queue ----
     unsigned int idle = __ballot_sync(0xffffffffu, ref == RT_DONE && best.t == -1.0f);
     if (idle && !exhausted) {
@@ -886,7 +985,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_TAIL_BLOCKS)
         do {
           if (STATS)
             n_tests++;
-          leaf_test(sc, ~ref, r, RT_T_MIN, best, skip, key);
+          leaf_test<TIES>(sc, ~ref, r, RT_T_MIN, best, skip, key); // sharing needs the order-independent tie rule
           if (!stack_pop(stack, sp, best.t, ref))
             ref = RT_DONE;
         } while (ref < 0);
@@ -897,7 +996,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_TAIL_BLOCKS)
     }
 
     // ---- shade the segments whose traversal is complete ----
-    if (ref == RT_DONE && best.t != -1.0f) {
+    if (ref == RT_DONE && best.t != -1.0f && (!SHARE || (owner == (int)lane && helpers == 0))) {
       ray_stats<STATS>(stats, ray_nodes);
       ray_nodes = 0;
       float4 a = ray_a[q], b = ray_b[q];
@@ -1256,6 +1355,7 @@ __global__ void k_scatter_gathered(int width, int height, int n_ranks, int tile_
 // ---------------------------------------------------------------------------------------------------
 // parity hook: FP32 closest hit for explicit rays, through the same traverse() as k_extend
 // ---------------------------------------------------------------------------------------------------
+template <bool TIES>
 __global__ void __launch_bounds__(RT_BLOCK)
     k_trace_fast(const __grid_constant__ DScene sc, const rt_ray *__restrict__ rays, long long n, uint64_t seed,
                  const int *__restrict__ leaf_object, const int *__restrict__ leaf_id, rt_hit *__restrict__ hits) {
@@ -1275,7 +1375,7 @@ __global__ void __launch_bounds__(RT_BLOCK)
     Hit best;
     best.t = (float)in.t_max;
     best.prim = -1;
-    traverse(sc, r, (float)in.t_min, best, -1, key, stack);
+    traverse<SmemStack, TIES>(sc, r, (float)in.t_min, best, -1, key, stack);
     rt_hit out;
     out.t = best.prim >= 0 ? (double)best.t : (double)RT_INF_F;
     out.prim = best.prim >= 0 ? leaf_id[best.prim] : -1;
@@ -1650,8 +1750,11 @@ void launch_extend(const rt_context *ctx, const DScene &sc, const PassParams &pp
                                             w.stats);
     return;
   }
-  auto kernel = gen ? (ctx->stats ? k_extend<true, true> : k_extend<false, true>)
-                    : (ctx->stats ? k_extend<true, false> : k_extend<false, false>);
+  const bool ties = rt_scene_tie_rule(sc); // the tie rule of leaf_test goes with k_tail's end-game sharing
+  auto kernel = ties ? (gen ? (ctx->stats ? k_extend<true, true, true> : k_extend<false, true, true>)
+                            : (ctx->stats ? k_extend<true, false, true> : k_extend<false, false, true>))
+                     : (gen ? (ctx->stats ? k_extend<true, true, false> : k_extend<false, true, false>)
+                            : (ctx->stats ? k_extend<true, false, false> : k_extend<false, false, false>));
   // RT_EXTEND_DYN_SMEM=<bytes>: unused dynamic shared memory per block (experiment aid: how much the kernel
   // depends on the L1 capacity that shared memory is carved out of)
   static const size_t dyn_smem = getenv("RT_EXTEND_DYN_SMEM") ? (size_t)atol(getenv("RT_EXTEND_DYN_SMEM")) : 0;
@@ -1688,14 +1791,15 @@ void launch_tail(const rt_context *ctx, const DScene &sc, const PassParams &pp, 
                                              sc.n_media > 0, w.stats);
     return;
   }
-  if (ctx->stats)
-    k_tail<true><<<blocks, RT_BLOCK, 0, ctx->pass_stream>>>(sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b], w.ray_a[nb], w.ray_b[nb],
-                                                       w.hit[nb], w.thr[b], w.thr[nb], w.radiance, w.counts, cursor, first_bounce,
-                                                       end_bounce, sc.n_media > 0, w.stats);
-  else
-    k_tail<false><<<blocks, RT_BLOCK, 0, ctx->pass_stream>>>(sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b], w.ray_a[nb], w.ray_b[nb],
-                                                        w.hit[nb], w.thr[b], w.thr[nb], w.radiance, w.counts, cursor, first_bounce,
-                                                        end_bounce, sc.n_media > 0, w.stats);
+  // End-game sharing pays where single traversals get long enough to hold a launch up - large scenes (10^6 spheres:
+  // tail 1.54 -> 1.27 ms) - and costs 2-4 % of the kernel elsewhere (its bookkeeping in a 96-register kernel).
+  // RT_TAIL_SHARE=0 / 1 forces it off / on.
+  const bool share = rt_scene_shares_traversals(sc), ties = rt_scene_tie_rule(sc);
+  auto kernel = ctx->stats ? (share ? k_tail<true, true, true> : (ties ? k_tail<true, false, true> : k_tail<true, false, false>))
+                           : (share ? k_tail<false, true, true> : (ties ? k_tail<false, false, true> : k_tail<false, false, false>));
+  kernel<<<blocks, RT_BLOCK, 0, ctx->pass_stream>>>(sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b], w.ray_a[nb], w.ray_b[nb], w.hit[nb],
+                                                    w.thr[b], w.thr[nb], w.radiance, w.counts, cursor, first_bounce, end_bounce,
+                                                    sc.n_media > 0, w.stats);
 }
 
 void launch_accumulate(const rt_context *ctx, const PassParams &pp, WaveBuffers &w, float4 *film) {
@@ -1740,6 +1844,6 @@ void launch_trace_fast(const rt_context *ctx, const DScene &sc, const rt_ray *d_
     return;
   LaunchShape sh = rt_persistent_shape(ctx, RT_BLOCK, 8);
   int need = ceil_div(n, RT_BLOCK);
-  k_trace_fast<<<need < sh.blocks ? need : sh.blocks, RT_BLOCK, 0, ctx->stream>>>(sc, d_rays, n, seed, leaf_object,
-                                                                                  leaf_id, d_hits);
+  auto kernel = rt_scene_tie_rule(sc) ? k_trace_fast<true> : k_trace_fast<false>;
+  kernel<<<need < sh.blocks ? need : sh.blocks, RT_BLOCK, 0, ctx->stream>>>(sc, d_rays, n, seed, leaf_object, leaf_id, d_hits);
 }

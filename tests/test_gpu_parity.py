@@ -814,3 +814,20 @@ def test_a_tree_deeper_than_the_traversal_stack_is_rebuilt(ctx, oracle, monkeypa
     assert np.array_equal(a["prim"][distinct], b["prim"][distinct])
     oracle.ora_scene_destroy(osc)
     scene.close()
+
+
+def test_shared_end_game_traversals_render_the_same_bits():
+    """k_tail<SHARE>: once the queue is empty, idle lanes trace pending subtrees of the warp's longest traversals and the
+    results are merged with leaf_test's order-independent tie rule.  Who traces what depends on timing; the image must
+    not: five scenes (depth-50 media, coincident box faces, 40 k and 10 k spheres) rendered with the sharing on
+    (RT_TAIL_SHARE=1) equal the same tie rule without sharing (=2) bit for bit, under two schedules; and with the
+    switch off (=0, what scenes below 32,768 primitives run) nothing of it is compiled in."""
+    import subprocess
+    import sys
+    import os
+
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for runs in (["RT_TAIL_SHARE=2", "RT_TAIL_SHARE=1"], ["RT_TAIL_SHARE=2,RT_WAVE_BOUNCES=1", "RT_TAIL_SHARE=1,RT_WAVE_BOUNCES=1"]):
+        r = subprocess.run([sys.executable, os.path.join(repo, "tools", "env_check.py")] + runs, capture_output=True, text=True,
+                           timeout=900)
+        assert r.returncode == 0 and r.stdout.strip().endswith("IDENTICAL"), (r.stdout[-1200:], r.stderr[-800:])

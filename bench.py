@@ -656,9 +656,9 @@ def rmse_leg(ctx):
     engine.render_static(scene, cam, film, 10, 50, 7)
     got = film.read_rgb(1.0 / 100).reshape(cam.image_height, cam.image_width, 3)
     ref_a, secs, cores = reference_render(SCENE, 11, 0, 400, 100, 50, 11)
-    ref_b, _, _ = reference_render(SCENE, 11, 0, 400, 100, 50, 12)
+    ref_b, _, _ = reference_render(SCENE, 11, 0, 400, 100, 50, 100011)  # far from seed 11: thread t is seeded seed + 1 + t
     out = {"config": "BASELINE config 1: spheres scene 400x225, 100 spp, depth 50; reference = oracle/_ref (unmodified reference "
-                     "sources, all host threads), seeds 11 and 12",
+                     "sources, all host threads), seeds 11 and 100011",
            "reference_cpu_s": secs, "reference_cores": cores}
     out.update(image_distance(got, ref_a, ref_b))
     film.close()

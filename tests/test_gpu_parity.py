@@ -642,7 +642,10 @@ def test_at_size_rmse_against_the_reference_render(ctx, host_scenes, cid, name, 
     film.close()
     scene.close()
     ref_a, _, _ = bench.reference_render(name, p0, p1, width, root * root, depth, 11, aspect)
-    ref_b, _, _ = bench.reference_render(name, p0, p1, width, root * root, depth, 12, aspect)
+    # the second seed is far from the first: the harness seeds thread t with seed + 1 + t, and with neighbouring seeds
+    # two renders share 15 of their 16 random streams - now and then the same stream meets the same scanline in both,
+    # the renders agree there and the noise floor comes out up to 12 % too low (seen: ratio 1.13 with seeds 11 / 12)
+    ref_b, _, _ = bench.reference_render(name, p0, p1, width, root * root, depth, 100011, aspect)
     assert ref_a.shape == got.shape
     d = bench.image_distance(got, ref_a, ref_b)
     print(cid, {k: round(v, 5) for k, v in d.items()})

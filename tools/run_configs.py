@@ -145,7 +145,7 @@ def main():
             if rank == 0:
                 ref_a, secs, cores = reference_render("spheres", 11, 400, 100, 50, 11)
                 if ref_a is not None:
-                    ref_b, _, _ = reference_render("spheres", 11, 400, 100, 50, 12)
+                    ref_b, _, _ = reference_render("spheres", 11, 400, 100, 50, 100011)
                     clip = lambda x: np.minimum(x, 4.0)
                     floor = float(np.sqrt(np.mean((clip(ref_a) - clip(ref_b)) ** 2)))
                     rmse = float(np.sqrt(np.mean((clip(img.astype(np.float64)) - clip(ref_a)) ** 2)))

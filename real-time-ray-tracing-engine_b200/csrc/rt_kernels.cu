@@ -20,9 +20,37 @@
 
 #include <cstdlib>
 #include <string>
+#include <utility>
 
 #define RT_BLOCK 128
 #define RT_STACK_SMEM 8
+
+// Programmatic dependent launch (sm_90+), RT_PDL=1: the extend / shade / tail kernels of a pass are launched with the
+// programmatic-serialization attribute, so the next kernel's launch is processed - and its blocks take the SM slots the
+// previous kernel's blocks free - while the previous kernel still runs its last rays; every kernel waits for its
+// predecessor's completion (and memory) before it touches anything, and lets its successor start launching at once.
+// Measured on B200 inside the pass graph (profiles/r02_experiments.md): images identical, frames 0.4-1.2 % SLOWER (the
+// graph already leaves no launch gap to hide, and waiting blocks hold SM slots), so it is off unless asked for.
+__device__ __forceinline__ void rt_pdl_enter() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;");
+}
+template <class... KArgs, class... Args>
+static void rt_launch(void (*kernel)(KArgs...), int blocks, int threads, size_t smem, cudaStream_t stream, bool dependent,
+                      Args &&...args) {
+  static const bool pdl = getenv("RT_PDL") && atoi(getenv("RT_PDL")) != 0;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)blocks);
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && dependent) ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 #ifndef RT_TAIL_SHARE_MIN_PRIMS
 #define RT_TAIL_SHARE_MIN_PRIMS 32768 // end-game sharing in k_tail from this many primitives on (0: always, -1: never)
@@ -148,6 +176,7 @@ __device__ __forceinline__ Ray path_camera_ray(const PassParams &pp, int p) {
 __global__ void __launch_bounds__(RT_BLOCK)
     k_generate(const __grid_constant__ PassParams pp, float4 *__restrict__ ray_a, float4 *__restrict__ ray_b,
                unsigned int *__restrict__ counts) {
+  rt_pdl_enter();
   int stride = gridDim.x * blockDim.x;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < pp.n_paths; p += stride) {
     Ray r = path_camera_ray(pp, pp.path_base + p);
@@ -221,6 +250,7 @@ __global__ void __launch_bounds__(RT_BLOCK, 8)
              const float4 *__restrict__ ray_a, const float4 *__restrict__ ray_b, float2 *__restrict__ hit,
              unsigned int *__restrict__ counts, unsigned int *__restrict__ cursor, int bounce, int has_media,
              unsigned long long *stats) {
+  rt_pdl_enter();
   RT_DECLARE_STACK(stack);
   constexpr bool PARK = GEN || RT_RAY_SMEM;
   const unsigned int n = GEN ? (unsigned int)pp.n_paths : counts[bounce];
@@ -663,6 +693,7 @@ __global__ void __launch_bounds__(RT_SHADE_THREADS, RT_SHADE_BLOCKS * RT_BLOCK /
             unsigned int *__restrict__ cursor, int bounce) {
   __shared__ unsigned int s_count[RT_SHADE_WARPS], s_first[RT_SHADE_WARPS];
   __shared__ unsigned int s_base; // the block's next 256 queue entries (dynamic fetch: RT_SHADE_DYNAMIC)
+  rt_pdl_enter();
 #if RT_SHADE_SORT
   __shared__ unsigned int s_sort[8 * RT_SHADE_WARPS];
 #endif
@@ -842,6 +873,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_TAIL_BLOCKS)
            float4 *__restrict__ next_thr, float4 *__restrict__ radiance, unsigned int *__restrict__ counts,
            unsigned int *__restrict__ cursor,
            int first_bounce, int end_bounce, int has_media, unsigned long long *stats) {
+  rt_pdl_enter();
   RT_DECLARE_STACK(stack);
   const unsigned int n = counts[first_bounce];
   const unsigned int lane = threadIdx.x & 31u;
@@ -1758,8 +1790,8 @@ void launch_extend(const rt_context *ctx, const DScene &sc, const PassParams &pp
   // RT_EXTEND_DYN_SMEM=<bytes>: unused dynamic shared memory per block (experiment aid: how much the kernel
   // depends on the L1 capacity that shared memory is carved out of)
   static const size_t dyn_smem = getenv("RT_EXTEND_DYN_SMEM") ? (size_t)atol(getenv("RT_EXTEND_DYN_SMEM")) : 0;
-  kernel<<<blocks, RT_BLOCK, dyn_smem, ctx->pass_stream>>>(sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b], w.counts, cursor, bounce,
-                                                      sc.n_media > 0, w.stats);
+  rt_launch(kernel, blocks, RT_BLOCK, dyn_smem, ctx->pass_stream, true, sc, pp, (const float4 *)w.ray_a[b], (const float4 *)w.ray_b[b],
+            w.hit[b], w.counts, cursor, bounce, (int)(sc.n_media > 0), w.stats);
 }
 
 void launch_shade(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int bounce, bool gen) {
@@ -1768,9 +1800,9 @@ void launch_shade(const rt_context *ctx, const DScene &sc, const PassParams &pp,
   int b = bounce & 1, nb = b ^ 1;
   auto kernel = gen ? k_shade<true> : k_shade<false>;
   unsigned int *cursor = w.counts + 2 * (pp.max_depth + 2) + bounce; // third block of the count words: shade fetch cursors
-  kernel<<<need < sh.blocks ? need : sh.blocks, RT_SHADE_THREADS, 0, ctx->pass_stream>>>(
-      sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b], w.ray_a[nb], w.ray_b[nb], w.hit[nb], w.thr[b], w.thr[nb], w.radiance, w.counts,
-      cursor, bounce);
+  rt_launch(kernel, need < sh.blocks ? need : sh.blocks, RT_SHADE_THREADS, 0, ctx->pass_stream, true, sc, pp,
+            (const float4 *)w.ray_a[b], (const float4 *)w.ray_b[b], (const float2 *)w.hit[b], w.ray_a[nb], w.ray_b[nb], w.hit[nb],
+            (const float4 *)w.thr[b], w.thr[nb], w.radiance, w.counts, cursor, bounce);
 }
 
 void launch_tail(const rt_context *ctx, const DScene &sc, const PassParams &pp, WaveBuffers &w, int first_bounce,
@@ -1797,9 +1829,8 @@ void launch_tail(const rt_context *ctx, const DScene &sc, const PassParams &pp, 
   const bool share = rt_scene_shares_traversals(sc), ties = rt_scene_tie_rule(sc);
   auto kernel = ctx->stats ? (share ? k_tail<true, true, true> : (ties ? k_tail<true, false, true> : k_tail<true, false, false>))
                            : (share ? k_tail<false, true, true> : (ties ? k_tail<false, false, true> : k_tail<false, false, false>));
-  kernel<<<blocks, RT_BLOCK, 0, ctx->pass_stream>>>(sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b], w.ray_a[nb], w.ray_b[nb], w.hit[nb],
-                                                    w.thr[b], w.thr[nb], w.radiance, w.counts, cursor, first_bounce, end_bounce,
-                                                    sc.n_media > 0, w.stats);
+  rt_launch(kernel, blocks, RT_BLOCK, 0, ctx->pass_stream, true, sc, pp, w.ray_a[b], w.ray_b[b], w.hit[b], w.ray_a[nb], w.ray_b[nb],
+            w.hit[nb], w.thr[b], w.thr[nb], w.radiance, w.counts, cursor, first_bounce, end_bounce, (int)(sc.n_media > 0), w.stats);
 }
 
 void launch_accumulate(const rt_context *ctx, const PassParams &pp, WaveBuffers &w, float4 *film) {

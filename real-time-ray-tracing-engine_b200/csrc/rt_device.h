@@ -724,8 +724,10 @@ RT_HD bool node_visit(const DScene &sc, int node, const RayTrav &rt, float tmin,
 }
 
 // Pops the next stack entry whose entry distance is still inside the interval.
-template <class Stack> RT_HD bool stack_pop(Stack &stack, int &sp, float tmax, int &ref) {
-  while (sp > 0) {
+// `floor`: entries below it are not this traversal's any more (k_tail's end-game sharing hands the oldest - largest -
+// pending subtrees of a long traversal to idle lanes).
+template <class Stack> RT_HD bool stack_pop(Stack &stack, int &sp, float tmax, int &ref, int floor = 0) {
+  while (sp > floor) {
     float t;
     sp--;
     stack.get(sp, ref, t);

@@ -888,7 +888,8 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_TAIL_BLOCKS)
   best.prim = -1;
   // End-game sharing (below): `owner` = the lane whose segment this lane is tracing (itself, or the lane it helps),
   // `helpers` = how many lanes are still tracing subtrees of this lane's own segment.  (Dead without SHARE.)
-  int owner = (int)lane, helpers = 0;
+  // `lo` = floor of this lane's stack: entries below it were handed to helpers.
+  int owner = (int)lane, helpers = 0, lo = 0;
 
   for (;;) {
     // ---- end-game sharing: once the queue is empty, a warp's last long traversals would run on one lane each while
@@ -921,13 +922,16 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_TAIL_BLOCKS)
       }
       if (exhausted) {
         const unsigned int free_lanes = __ballot_sync(0xffffffffu, ref == RT_DONE && best.t == -1.0f);
-        // the donor: the lane with the most pending subtrees, all of them in the shared-memory part of its stack
-        const int key = (ref != RT_DONE && sp >= 1 && sp <= RT_STACK_SMEM) ? ((sp << 5) | (int)lane) : -1;
+        // the donor: the lane with the most pending subtrees in the shared-memory part of its stack; it gives away the
+        // OLDEST ones (pushed nearest to the root: the largest subtrees, and entries that a deep traversal would only
+        // come back to at its very end)
+        const int avail = ref != RT_DONE ? (sp < RT_STACK_SMEM ? sp : RT_STACK_SMEM) - lo : 0;
+        const int key = avail >= 1 ? ((avail << 5) | (int)lane) : -1;
         const int top = __reduce_max_sync(0xffffffffu, key);
         if (free_lanes && top >= 0) {
-          const int donor = top & 31, dsp = top >> 5;
+          const int donor = top & 31, davail = top >> 5;
           const int n_free = __popc(free_lanes);
-          const int k = n_free < dsp ? n_free : dsp;
+          const int k = n_free < davail ? n_free : davail;
           const int rank = __popc(free_lanes & lt_mask);
           const bool take = ((free_lanes >> lane) & 1u) && rank < k;
           __syncwarp(); // the donor's pushes are visible to the lanes that read its column
@@ -939,6 +943,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_TAIL_BLOCKS)
           const int dp = __shfl_sync(0xffffffffu, best.prim, donor);
           const unsigned int dq = __shfl_sync(0xffffffffu, q, donor);
           const int db = __shfl_sync(0xffffffffu, bounce, donor);
+          const int dlo = __shfl_sync(0xffffffffu, lo, donor);
           if (take) {
             rt = trav_from(F3(ix, iy, iz), F3(ox, oy, oz));
             best.t = dt;
@@ -947,15 +952,16 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_TAIL_BLOCKS)
             bounce = db;
             owner = donor;
             sp = 0;
-            // entry dsp - 1 - rank of the donor's column (columns are 8 bytes apart, rows 1 KB)
+            lo = 0;
+            // entry dlo + rank of the donor's column (columns are 8 bytes apart, rows 1 KB)
             int eref;
             float et;
-            stack.get_from(donor - (int)lane, dsp - 1 - rank, eref, et);
+            stack.get_from(donor - (int)lane, dlo + rank, eref, et);
             ref = et <= best.t ? eref : RT_DONE;
           }
           __syncwarp(); // ... and read before the donor pushes over them
           if ((int)lane == donor) {
-            sp -= k;
+            lo += k;
             helpers += k;
           }
         }
@@ -978,6 +984,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_TAIL_BLOCKS)
           best.t = RT_INF_F;
           best.prim = -1;
           sp = 0;
+          lo = 0;
           ref = 0;
           bounce = first_bounce;
           segments++;
@@ -996,7 +1003,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_TAIL_BLOCKS)
           ray_nodes++;
         }
         if (!node_visit(sc, ref, rt, RT_T_MIN, best.t, stack, sp, ref))
-          if (!stack_pop(stack, sp, best.t, ref))
+          if (!stack_pop(stack, sp, best.t, ref, SHARE ? lo : 0))
             ref = RT_DONE;
       }
       if (ref < 0) {
@@ -1018,7 +1025,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_TAIL_BLOCKS)
           if (STATS)
             n_tests++;
           leaf_test<TIES>(sc, ~ref, r, RT_T_MIN, best, skip, key); // sharing needs the order-independent tie rule
-          if (!stack_pop(stack, sp, best.t, ref))
+          if (!stack_pop(stack, sp, best.t, ref, SHARE ? lo : 0))
             ref = RT_DONE;
         } while (ref < 0);
       }
@@ -1061,6 +1068,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_TAIL_BLOCKS)
         best.t = RT_INF_F;
         best.prim = -1;
         sp = 0;
+        lo = 0;
         ref = 0;
         bounce++;
         segments++;

@@ -27,6 +27,8 @@ FULL_METRICS = [
     ("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "ALU pipe active %"),
     ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "FMA pipe active % (FP32 issue)"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),
+    ("sm__cycles_active.avg", "cycles an SM is active, average over the SMs"),
+    ("sm__cycles_elapsed.max", "cycles of the launch (an SM active for fewer is idling at the launch's ends)"),
     ("l1tex__t_sector_hit_rate.pct", "L1 hit rate %"),
     ("l1tex__throughput.avg.pct_of_peak_sustained_active", "L1 throughput % of peak"),
     ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "L1 data pipe (LSU wavefronts) % of peak, over the launch"),

@@ -148,16 +148,25 @@ struct StageSpan {
 // How many bounces run as wavefront launches before k_tail takes the rest.  Every wavefront launch ends with
 // its slowest rays, the tail kernel pays that once, and the larger the scene the longer the slowest rays: measured
 // on 1080p frames of the spheres scene (ms for 1 / 2 / 3 wavefront bounces): 485 primitives 0.681 / 0.657 / 0.657,
-// 4 k 0.896 / 0.865 / 0.873, 16 k 0.968 / 0.965 / 1.020, 65 k 1.33 / 1.39 / 1.60, 10^6 2.15 / 2.70 / 3.50.
-static int wave_depth(const rt_context *ctx, const rt_scene *scene) {
+// 4 k 0.896 / 0.865 / 0.873, 16 k 0.968 / 0.965 / 1.020, 65 k 1.33 / 1.39 / 1.60, 10^6 2.15 / 2.70 / 3.50; with the
+// kernels of the end of round 2: 485 primitives 0.643 / 0.619 / 0.619 / 0.624 (4), 14 k 0.915 / 0.902 / 0.949,
+// 10^6 1.80 / 2.35 / 3.01, Cornell box 0.510 / 0.490 / 0.488 / 0.489.
+// `long_render`: the call is a static render of many samples (>= 32 M paths over the whole image, whatever the number
+// of GPUs: the choice must not depend on the rank count, or the image would).  Its passes are 16 M paths each, the
+// launch ends weigh little, and the wavefront kernels - better lane utilisation than the tail kernel - pay for more
+// bounces: final scene 3840x2160, 256 spp, Mpath-samples/s for 1 / 2 / 3 / 4 / 6 / 8 / 12 wavefront bounces: 1770 /
+// 1884 / 1949 / 1991 / 2032 / 2037 / 2032; Cornell + smoke 1080p 5280 (2) / 5317 / 5366 (4, 6) / 5301 (8); 10^6 spheres
+// 64 spp 99.5 / 97.8 / 100.8 / 104.6 ms.
+static int wave_depth(const rt_context *ctx, const rt_scene *scene, bool long_render) {
   if (ctx->audit) // the audit brackets extend launches; the tail kernel traces inside one launch
     return 1 << 20;
   if (ctx->wave_bounces >= 0)
     return ctx->wave_bounces;
-  // participating media make single rays expensive (boundary tests + free-flight sampling at every candidate):
-  // the 3.4 k-primitive final scene with its two media measures 1.33 / 1.45 / 1.47 ms
-  if (scene->d.n_media > 0 && scene->n_leaf > 2048)
-    return 1;
+  // (Round 1 also sent every scene with participating media above 2,048 primitives to depth 1; that measurement was
+  // distorted by rays with a zero direction component walking the whole tree - rt_device.h, RayTrav.  Re-measured on
+  // the final scene with its two media: 0.893 / 0.872 / 0.883 / 0.899 ms for 1 / 2 / 3 / 4.)
+  if (long_render)
+    return scene->n_leaf > 32768 ? 2 : (scene->n_leaf > 2048 ? 6 : 4);
   return scene->n_leaf > 32768 ? 1 : (scene->n_leaf > 2048 ? 2 : 3);
 }
 
@@ -184,7 +193,7 @@ namespace {
 
 // One wavefront pass over `n_samples` strata starting at linear stratum `first_sample`.
 int render_pass(rt_scene *scene, const rt_camera *camera, rt_film *film, int first_sample, int n_samples,
-                int sqrt_spp, int max_depth, uint64_t seed) {
+                int sqrt_spp, int max_depth, uint64_t seed, bool long_render = false) {
   rt_context *ctx = scene->ctx;
   PassParams pp{};
   pp.cam = to_device_camera(camera);
@@ -237,7 +246,7 @@ int render_pass(rt_scene *scene, const rt_camera *camera, rt_film *film, int fir
   RT_CUDA(cudaMemsetAsync(w.counts, 0, count_words * (size_t)n_split * sizeof(unsigned int), ctx->stream));
   // wavefront launches while the path population is large, then one tail kernel that runs whatever is
   // left to completion (rt_kernels.cu, k_tail)
-  const int wave_bounces = std::min(max_depth, wave_depth(ctx, scene));
+  const int wave_bounces = std::min(max_depth, wave_depth(ctx, scene, long_render));
   // The first extend launch derives the camera rays itself and queue 0 is never written (k_extend<GEN>), unless
   // something else reads queue 0: a tail-only schedule, the parity audit, RT_FUSED_GENERATE=0 (A/B aid).
   const bool fused_generate = wave_bounces >= 1 && !ctx->audit && ctx->fused_generate;
@@ -741,9 +750,11 @@ static int render_strata(rt_scene *scene, const rt_camera *camera, rt_film *film
                          int max_depth, uint64_t seed) {
   const int64_t target_paths = scene->ctx->pass_paths;
   int per_pass = (int)std::max<int64_t>(1, std::min<int64_t>(count, target_paths / std::max<int64_t>(film->n_owned, 1)));
+  // the schedule of a long static render (wave_depth): decided from the whole image, not from this rank's share
+  const bool long_render = (int64_t)count * film->map.width * film->map.height >= ((int64_t)32 << 20);
   for (int s = first; s < first + count; s += per_pass) {
     int n = std::min(per_pass, first + count - s);
-    int st = render_pass(scene, camera, film, s, n, sqrt_spp, max_depth, seed);
+    int st = render_pass(scene, camera, film, s, n, sqrt_spp, max_depth, seed, long_render);
     if (st != RT_OK)
       return st;
     film->samples += n;

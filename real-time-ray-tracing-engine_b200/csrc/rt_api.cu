@@ -490,7 +490,7 @@ int rt_context_create(int device, rt_context **out) {
   if (const char *env = std::getenv("RT_TAIL_SPAN"))
     ctx->tail_span = std::max(1, std::atoi(env));
   if (const char *env = std::getenv("RT_PASS_PATHS"))
-    ctx->pass_paths = std::max<int64_t>(1, std::atoll(env));
+    ctx->pass_paths = ctx->pass_paths_long = std::max<int64_t>(1, std::atoll(env));
   if (const char *env = std::getenv("RT_SPLIT")) // sub-passes of a small pass (1 = one launch sequence)
     ctx->split = std::min(4, std::max(1, std::atoi(env)));
   RT_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -748,10 +748,10 @@ int rt_render_accumulate(rt_scene *scene, const rt_camera *camera, rt_film *film
 // so that the queues stay modest.
 static int render_strata(rt_scene *scene, const rt_camera *camera, rt_film *film, int first, int count, int sqrt_spp,
                          int max_depth, uint64_t seed) {
-  const int64_t target_paths = scene->ctx->pass_paths;
-  int per_pass = (int)std::max<int64_t>(1, std::min<int64_t>(count, target_paths / std::max<int64_t>(film->n_owned, 1)));
   // the schedule of a long static render (wave_depth): decided from the whole image, not from this rank's share
   const bool long_render = (int64_t)count * film->map.width * film->map.height >= ((int64_t)32 << 20);
+  const int64_t target_paths = long_render ? scene->ctx->pass_paths_long : scene->ctx->pass_paths;
+  int per_pass = (int)std::max<int64_t>(1, std::min<int64_t>(count, target_paths / std::max<int64_t>(film->n_owned, 1)));
   for (int s = first; s < first + count; s += per_pass) {
     int n = std::min(per_pass, first + count - s);
     int st = render_pass(scene, camera, film, s, n, sqrt_spp, max_depth, seed, long_render);

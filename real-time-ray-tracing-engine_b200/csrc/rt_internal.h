@@ -97,6 +97,10 @@ struct rt_context {
                            // fastest, even at depth 50; shorter spans chain launches through the queues)
   int64_t pass_paths = (int64_t)16 << 20; // static renders: paths per wavefront pass (queue storage ~110 B per
                                           // path; measured 4 M / 8 M / 16 M / 32 M: 16 M is fastest on C1 and C3)
+  int64_t pass_paths_long = (int64_t)64 << 20; // long static renders (rt_api.cu, wave_depth): with six wavefront bounces
+                                               // larger passes keep paying - final scene 4K, Mpath-samples/s for 8 / 16 /
+                                               // 32 / 64 / 128 M paths per pass: 1903 / 2033 / 2102 / 2139 / 2155 (7 GB of
+                                               // queues at 64 M); RT_PASS_PATHS sets both
   // RT_FUSED_GENERATE=1: the first extend launch derives the camera rays itself and the first shade launch
   // re-derives them (no k_generate launch, queue 0 never written: 64 B per path of queue memory and traffic less).
   // Measured on B200 (profiles/r02_experiments.md): the saved launch (0.025 ms on C2) and traffic are paid back by

@@ -171,9 +171,9 @@ def main():
             cfg = hs.camera_config(1920, root * root, 50)
             cfg.aspect_ratio = 16.0 / 9.0  # BASELINE config 3: 1080p (the scene's native aspect is 1.0)
             cam = engine.camera_from_config(cfg)
-            # warm-up with full-size passes (9 strata >= the 8 of a 16 M-path pass): the queue storage must not grow -
-            # cudaFree + cudaMalloc of ~2 GB, 20 ... 470 ms depending on the box - inside the timed render
-            render(ctx, stream, sc, cam, 3, 50, 1, world, rank)
+            # warm-up with full-size passes (36 strata: a long render, 64 M-path passes): the queue storage must not grow -
+            # cudaFree + cudaMalloc of several GB, 20 ... 470 ms depending on the box - inside the timed render
+            render(ctx, stream, sc, cam, 3 if quick else 6, 50, 1, world, rank)
             ms, img, spp_seg = render(ctx, stream, sc, cam, root, 50, 3, world, rank)
             paths = cam.image_width * cam.image_height * root * root
             emit({"config": f"c3 cornell+smoke {cam.image_width}x{cam.image_height} {root * root}spp depth50 static", "ms": ms,
@@ -199,7 +199,7 @@ def main():
             hs, sc, binfo = load("final", 20, 1000)
             root = 16 if quick else 64
             cam = engine.camera_from_config(hs.camera_config(3840, root * root, 50))
-            render(ctx, stream, sc, cam, 4, 50, 1, world, rank)  # warm-up: 16 strata = full-size passes on up to 8 GPUs
+            render(ctx, stream, sc, cam, 4 if quick else 8, 50, 1, world, rank)  # warm-up: 64 strata = full-size passes on up to 8 GPUs
             ms, img, spp_seg = render(ctx, stream, sc, cam, root, 50, 9, world, rank)
             paths = cam.image_width * cam.image_height * root * root
             emit({"config": f"c5 final scene {cam.image_width}x{cam.image_height} {root * root}spp depth50 static, tiles over "

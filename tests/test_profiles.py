@@ -51,6 +51,13 @@ def test_round2_bench_lines_and_scaling_curves():
         assert lines[n]["static_4k"]["frame_sha"] == one["static_4k"]["frame_sha"]
     c5 = {n: json.load(open(os.path.join(PROFILES, f"r02_c5_n{n}.json")))["ms"] for n in (1, 2, 4, 8)}
     assert c5[1] / c5[8] > 0.95 * 8
+    # the round's last build (larger passes for long static renders): same pictures, less time
+    last = json.load(open(os.path.join(PROFILES, "r02_bench_n1_final.json")))
+    assert last["static_4k"]["frame_sha"] == one["static_4k"]["frame_sha"] and last["static_4k"]["ms"] < one["static_4k"]["ms"]
+    assert last["value"] > 0.98 * one["value"] and last["rmse"]["ratio"] <= 1.15
+    c5_last = {n: json.load(open(os.path.join(PROFILES, f"r02_c5_n{n}_final.json"))) for n in (1, 2)}
+    assert c5_last[1]["ms"] < c5[1] and c5_last[1]["ms"] / c5_last[2]["ms"] > 0.95 * 2
+    assert c5_last[1]["mean_luminance"] == c5_last[2]["mean_luminance"]
 
 
 def test_launch_list_summary_can_be_regenerated(tmp_path):

@@ -32,6 +32,21 @@ def test_reference_arm_runs_the_cpu_implementation():
     assert d["config"] == bench.workload_config()  # the same object our arm prints: the two lines compare key by key
 
 
+def test_reference_arm_under_torchrun_prints_one_line_from_rank_0():
+    """The driver launches the reference arm like ours (torchrun, one process per GPU): rank 0 alone measures and
+    prints, the other ranks leave with exit code 0 and no output."""
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29583", os.path.join(REPO, "bench.py"),
+                        "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
+    assert d["e2e"]["value"] == d["value"] and d["cpu_baseline"]["value"] == d["value"]
+
+
 @pytest.mark.gpu
 def test_our_arm_reports_every_contract_key():
     d = run_bench(["--steps", "5", "--warmup", "3"])
